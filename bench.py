@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- DCNv3 core fwd+bwd throughput on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A *step* is one forward + one backward of the DCNv3 core over one batch of synthetic tensors of
+BASELINE.json configs[1]: N=16 per GPU, 80x80, C=256, group=16, 3x3, stride 1, pad 1, bf16
+(value~N(0,1), offset~N(0,1) px, mask=softmax(N(0,1)), grad_out~N(0,1), sigma=1).
+Unit of work: one sampled point (n,ho,wo,g,p); a step processes N*Ho*Wo*G*9 = 14,745,600 per GPU.
+
+  value      whole-job sampled-points/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        same metric through the public API with HOST (pinned) buffers: H2D of the four inputs
+             and D2H of the four results inside the timed region
+  roofline   backward pass (the dominant launches), algorithmic bytes / event time vs measured HBM
+  cpu_baseline  the oracle's grid_sample port of dcnv3_core_pytorch on this box's host cores,
+             bounded sample (rank 0, N=1 only)
+
+Multi-GPU: the batch shards over ranks with no data-path collective -> weak scaling.
+`--impl reference` times the reference's CPU path (oracle port; the Python reference cannot travel
+to the GPU box) on the host cores, rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "dcnv3_core_fwd_bwd_sampled_points_per_s"
+UNIT = "sampled-pts/s"
+CFG = dict(N=16, H=80, W=80, C=256, G=16, K=3, stride=1, pad=1, dil=1, sigma=1.0, dtype="bf16")
+WORKLOAD = "DCNv3 core fwd+bwd, N=16/GPU H=W=80 C=256 group=16 k=3 s=1 p=1 bf16 (BASELINE configs[1])"
+ROTATE = 3  # input sets cycled so that a step never finds its inputs in the 126 MB L2
+
+
+def geom():
+    gc = CFG["C"] // CFG["G"]
+    k, s, p, d = CFG["K"], CFG["stride"], CFG["pad"], CFG["dil"]
+    return (k, k, s, s, p, p, d, d, CFG["G"], gc, CFG["sigma"])
+
+
+def points_per_step(n=None):
+    n = CFG["N"] if n is None else n
+    return n * CFG["H"] * CFG["W"] * CFG["G"] * CFG["K"] ** 2
+
+
+def algorithmic_bytes(n=None, s=2):
+    """fwd = s(V+O+3Q), bwd = s(2V+O+6Q) with every tensor touched once."""
+    n = CFG["N"] if n is None else n
+    V = n * CFG["H"] * CFG["W"] * CFG["C"]
+    O = V
+    Q = points_per_step(n)
+    return dict(fwd=s * (V + O + 3 * Q), bwd=s * (2 * V + O + 6 * Q))
+
+
+def make_inputs(n, device, dtype, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    H, W, C, G, P = CFG["H"], CFG["W"], CFG["C"], CFG["G"], CFG["K"] ** 2
+    value = torch.randn(n, H, W, C, generator=g)
+    offset = torch.randn(n, H, W, G * P * 2, generator=g)
+    mask = torch.softmax(torch.randn(n, H, W, G, P, generator=g), -1).reshape(n, H, W, G * P)
+    grad = torch.randn(n, H, W, C, generator=g)
+    return tuple(t.to(dtype).to(device) for t in (value, offset, mask, grad))
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_run(sample_n, repeats):
+    """The reference's CPU path (oracle port of dcnv3_core_pytorch, fp32) on `sample_n` images of
+    the workload; returns best seconds per fwd+bwd and the thread count."""
+    from oracle import dcnv3_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    v, o, m, g = make_inputs(sample_n, "cpu", torch.bfloat16, seed=1234)
+    v, o, m, g = (t.float() for t in (v, o, m, g))     # bf16-rounded values, fp32 arithmetic
+    best = float("inf")
+    for i in range(repeats + 1):                       # first pass is warm-up
+        t0 = time.perf_counter()
+        orc.gridsample_fwd_bwd(v, o, m, g, *geom())
+        dt = time.perf_counter() - t0
+        if i:
+            best = min(best, dt)
+    return best, torch.get_num_threads()
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    sample_n = 2
+    times = []
+    threads = 1
+    for i in range(args.warmup + args.steps):
+        t, threads = cpu_reference_run(sample_n, 1)
+        if i >= args.warmup:
+            times.append(t)
+    total = sum(times)
+    val = points_per_step(sample_n) * len(times) / total
+    sample = (f"{sample_n} of {CFG['N']} images per step (same shape, fp32 arithmetic on bf16-rounded "
+              f"inputs), oracle port of dcnv3_core_pytorch (grid_sample + autograd)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local_rank):
+    import DCNv3  # the drop-in shim (repo root) over libdcnv3_sm100.so; raises if the .so is absent
+    from yolo_somi_b200 import _native
+    _native.load()
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dtype = torch.bfloat16
+    n = CFG["N"]
+    g = geom()
+    sets = [make_inputs(n, dev, dtype, seed=100 * rank + i) for i in range(ROTATE)]
+
+    def step(i):
+        v, o, m, go = sets[i % ROTATE]
+        out = DCNv3.dcnv3_forward(v, o, m, *g, 256)
+        grads = DCNv3.dcnv3_backward(v, o, m, *g, go, 256)
+        return out, grads
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        # per-pass timing (same launches, same rotation) for the roofline object
+        fwd_ms, bwd_ms = [], []
+        for i in range(args.steps):
+            v, o, m, go = sets[i % ROTATE]
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            a.record(); DCNv3.dcnv3_forward(v, o, m, *g, 256)
+            b.record(); DCNv3.dcnv3_backward(v, o, m, *g, go, 256)
+            c.record(); c.synchronize()
+            fwd_ms.append(a.elapsed_time(b)); bwd_ms.append(b.elapsed_time(c))
+    clocks = clk.summary()
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+
+    # ---- end to end: pinned host buffers in, results back to pinned host buffers
+    host_in = [t.cpu().pin_memory() for t in sets[0]]
+    host_out = None
+    def e2e_step():
+        nonlocal host_out
+        v, o, m, go = (t.to(dev, non_blocking=True) for t in host_in)
+        out = DCNv3.dcnv3_forward(v, o, m, *g, 256)
+        grads = DCNv3.dcnv3_backward(v, o, m, *g, go, 256)
+        res = (out, *grads)
+        if host_out is None:
+            host_out = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in res]
+        for h, t in zip(host_out, res):
+            h.copy_(t, non_blocking=True)
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    h2d = sum(t.numel() * t.element_size() for t in host_in)
+    d2h = sum(t.numel() * t.element_size() for t in host_out)
+
+    if rank != 0:
+        return
+    pts = points_per_step()
+    value = world * pts * args.steps / (ms * 1e-3)
+    ab = algorithmic_bytes()
+    peak, peak_src = peaks()
+    bwd_t = statistics.mean(bwd_ms) * 1e-3
+    fwd_t = statistics.mean(fwd_ms) * 1e-3
+    ach = ab["bwd"] / bwd_t / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "per_gpu_batch": n, "points_per_step_per_gpu": pts,
+                   "l2": f"{ROTATE} rotating input sets (each step's operands ~390 MB > 126 MB L2)",
+                   "arithmetic": "fp32 accumulate, bf16 I/O"},
+        "clocks": clocks,
+        "e2e": {"value": world * pts * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / e2e_steps},
+        "gpu_launches": 3 * args.steps,
+        "roofline": {"bound": "hbm", "kernel": "backward pass (memset + bwd_scatter + narrow)",
+                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes": ab["bwd"], "avg_ms": bwd_t * 1e3},
+        "passes": {"fwd_ms": fwd_t * 1e3, "bwd_ms": bwd_t * 1e3,
+                   "fwd_gbs": ab["fwd"] / fwd_t / 1e9, "fwd_frac": ab["fwd"] / fwd_t / 1e9 / peak,
+                   "step_gbs": (ab["fwd"] + ab["bwd"]) / (ms / args.steps * 1e-3) / 1e9,
+                   "step_frac": (ab["fwd"] + ab["bwd"]) / (ms / args.steps * 1e-3) / 1e9 / peak},
+    }
+    if world == 1 and not args.no_cpu:
+        t, threads = cpu_reference_run(2, 3)
+        line["cpu_baseline"] = {
+            "value": points_per_step(2) / t, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "2 of 16 images (same shape), fp32 on bf16-rounded inputs, best of 3, oracle "
+                      "port of dcnv3_core_pytorch (grid_sample fwd + autograd bwd)"}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the DCNv3 core has no CPU path); "
+                         "use --impl reference for the CPU baseline")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

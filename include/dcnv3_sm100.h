@@ -1,0 +1,104 @@
+/*
+ * dcnv3_sm100.h -- C ABI of libdcnv3_sm100.so: the DCNv3 core (grouped deformable bilinear
+ * sampling x modulation mask, forward + backward) as hand-written sm_100a CUDA kernels.
+ *
+ * This is the drop-in seam for the native extension the reference calls "DCNv3"
+ * (paths relative to the reference tree):
+ *
+ *   dcnv3_forward_sm100   replaces  dcnv3_forward   models/ops_dcnv3/src/dcnv3.h:20-38
+ *                                   -> dcnv3_cuda_forward   src/cuda/dcnv3_cuda.cu:21-85
+ *                                   -> dcnv3_im2col_cuda    src/cuda/dcnv3_im2col_cuda.cuh:841-868
+ *   dcnv3_backward_sm100  replaces  dcnv3_backward  models/ops_dcnv3/src/dcnv3.h:40-59
+ *                                   -> dcnv3_cuda_backward  src/cuda/dcnv3_cuda.cu:87-174
+ *                                   -> dcnv3_col2im_cuda    src/cuda/dcnv3_im2col_cuda.cuh:870-1045
+ *
+ * The reference binds those two through pybind11 (src/vision.cpp:14-17) with at::Tensor
+ * arguments.  Here the boundary is plain C: device pointers, sizes, a dtype tag and a CUDA
+ * stream.  The Python module `DCNv3` (repo root) rebuilds the reference's tensor-level
+ * signatures on top of it, see INTEGRATION.md.
+ *
+ * Contract (same as the reference unless noted)
+ *   - every tensor is dense, channels-last:  value [N,H,W,G*gc], offset [N,Ho,Wo,G*K*2]
+ *     ((dx,dy) per point, point index p = i_w*kernel_h + j_h), mask [N,Ho,Wo,G*K],
+ *     out / grad_out [N,Ho,Wo,G*gc];  Ho = (H + 2*pad_h - (dil_h*(kernel_h-1)+1))/stride_h + 1
+ *     (src/cuda/dcnv3_cuda.cu:40-45), K = kernel_h*kernel_w;
+ *   - all tensors of one call share one dtype (fp32 / fp16 / bf16; the reference has no bf16 and
+ *     also dispatches fp64, which this library rejects);  arithmetic is fp32 for every dtype
+ *     (reference: opmath_t, dcnv3_im2col_cuda.cuh:30);  gradients are produced in the I/O dtype
+ *     (reference: fp32 accumulate then cast, dcnv3_cuda.cu:126-133,168-173);
+ *   - inputs are borrowed, outputs are caller-allocated and fully overwritten: no pre-zeroing
+ *     is needed (the reference zero-fills everything, dcnv3_cuda.cu:55-57,131-133);
+ *   - work is enqueued on `stream`; the call does not synchronise and does not allocate;
+ *   - re-entrant, no global state, no device guard (caller selects the device).
+ *
+ * Return value: 0 on success; a positive value is a cudaError_t from a launch (the reference
+ * only printf()s launch errors, dcnv3_im2col_cuda.cuh:864-867,1041-1044); negative values are the
+ * DCNV3_E_* argument errors below.  dcnv3_sm100_strerror() describes either.
+ */
+#ifndef DCNV3_SM100_H_
+#define DCNV3_SM100_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCNV3_SM100_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DCNV3_API __attribute__((visibility("default")))
+#else
+#define DCNV3_API
+#endif
+
+enum dcnv3_dtype { DCNV3_F32 = 0, DCNV3_F16 = 1, DCNV3_BF16 = 2 };
+
+enum dcnv3_error {
+    DCNV3_OK = 0,
+    DCNV3_E_DTYPE = -1,     /* dtype tag not one of dcnv3_dtype                            */
+    DCNV3_E_SHAPE = -2,     /* non-positive extent / kernel / stride / dilation, or Ho/Wo  */
+                            /* inconsistent with the formula above                         */
+    DCNV3_E_NULL = -3,      /* a required pointer is NULL                                  */
+    DCNV3_E_WORKSPACE = -4, /* workspace smaller than dcnv3_backward_workspace_bytes()     */
+    DCNV3_E_TOO_LARGE = -5, /* a per-image tensor has 2^31 or more elements                */
+    DCNV3_E_ALIGN = -6      /* offset/grad_offset not aligned to 2*sizeof(dtype), or       */
+                            /* workspace not 16-byte aligned                               */
+};
+
+/* flags for dcnv3_backward_sm100 */
+#define DCNV3_BWD_DETERMINISTIC 1u /* bit-reproducible grad_value (fixed-point accumulation) */
+
+DCNV3_API int dcnv3_sm100_abi_version(void);
+DCNV3_API const char *dcnv3_sm100_strerror(int code);
+
+/* out[n,ho,wo,g,c] = sum_p mask_p * bilinear(value[n,:,:,g,c], loc_p)
+ * (reference kernel: dcnv3_im2col_gpu_kernel, dcnv3_im2col_cuda.cuh:216-275). */
+DCNV3_API int dcnv3_forward_sm100(const void *value, const void *offset, const void *mask, void *out,
+                        int N, int H, int W, int Ho, int Wo, int G, int gc,
+                        int kernel_h, int kernel_w, int stride_h, int stride_w,
+                        int pad_h, int pad_w, int dil_h, int dil_w,
+                        float offset_scale, int dtype, void *stream /* cudaStream_t */);
+
+/* Scratch the backward needs (fp32 / fixed-point accumulator for grad_value when the I/O dtype
+ * is 16-bit or the deterministic flag is set); 0 when none is needed. */
+DCNV3_API size_t dcnv3_backward_workspace_bytes(int N, int H, int W, int G, int gc, int dtype,
+                                      unsigned flags);
+
+/* grad_value, grad_offset, grad_mask of the forward above for upstream gradient grad_out
+ * (reference kernels: dcnv3_col2im_*, dcnv3_im2col_cuda.cuh:82-147,278-839).
+ * `workspace` must be device memory of at least dcnv3_backward_workspace_bytes() bytes
+ * (may be NULL when that is 0); its contents need not be initialised. */
+DCNV3_API int dcnv3_backward_sm100(const void *value, const void *offset, const void *mask,
+                         const void *grad_out, void *grad_value, void *grad_offset,
+                         void *grad_mask, void *workspace, size_t workspace_bytes,
+                         int N, int H, int W, int Ho, int Wo, int G, int gc,
+                         int kernel_h, int kernel_w, int stride_h, int stride_w,
+                         int pad_h, int pad_w, int dil_h, int dil_w,
+                         float offset_scale, int dtype, unsigned flags,
+                         void *stream /* cudaStream_t */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCNV3_SM100_H_ */

@@ -1,0 +1,319 @@
+"""GPU parity: the sm_100a DCNv3 core, called through DCNv3Function -> `DCNv3` shim -> C ABI,
+against the oracle (oracle/) and the golden vectors of the real reference (tests/golden/).
+
+Tolerances (BASELINE.json north_star): fp32 1e-5 relative / 1e-6 absolute, bf16/fp16 1e-2 relative;
+the reference's own script uses rtol=1e-2, atol=1e-3 (models/ops_dcnv3/test.py:85,134).
+Because the reference oracle itself carries ~1e-5 absolute fp32 coordinate-rounding error on
+N(0,1) data, fp32 parity is asserted three ways:
+  (a) strict allclose(1e-5, 1e-6) against the reference on the reference script's distribution;
+  (b) strict allclose(1e-5, 1e-6) against the direct-form fp32 oracle (same formula, CPU);
+  (c) error against the fp64 run of the reference no larger than the fp32 reference's own error.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from helpers import allclose_frac, check_inputs_unchanged, golden, max_abs, view_like_golden
+
+pytestmark = pytest.mark.gpu
+
+WHAT = ("out", "gv", "go", "gm")
+TDT = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}
+
+
+def _fn():
+    from yolo_somi_b200.ops_dcnv3.functions import DCNv3Function
+    return DCNv3Function
+
+
+def run_cuda(arrs, geom, dtype=torch.float32, im2col_step=256):
+    """fwd + bwd on the GPU; returns float64 numpy (out, gv, go, gm)."""
+    v, o, m, g = (torch.as_tensor(a).to(device="cuda", dtype=dtype) for a in arrs)
+    v.requires_grad_(True); o.requires_grad_(True); m.requires_grad_(True)
+    out = _fn().apply(v, o, m, *geom, im2col_step)
+    out.backward(g)
+    torch.cuda.synchronize()
+    return tuple(t.detach().double().cpu().numpy() for t in (out, v.grad, o.grad, m.grad))
+
+
+def rounded(arrs, dtype):
+    """Inputs as the low-precision kernel sees them, back in float64."""
+    return tuple(torch.as_tensor(a).to(dtype).double().numpy() for a in arrs)
+
+
+# ----------------------------------------------------------------------------- fp32
+@pytest.mark.parametrize("case", [cases.REFTEST_FWD] + cases.REFTEST_BWD, ids=lambda c: c.name)
+def test_fp32_reference_script_cases_strict(case):
+    """(a): the reference's own cases (test.py: seed-3 distribution, gc in {1,16,30,32,64,71,1025})
+    against the reference's fp32 AND fp64 outputs, at the north-star tolerance."""
+    arrs = check_inputs_unchanged(case)
+    got = run_cuda(arrs, case.geom)
+    for name, a in zip(WHAT, got):
+        for dt in ("f32", "f64"):
+            kind, want, _ = golden(case.name, dt, name)
+            frac = allclose_frac(view_like_golden(kind, a), want, rtol=1e-5, atol=1e-6)
+            assert frac == 0.0, (name, dt, frac, max_abs(view_like_golden(kind, a), want))
+        # and the reference script's own (looser) criterion
+        kind, want, _ = golden(case.name, "f32", name)
+        assert np.allclose(view_like_golden(kind, a), want, rtol=1e-2, atol=1e-3)
+
+
+@pytest.mark.parametrize("case", cases.SWEEP + [cases.CFG1], ids=lambda c: c.name)
+def test_fp32_sweep_vs_direct_oracle_and_reference(case):
+    from oracle import dcnv3_oracle as orc
+    arrs = check_inputs_unchanged(case)
+    got = run_cuda(arrs, case.geom)
+    f32 = [a.astype(np.float32) for a in arrs]
+    d_out = orc.direct_forward(*f32[:3], *case.geom, dtype=np.float32)
+    d_gv, d_go, d_gm = orc.direct_backward(*f32, *case.geom, dtype=np.float32)
+    for name, a, d in zip(WHAT, got, (d_out, d_gv, d_go, d_gm)):
+        # (b) same formula in fp32 on the CPU: only summation order / FMA contraction differ
+        frac = allclose_frac(a, d, rtol=1e-5, atol=1e-5 if name == "go" else 2e-6)
+        assert frac <= (1e-3 if name == "go" else 0.0), (name, frac, max_abs(a, d))
+        # (c) no worse than the reference's own fp32 run, both measured against its fp64 run
+        kind, want64, _ = golden(case.name, "f64", name)
+        _, ref32, _ = golden(case.name, "f32", name)
+        ours = np.abs(view_like_golden(kind, a) - want64)
+        theirs = np.abs(ref32.astype(np.float64) - want64)
+        q = 0.999 if name == "go" else 1.0   # floor() flips at pixel boundaries hit grad_offset
+        assert np.quantile(ours, q) <= max(2.0 * np.quantile(theirs, q), 2e-6), \
+            (name, float(ours.max()), float(theirs.max()))
+        assert np.allclose(view_like_golden(kind, a), ref32, rtol=1e-2, atol=1e-3) or name == "go"
+
+
+# ----------------------------------------------------------------------------- 16-bit
+@pytest.mark.parametrize("dt", ["bf16", "f16"])
+@pytest.mark.parametrize("case", [cases.REFTEST_FWD, cases.REFTEST_BWD[1], cases.REFTEST_BWD[4],
+                                  cases.REFTEST_BWD[5], cases.SWEEP[0], cases.SWEEP[2],
+                                  cases.SWEEP[3], cases.SWEEP[4], cases.CFG1],
+                         ids=lambda c: c.name)
+def test_half_precision_vs_oracle(case, dt):
+    """bf16/fp16: the oracle runs in fp64 on the inputs as rounded to the I/O dtype; 1e-2 relative
+    (north_star) with an absolute floor of 1e-2 x the tensor's RMS for cancellation-heavy sums."""
+    from oracle import dcnv3_oracle as orc
+    arrs = rounded(cases.make_inputs(case), TDT[dt])
+    got = run_cuda(arrs, case.geom, dtype=TDT[dt])
+    out = orc.direct_forward(*arrs[:3], *case.geom)
+    gv, go, gm = orc.direct_backward(*arrs, *case.geom)
+    for name, a, w in zip(WHAT, got, (out, gv, go, gm)):
+        rms = float(np.sqrt(np.mean(w ** 2))) + 1e-30
+        frac = allclose_frac(a, w, rtol=1e-2, atol=1e-2 * rms)
+        assert frac <= (2e-3 if name == "go" else 1e-4), (name, frac, max_abs(a, w), rms)
+
+
+# ----------------------------------------------------------------------------- edge cases
+def test_empty_batch():
+    c = cases.Case("empty", N=0, H=5, W=6, G=2, gc=8)
+    arrs = cases.make_inputs(c)
+    got = run_cuda(arrs, c.geom)
+    assert got[0].shape == (0, 5, 6, 16) and got[1].shape == (0, 5, 6, 16)
+
+
+def test_all_points_outside_gives_zeros():
+    c = cases.Case("outside", N=1, H=6, W=7, G=2, gc=8, seed=9)
+    v, o, m, g = cases.make_inputs(c)
+    o = np.full_like(o, 1000.0)
+    out, gv, go, gm = run_cuda((v, o, m, g), c.geom)
+    assert not out.any() and not gv.any() and not go.any() and not gm.any()
+
+
+def test_output_buffers_need_no_zero_fill():
+    """Every output element is written (the reference zero-fills first, dcnv3_cuda.cu:55-57)."""
+    import DCNv3
+    c = cases.SWEEP[0]
+    v, o, m, g = (torch.as_tensor(a).float().cuda() for a in cases.make_inputs(c))
+    poison = torch.full((64 << 20,), float("nan"), device="cuda"); del poison  # dirty the allocator
+    a = DCNv3.dcnv3_forward(v, o, m, *c.geom, 256)
+    b = DCNv3.dcnv3_backward(v, o, m, *c.geom, g, 256)
+    for t in (a, *b):
+        assert torch.isfinite(t).all()
+
+
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+def test_large_channel_count_and_kat_average_pool(dt):
+    """KAT-1 at a wide layer: zero offsets + uniform mask == 3x3 avg-pool (count_include_pad)."""
+    torch.manual_seed(0)
+    N, H, W, G, gc = 2, 17, 23, 8, 32
+    v = torch.randn(N, H, W, G * gc, device="cuda").to(TDT[dt])
+    o = torch.zeros(N, H, W, G * 18, device="cuda", dtype=TDT[dt])
+    m = torch.full((N, H, W, G * 9), 1.0 / 9, device="cuda", dtype=TDT[dt])
+    out = _fn().apply(v, o, m, 3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0, 256)
+    want = torch.nn.functional.avg_pool2d(v.float().permute(0, 3, 1, 2), 3, 1, 1).permute(0, 2, 3, 1)
+    want = want * (9 * float(m[0, 0, 0, 0]))
+    tol = 2e-6 if dt == "f32" else 2e-2
+    assert float((out.float() - want).abs().max()) <= tol
+
+
+def test_kat_one_hot_shift():
+    """KAT-2: one-hot mask + integer offsets copy a shifted pixel exactly (pins point order)."""
+    torch.manual_seed(1)
+    N, H, W, G, gc, K = 1, 9, 11, 2, 4, 3
+    v = torch.randn(N, H, W, G * gc, device="cuda")
+    for p, dx, dy in [(0, 0, 0), (5, 1, -1), (7, -2, 1), (2, 0, 2)]:
+        o = torch.zeros(N, H, W, G, 9, 2, device="cuda"); o[..., p, 0] = dx; o[..., p, 1] = dy
+        m = torch.zeros(N, H, W, G, 9, device="cuda"); m[..., p] = 1
+        out = _fn().apply(v, o.reshape(N, H, W, -1), m.reshape(N, H, W, -1), K, K, 1, 1, 1, 1, 1, 1, G, gc, 1.0, 256)
+        want = torch.zeros_like(v)
+        sy, sx = (p % K) - 1 + dy, (p // K) - 1 + dx
+        ys = slice(max(0, -sy), min(H, H - sy)); xs = slice(max(0, -sx), min(W, W - sx))
+        yd = slice(ys.start + sy, ys.stop + sy); xd = slice(xs.start + sx, xs.stop + sx)
+        want[:, ys, xs] = v[:, yd, xd]
+        assert torch.equal(out, want), (p, dx, dy)
+
+
+# ----------------------------------------------------------------------------- error behaviour
+def test_error_conditions_match_reference():
+    """dcnv3_cuda.cu:29-53 / dcnv3.h:37 raise RuntimeError; so does the shim, for the same inputs."""
+    import DCNv3
+    c = cases.SWEEP[0]
+    v, o, m, g = (torch.as_tensor(a).float().cuda() for a in cases.make_inputs(c))
+    geom = c.geom
+    with pytest.raises(RuntimeError, match="contiguous"):
+        DCNv3.dcnv3_forward(v.transpose(1, 2), o, m, *geom, 256)
+    with pytest.raises(RuntimeError, match="CPU"):
+        DCNv3.dcnv3_forward(v.cpu(), o.cpu(), m.cpu(), *geom, 256)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        DCNv3.dcnv3_forward(v, o.cpu(), m, *geom, 256)
+    bad = list(geom); bad[8] = c.G + 1
+    with pytest.raises(RuntimeError, match="wont match"):
+        DCNv3.dcnv3_forward(v, o, m, *bad, 256)
+    v3 = torch.cat([v, v[:1]]); o3 = torch.cat([o, o[:1]]); m3 = torch.cat([m, m[:1]])
+    with pytest.raises(RuntimeError, match="must divide"):
+        DCNv3.dcnv3_forward(v3, o3, m3, *geom, 2)         # batch 3, step 2
+    assert DCNv3.dcnv3_forward(v3, o3, m3, *geom, 3).shape[0] == 3
+    with pytest.raises(RuntimeError):
+        DCNv3.dcnv3_forward(v.double(), o.double(), m.double(), *geom, 256)   # documented deviation
+    with pytest.raises(RuntimeError):
+        DCNv3.dcnv3_forward(v, o.half(), m, *geom, 256)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        DCNv3.dcnv3_backward(v, o, m, *geom, g.transpose(1, 2), 256)
+
+
+def test_unaligned_views_are_handled():
+    c = cases.SWEEP[0]
+    arrs = cases.make_inputs(c)
+    want = run_cuda(arrs, c.geom)
+    v, o, m, g = (torch.as_tensor(a).float().cuda() for a in arrs)
+
+    def shifted(t):  # same values, storage offset of one element (4-byte aligned only)
+        buf = torch.empty(t.numel() + 1, device="cuda", dtype=t.dtype)
+        buf[1:].copy_(t.reshape(-1))
+        return buf[1:].view(t.shape)
+    import DCNv3
+    out = DCNv3.dcnv3_forward(shifted(v), shifted(o), shifted(m), *c.geom, 256)
+    assert max_abs(out.double().cpu().numpy(), want[0]) == 0.0
+    gv, go, gm = DCNv3.dcnv3_backward(shifted(v), shifted(o), shifted(m), *c.geom, shifted(g), 256)
+    assert max_abs(go.double().cpu().numpy(), want[2]) == 0.0
+
+
+# ----------------------------------------------------------------------------- deterministic mode
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+def test_deterministic_backward_is_bit_reproducible(dt, monkeypatch):
+    c = cases.Case("det", N=2, H=24, W=20, G=4, gc=16, seed=77)
+    arrs = rounded(cases.make_inputs(c), TDT[dt])
+    base = run_cuda(arrs, c.geom, dtype=TDT[dt])
+    monkeypatch.setenv("DCNV3_DETERMINISTIC", "1")
+    runs = [run_cuda(arrs, c.geom, dtype=TDT[dt]) for _ in range(3)]
+    for r in runs[1:]:
+        for a, b in zip(runs[0], r):
+            assert np.array_equal(a, b)
+    tol = 1e-5 if dt == "f32" else 1e-2
+    for a, b in zip(runs[0], base):
+        assert allclose_frac(a, b, rtol=tol, atol=tol * 0.1 * (np.abs(b).max() + 1e-30)) == 0.0
+
+
+# ----------------------------------------------------------------------------- BASELINE sizes
+def _cfg2(dtype, seed=0, N=16):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    H = W = 80; G = 16; gc = 16
+    v = torch.randn(N, H, W, G * gc, device="cuda", generator=g).to(dtype)
+    o = torch.randn(N, H, W, G * 18, device="cuda", generator=g).to(dtype)
+    m = torch.softmax(torch.randn(N, H, W, G, 9, device="cuda", generator=g), -1).reshape(N, H, W, -1).to(dtype)
+    go = torch.randn(N, H, W, G * gc, device="cuda", generator=g).to(dtype)
+    return v, o, m, go, (3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0)
+
+
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+def test_cfg2_full_size_against_direct_oracle(dt):
+    """BASELINE.json configs[1] (N=16, 80x80, C=256, G=16) in full, vs the C oracle in fp64."""
+    from oracle import dcnv3_oracle as orc
+    v, o, m, go, geom = _cfg2(TDT[dt])
+    arrs = tuple(t.double().cpu().numpy() for t in (v, o, m, go))
+    got = run_cuda(arrs, geom, dtype=TDT[dt])
+    out = orc.direct_forward(*arrs[:3], *geom)
+    gv, goff, gm = orc.direct_backward(*arrs, *geom)
+    rtol = 1e-5 if dt == "f32" else 1e-2
+    for name, a, w in zip(WHAT, got, (out, gv, goff, gm)):
+        rms = float(np.sqrt(np.mean(w ** 2)))
+        frac = allclose_frac(a, w, rtol=rtol, atol=(2e-5 if dt == "f32" else 1e-2) * rms)
+        assert frac <= (1e-4 if name == "go" else 1e-6), (name, frac, max_abs(a, w), rms)
+
+
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+def test_cfg2_size_independent_properties(dt):
+    """Linearity in value and mask, and the adjoint identities <f(v),g> = <v, grad_v> = <m, grad_m>
+    that tie the backward to the forward, at BASELINE.json's full size."""
+    dtype = TDT[dt]
+    v, o, m, go, geom = _cfg2(dtype, seed=1)
+    fn = _fn()
+    f = lambda vv, mm: fn.apply(vv, o, mm, *geom, 256).double()
+    v2 = torch.randn_like(v)
+    tol = 2e-5 if dt == "f32" else 2e-2
+    lhs = f((v.float() * 0.5 + v2.float()).to(dtype), m)
+    rhs = 0.5 * f(v, m) + f(v2, m)
+    scale = float(rhs.abs().max())
+    assert float((lhs - rhs).abs().max()) <= tol * scale
+    vr = v.clone().requires_grad_(True); mr = m.clone().requires_grad_(True)
+    out = fn.apply(vr, o, mr, *geom, 256)
+    out.backward(go)
+    dot_out = float((out.double() * go.double()).sum())
+    dot_v = float((vr.grad.double() * v.double()).sum())
+    dot_m = float((mr.grad.double() * m.double()).sum())
+    ref = float((out.double().abs() * go.double().abs()).sum())
+    assert abs(dot_out - dot_v) <= (1e-6 if dt == "f32" else 2e-3) * ref
+    assert abs(dot_out - dot_m) <= (1e-6 if dt == "f32" else 2e-3) * ref
+
+
+# ----------------------------------------------------------------------------- layer level
+@pytest.mark.parametrize("mc", cases.MODULE_CASES, ids=lambda m: m.name)
+def test_layer_matches_reference_module_golden(mc):
+    """DCNv3 layer (product, CUDA core) vs the reference's DCNv3_pytorch outputs."""
+    from helpers import module_golden
+    from yolo_somi_b200.ops_dcnv3.modules import DCNv3
+    z = module_golden()
+    state_np, x_np, grad_np = cases.make_module_state(mc)
+    mod = DCNv3(channels=mc.channels, kernel_size=mc.kernel_size, stride=mc.stride, pad=mc.pad,
+                dilation=mc.dilation, group=mc.group, offset_scale=mc.offset_scale,
+                center_feature_scale=mc.center_feature_scale)
+    mod.load_state_dict({k: torch.from_numpy(v) for k, v in state_np.items()})
+    mod = mod.cuda()
+    prev = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        x = torch.from_numpy(x_np).cuda().requires_grad_(True)
+        y = mod(x)
+        y.backward(torch.from_numpy(grad_np).cuda())
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+    assert max_abs(y.detach().cpu().numpy(), z[f"{mc.name}/y"]) <= 5e-5
+    assert max_abs(x.grad.cpu().numpy(), z[f"{mc.name}/gx"]) <= 2e-4
+    for k, p in mod.named_parameters():
+        want = z[f"{mc.name}/gp/{k}"]
+        assert max_abs(p.grad.cpu().numpy(), want) <= 3e-4 * max(1.0, float(np.abs(want).max())), k
+
+
+def test_layer_bf16_autocast_runs_and_is_close():
+    from yolo_somi_b200.ops_dcnv3.modules import DCNv3
+    mc = cases.MODULE_CASES[0]
+    state_np, x_np, _ = cases.make_module_state(mc)
+    mod = DCNv3(channels=mc.channels, group=mc.group).cuda()
+    mod.load_state_dict({k: torch.from_numpy(v) for k, v in state_np.items()})
+    x = torch.from_numpy(x_np).cuda()
+    ref = mod(x)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = mod(x)
+    assert y.dtype == torch.bfloat16
+    assert float((y.float() - ref).abs().max()) <= 0.08 * float(ref.abs().max())

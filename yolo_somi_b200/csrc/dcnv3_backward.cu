@@ -1,0 +1,374 @@
+// dcnv3_backward.cu -- DCNv3 core backward for sm_100a.
+//
+// For upstream gradient g = grad_out[n,ho,wo,g,c] and every sampling point p of (n,ho,wo,g):
+//   grad_value[corner_k] += w_k * m * g                                   (scatter, 4 corners)
+//   grad_mask[p]          = sum_c g * (w1 v1 + w2 v2 + w3 v3 + w4 v4)
+//   grad_offset[p].x      = sigma * m * sum_c g * (hh (v2 - v1) + lh (v4 - v3))
+//   grad_offset[p].y      = sigma * m * sum_c g * (hw (v3 - v1) + lw (v4 - v2))
+// (models/ops_dcnv3/src/cuda/dcnv3_im2col_cuda.cuh:82-147; points failing the range test give 0).
+//
+// Replaces the reference's dcnv3_col2im_* family (:278-839), which launches one block of
+// `group_channels` threads per (n,ho,wo,g) (16 threads at C=256/G=16), lets thread 0 add up the
+// per-channel partials serially behind 18 __syncthreads, issues 4 scalar fp32 atomics per
+// (point, channel), and needs zero-filled fp32 gradient buffers plus three cast passes for half
+// (dcnv3_cuda.cu:126-133,168-173).
+//
+// Kernel `bwd_scatter` (this file): one thread owns VEC contiguous channels of one (n,ho,wo,g).
+//   * the channel sums of grad_mask / grad_offset are folded to four per-corner dot products
+//     d_k = sum_c g_c v_k,c in registers, then combined across the gc/VEC lanes of the group with
+//     xor-shuffles; lane 0 of the group writes grad_offset / grad_mask once, in the I/O dtype --
+//     no atomics, no zero-fill, deterministic;
+//   * grad_value contributions leave as 128-bit vector reductions (REDG.E.ADD.F32x4) into an fp32
+//     accumulator: grad_value itself for fp32 I/O, a scratch plane for 16-bit I/O which one cast
+//     pass then narrows;
+//   * DETERMINISTIC mode accumulates grad_value in 64-bit fixed point (integer adds commute, so
+//     the result does not depend on arrival order), scaled by a power of two derived on the device
+//     from max|grad_out|.
+// Kernel `bwd_scatter_warp`: generic fallback (any group_channels, any alignment): one warp per
+// (n,ho,wo,g), lanes stride over channels, full-warp shuffle reduction.
+#include "dcnv3_common.cuh"
+#include "dcnv3_launch.h"
+
+namespace dcnv3 {
+
+constexpr int kBwdThreads = 256;
+constexpr int kFixedBits = 40;  // fixed-point fraction: contributions are scaled to ~2^40 * |g|/max|g|
+
+// ---------------------------------------------------------------------------------------------
+// grad_value accumulators
+struct AccumF32 {
+    float *buf;
+    template <int VEC>
+    __device__ __forceinline__ void add(size_t idx, const float (&c)[VEC]) const {
+        if constexpr (VEC % 4 == 0) {
+#pragma unroll
+            for (int v = 0; v < VEC; v += 4)
+                atomicAdd(reinterpret_cast<float4 *>(buf + idx + v),
+                          make_float4(c[v], c[v + 1], c[v + 2], c[v + 3]));
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) atomicAdd(buf + idx + v, c[v]);
+        }
+    }
+};
+
+struct AccumFixed {
+    unsigned long long *buf;
+    float scale;  // power of two
+    template <int VEC>
+    __device__ __forceinline__ void add(size_t idx, const float (&c)[VEC]) const {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+            atomicAdd(buf + idx + v, (unsigned long long)__float2ll_rn(c[v] * scale));
+    }
+};
+
+// Power-of-two scale for the fixed-point accumulator: 2^(kFixedBits - ceil(log2(amax))).
+__device__ __forceinline__ float fixed_scale(const unsigned *amax_bits) {
+    const float amax = __uint_as_float(*amax_bits);
+    if (!(amax > 0.f) || !isfinite(amax)) return 1.f;
+    int e;
+    frexpf(amax, &e);  // amax = f * 2^e, f in [0.5, 1)
+    return ldexpf(1.f, kFixedBits - e);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+absmax_kernel(const T *__restrict__ x, size_t n, unsigned *__restrict__ out_bits) {
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = fabsf(to_f32(x[i]));
+        m = (v > m && isfinite(v)) ? v : m;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+    // non-negative floats order like their bit patterns; max is order-independent -> deterministic
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+narrow_f32_kernel(const float *__restrict__ src, T *__restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = from_f32<T>(src[i]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+narrow_fixed_kernel(const unsigned long long *__restrict__ src, const unsigned *__restrict__ amax_bits,
+                    T *__restrict__ dst, size_t n) {
+    const double inv = 1.0 / (double)fixed_scale(amax_bits);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = from_f32<T>((float)((double)(long long)src[i] * inv));
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename T, int VEC, int KH, int KW, typename Accum>
+__global__ void __launch_bounds__(kBwdThreads)
+bwd_scatter(const T *__restrict__ value, const T *__restrict__ offset, const T *__restrict__ mask,
+            const T *__restrict__ grad_out, Accum accum, const unsigned *__restrict__ amax_bits,
+            T *__restrict__ grad_offset, T *__restrict__ grad_mask, const Geom q,
+            const long long n_threads, const int vec_per_group) {
+    long long t = (long long)blockIdx.x * kBwdThreads + threadIdx.x;
+    // whole lane-groups are valid or not (n_threads is a multiple of vec_per_group, which divides
+    // 32); invalid lanes still take part in the shuffles but touch no memory
+    const bool live = t < n_threads;
+    if (!live) t = n_threads - 1;
+    const int cv = (int)(t % vec_per_group);
+    const long long pg = t / vec_per_group;
+    const int g = (int)(pg % q.G);
+    const long long pix = pg / q.G;
+    const int wo = (int)(pix % q.Wo);
+    const long long row = pix / q.Wo;
+    const int ho = (int)(row % q.Ho);
+    const int n = (int)(row / q.Ho);
+
+    if constexpr (sizeof(accum.buf[0]) == 8) accum.scale = fixed_scale(amax_bits);
+
+    const int kh = KH ? KH : q.kh, kw = KW ? KW : q.kw;
+    const int P = kh * kw;
+    const int C = q.G * q.gc;
+    const size_t img_base = (size_t)n * q.H * q.W * C + g * q.gc + cv * VEC;
+    const T *img = value + img_base;
+    const T *off = offset + pg * P * 2;
+    const T *msk = mask + pg * P;
+    T *goff = grad_offset + pg * P * 2;
+    T *gmsk = grad_mask + pg * P;
+
+    float go[VEC];
+    ChanVec<T, VEC>::load(grad_out + pg * q.gc + cv * VEC, live, go);
+
+    const float base_w = axis_base(wo, kw, q.sw, q.pw, q.dw, q.sigma);
+    const float base_h = axis_base(ho, kh, q.sh, q.ph, q.dh, q.sigma);
+
+#pragma unroll
+    for (int i = 0; i < kw; ++i) {
+#pragma unroll
+        for (int j = 0; j < kh; ++j) {
+            const int p = i * kh + j;
+            const float2 d = load_pair(off + 2 * p);
+            const float m = to_f32(__ldg(msk + p));
+            const float loc_w = base_w + ((float)(i * q.dw) + d.x) * q.sigma;
+            const float loc_h = base_h + ((float)(j * q.dh) + d.y) * q.sigma;
+            const Tap tp = make_tap(loc_h, loc_w, q.H, q.W);
+
+            float gm = 0.f, gx = 0.f, gy = 0.f;
+            if (tp.inside) {
+                const ptrdiff_t at = ((ptrdiff_t)tp.h0 * q.W + tp.w0) * C;
+                const ptrdiff_t down = (ptrdiff_t)q.W * C;
+                float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
+                ChanVec<T, VEC>::load(img + at, tp.tl, v1);
+                ChanVec<T, VEC>::load(img + at + C, tp.tr, v2);
+                ChanVec<T, VEC>::load(img + at + down, tp.bl, v3);
+                ChanVec<T, VEC>::load(img + at + down + C, tp.br, v4);
+                float d1 = 0.f, d2 = 0.f, d3 = 0.f, d4 = 0.f;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    d1 += go[v] * v1[v];
+                    d2 += go[v] * v2[v];
+                    d3 += go[v] * v3[v];
+                    d4 += go[v] * v4[v];
+                }
+                const float w1 = tp.hh * tp.hw, w2 = tp.hh * tp.lw, w3 = tp.lh * tp.hw, w4 = tp.lh * tp.lw;
+                gm = w1 * d1 + w2 * d2 + w3 * d3 + w4 * d4;
+                gx = m * (tp.hh * (d2 - d1) + tp.lh * (d4 - d3));
+                gy = m * (tp.hw * (d3 - d1) + tp.lw * (d4 - d2));
+                if (live) {
+                    float c[VEC];
+                    if (tp.tl) {
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) c[v] = (w1 * m) * go[v];
+                        accum.template add<VEC>(img_base + at, c);
+                    }
+                    if (tp.tr) {
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) c[v] = (w2 * m) * go[v];
+                        accum.template add<VEC>(img_base + at + C, c);
+                    }
+                    if (tp.bl) {
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) c[v] = (w3 * m) * go[v];
+                        accum.template add<VEC>(img_base + at + down, c);
+                    }
+                    if (tp.br) {
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) c[v] = (w4 * m) * go[v];
+                        accum.template add<VEC>(img_base + at + down + C, c);
+                    }
+                }
+            }
+            // fold the channel sums across the lanes of this (pixel, group)
+            for (int s = vec_per_group >> 1; s > 0; s >>= 1) {
+                gm += __shfl_xor_sync(0xffffffffu, gm, s);
+                gx += __shfl_xor_sync(0xffffffffu, gx, s);
+                gy += __shfl_xor_sync(0xffffffffu, gy, s);
+            }
+            if (live && cv == 0) {
+                store_pair(goff + 2 * p, q.sigma * gx, q.sigma * gy);
+                gmsk[p] = from_f32<T>(gm);
+            }
+        }
+    }
+}
+
+// Generic fallback: one warp per (n,ho,wo,g); lanes stride over the group's channels.
+template <typename T, typename Accum>
+__global__ void __launch_bounds__(kBwdThreads)
+bwd_scatter_warp(const T *__restrict__ value, const T *__restrict__ offset, const T *__restrict__ mask,
+                 const T *__restrict__ grad_out, Accum accum, const unsigned *__restrict__ amax_bits,
+                 T *__restrict__ grad_offset, T *__restrict__ grad_mask, const Geom q,
+                 const long long n_groups) {
+    const long long pg = ((long long)blockIdx.x * kBwdThreads + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (pg >= n_groups) return;  // warp-uniform
+    const int g = (int)(pg % q.G);
+    const long long pix = pg / q.G;
+    const int wo = (int)(pix % q.Wo);
+    const long long row = pix / q.Wo;
+    const int ho = (int)(row % q.Ho);
+    const int n = (int)(row / q.Ho);
+
+    if constexpr (sizeof(accum.buf[0]) == 8) accum.scale = fixed_scale(amax_bits);
+
+    const int P = q.kh * q.kw;
+    const int C = q.G * q.gc;
+    const size_t img_base = (size_t)n * q.H * q.W * C + g * q.gc;
+    const T *img = value + img_base;
+    const T *gout = grad_out + pg * q.gc;
+    const float base_w = axis_base(wo, q.kw, q.sw, q.pw, q.dw, q.sigma);
+    const float base_h = axis_base(ho, q.kh, q.sh, q.ph, q.dh, q.sigma);
+
+    for (int i = 0; i < q.kw; ++i)
+        for (int j = 0; j < q.kh; ++j) {
+            const int p = i * q.kh + j;
+            const float dx = to_f32(__ldg(offset + (pg * P + p) * 2));
+            const float dy = to_f32(__ldg(offset + (pg * P + p) * 2 + 1));
+            const float m = to_f32(__ldg(mask + pg * P + p));
+            const float loc_w = base_w + ((float)(i * q.dw) + dx) * q.sigma;
+            const float loc_h = base_h + ((float)(j * q.dh) + dy) * q.sigma;
+            const Tap tp = make_tap(loc_h, loc_w, q.H, q.W);
+            float gm = 0.f, gx = 0.f, gy = 0.f;
+            if (tp.inside) {  // warp-uniform
+                const ptrdiff_t at = ((ptrdiff_t)tp.h0 * q.W + tp.w0) * C;
+                const ptrdiff_t down = (ptrdiff_t)q.W * C;
+                const float w1 = tp.hh * tp.hw, w2 = tp.hh * tp.lw, w3 = tp.lh * tp.hw, w4 = tp.lh * tp.lw;
+                for (int c = lane; c < q.gc; c += 32) {
+                    const float gc_ = to_f32(__ldg(gout + c));
+                    float v1[1], v2[1], v3[1], v4[1];
+                    ChanVec<T, 1>::load(img + at + c, tp.tl, v1);
+                    ChanVec<T, 1>::load(img + at + C + c, tp.tr, v2);
+                    ChanVec<T, 1>::load(img + at + down + c, tp.bl, v3);
+                    ChanVec<T, 1>::load(img + at + down + C + c, tp.br, v4);
+                    gm += gc_ * (w1 * v1[0] + w2 * v2[0] + w3 * v3[0] + w4 * v4[0]);
+                    gx += gc_ * m * (tp.hh * (v2[0] - v1[0]) + tp.lh * (v4[0] - v3[0]));
+                    gy += gc_ * m * (tp.hw * (v3[0] - v1[0]) + tp.lw * (v4[0] - v2[0]));
+                    float t1[1];
+                    if (tp.tl) { t1[0] = (w1 * m) * gc_; accum.template add<1>(img_base + at + c, t1); }
+                    if (tp.tr) { t1[0] = (w2 * m) * gc_; accum.template add<1>(img_base + at + C + c, t1); }
+                    if (tp.bl) { t1[0] = (w3 * m) * gc_; accum.template add<1>(img_base + at + down + c, t1); }
+                    if (tp.br) { t1[0] = (w4 * m) * gc_; accum.template add<1>(img_base + at + down + C + c, t1); }
+                }
+            }
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) {
+                gm += __shfl_xor_sync(0xffffffffu, gm, s);
+                gx += __shfl_xor_sync(0xffffffffu, gx, s);
+                gy += __shfl_xor_sync(0xffffffffu, gy, s);
+            }
+            if (lane == 0) {
+                grad_offset[(pg * P + p) * 2] = from_f32<T>(q.sigma * gx);
+                grad_offset[(pg * P + p) * 2 + 1] = from_f32<T>(q.sigma * gy);
+                grad_mask[pg * P + p] = from_f32<T>(gm);
+            }
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+static inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+size_t backward_workspace_bytes(const Geom &q, int dtype, unsigned flags) {
+    const size_t plane = (size_t)q.N * q.H * q.W * q.G * q.gc;
+    if (flags & 1u) return kWorkspaceHeader + plane * sizeof(unsigned long long);
+    if (dtype != 0) return kWorkspaceHeader + plane * sizeof(float);
+    return 0;
+}
+
+template <typename T, int VEC, typename Accum>
+static cudaError_t launch_scatter(const T *v, const T *o, const T *m, const T *go, Accum accum,
+                                  const unsigned *amax_bits, T *goff, T *gmsk, const Geom &q,
+                                  bool vec_ok, cudaStream_t stream) {
+    const long long n_groups = (long long)q.N * q.Ho * q.Wo * q.G;
+    if (n_groups == 0) return cudaSuccess;
+    const int vec_per_group = q.gc / VEC;
+    if (vec_ok && q.gc % VEC == 0 && is_pow2(vec_per_group) && vec_per_group <= 32) {
+        const long long n_threads = n_groups * vec_per_group;
+        const long long blocks = (n_threads + kBwdThreads - 1) / kBwdThreads;
+        if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+        if (q.kh == 3 && q.kw == 3)
+            bwd_scatter<T, VEC, 3, 3, Accum><<<(unsigned)blocks, kBwdThreads, 0, stream>>>(
+                v, o, m, go, accum, amax_bits, goff, gmsk, q, n_threads, vec_per_group);
+        else
+            bwd_scatter<T, VEC, 0, 0, Accum><<<(unsigned)blocks, kBwdThreads, 0, stream>>>(
+                v, o, m, go, accum, amax_bits, goff, gmsk, q, n_threads, vec_per_group);
+    } else {
+        const long long blocks = (n_groups * 32 + kBwdThreads - 1) / kBwdThreads;
+        if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+        bwd_scatter_warp<T, Accum><<<(unsigned)blocks, kBwdThreads, 0, stream>>>(
+            v, o, m, go, accum, amax_bits, goff, gmsk, q, n_groups);
+    }
+    return cudaGetLastError();
+}
+
+template <typename T, int VEC>
+static cudaError_t backward_typed(const void *value, const void *offset, const void *mask,
+                                  const void *grad_out, void *grad_value, void *grad_offset,
+                                  void *grad_mask, void *workspace, const Geom &q, unsigned flags,
+                                  cudaStream_t stream) {
+    const T *v = static_cast<const T *>(value), *o = static_cast<const T *>(offset),
+            *m = static_cast<const T *>(mask), *go = static_cast<const T *>(grad_out);
+    T *gv = static_cast<T *>(grad_value), *goff = static_cast<T *>(grad_offset),
+      *gmsk = static_cast<T *>(grad_mask);
+    const size_t plane = (size_t)q.N * q.H * q.W * q.G * q.gc;
+    const size_t n_out = (size_t)q.N * q.Ho * q.Wo * q.G * q.gc;
+    const bool vec_ok = (((uintptr_t)value | (uintptr_t)grad_out | (uintptr_t)grad_value) % 16 == 0) &&
+                        (((uintptr_t)offset | (uintptr_t)grad_offset) % (2 * sizeof(T)) == 0);
+    const int aux_blocks = 148 * 8;
+    cudaError_t err;
+    if (plane == 0) return cudaSuccess;
+
+    if (flags & 1u) {  // deterministic: 64-bit fixed point
+        unsigned *amax_bits = static_cast<unsigned *>(workspace);
+        auto *acc = reinterpret_cast<unsigned long long *>(static_cast<char *>(workspace) + kWorkspaceHeader);
+        if ((err = cudaMemsetAsync(workspace, 0, kWorkspaceHeader + plane * sizeof(unsigned long long), stream)) != cudaSuccess) return err;
+        if (n_out) {
+            absmax_kernel<T><<<aux_blocks, 256, 0, stream>>>(go, n_out, amax_bits);
+            if ((err = cudaGetLastError()) != cudaSuccess) return err;
+        }
+        if ((err = launch_scatter<T, VEC>(v, o, m, go, AccumFixed{acc, 1.f}, amax_bits, goff, gmsk, q, vec_ok, stream)) != cudaSuccess) return err;
+        narrow_fixed_kernel<T><<<aux_blocks, 256, 0, stream>>>(acc, amax_bits, gv, plane);
+        return cudaGetLastError();
+    }
+    if constexpr (sizeof(T) == 4) {  // fp32 I/O: accumulate straight into grad_value
+        if ((err = cudaMemsetAsync(gv, 0, plane * sizeof(float), stream)) != cudaSuccess) return err;
+        return launch_scatter<T, VEC>(v, o, m, go, AccumF32{reinterpret_cast<float *>(gv)}, nullptr, goff, gmsk, q, vec_ok, stream);
+    } else {  // 16-bit I/O: fp32 scratch plane, then one narrowing pass
+        float *acc = reinterpret_cast<float *>(static_cast<char *>(workspace) + kWorkspaceHeader);
+        if ((err = cudaMemsetAsync(acc, 0, plane * sizeof(float), stream)) != cudaSuccess) return err;
+        if ((err = launch_scatter<T, VEC>(v, o, m, go, AccumF32{acc}, nullptr, goff, gmsk, q, vec_ok, stream)) != cudaSuccess) return err;
+        narrow_f32_kernel<T><<<aux_blocks, 256, 0, stream>>>(acc, gv, plane);
+        return cudaGetLastError();
+    }
+}
+
+cudaError_t launch_backward(const void *value, const void *offset, const void *mask,
+                            const void *grad_out, void *grad_value, void *grad_offset,
+                            void *grad_mask, void *workspace, const Geom &q, int dtype,
+                            unsigned flags, cudaStream_t stream) {
+    switch (dtype) {
+    case 0: return backward_typed<float, 4>(value, offset, mask, grad_out, grad_value, grad_offset, grad_mask, workspace, q, flags, stream);
+    case 1: return backward_typed<__half, 8>(value, offset, mask, grad_out, grad_value, grad_offset, grad_mask, workspace, q, flags, stream);
+    default: return backward_typed<__nv_bfloat16, 8>(value, offset, mask, grad_out, grad_value, grad_offset, grad_mask, workspace, q, flags, stream);
+    }
+}
+
+}  // namespace dcnv3
