@@ -29,6 +29,9 @@
 #include "dcnv3_common.cuh"
 #include "dcnv3_launch.h"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace dcnv3 {
 
 constexpr int kBwdThreads = 256;
@@ -103,40 +106,70 @@ narrow_fixed_kernel(const unsigned long long *__restrict__ src, const unsigned *
 }
 
 // ---------------------------------------------------------------------------------------------
-template <typename T, int VEC, int KH, int KW, typename Accum>
+// One thread owns NV 16-byte chunks of one (n,ho,wo,g).  PAIR: lanes 2j/2j+1 swap halves of their
+// fp32 contributions so that every 128-bit reduction instruction covers whole 32-byte sectors
+// (lane 2j sends the even 16-byte pieces of both lanes' contributions, lane 2j+1 the odd ones).
+// Grid: x covers the (ho, wo, g, part) threads of one image (32-bit index math), y = image.
+template <typename T, int NV, int KH, int KW, typename Accum, bool PAIR>
 __global__ void __launch_bounds__(kBwdThreads)
 bwd_scatter(const T *__restrict__ value, const T *__restrict__ offset, const T *__restrict__ mask,
             const T *__restrict__ grad_out, Accum accum, const unsigned *__restrict__ amax_bits,
             T *__restrict__ grad_offset, T *__restrict__ grad_mask, const Geom q,
-            const long long n_threads, const int vec_per_group) {
-    long long t = (long long)blockIdx.x * kBwdThreads + threadIdx.x;
-    // whole lane-groups are valid or not (n_threads is a multiple of vec_per_group, which divides
-    // 32); invalid lanes still take part in the shuffles but touch no memory
-    const bool live = t < n_threads;
-    if (!live) t = n_threads - 1;
-    const int cv = (int)(t % vec_per_group);
-    const long long pg = t / vec_per_group;
-    const int g = (int)(pg % q.G);
-    const long long pix = pg / q.G;
-    const int wo = (int)(pix % q.Wo);
-    const long long row = pix / q.Wo;
-    const int ho = (int)(row % q.Ho);
-    const int n = (int)(row / q.Ho);
+            const unsigned thr_per_image, const unsigned thr_per_group, const int n0) {
+    constexpr int E = Chunk<T>::kElems;
+    constexpr int CH = NV * E;       // channels per thread
+    constexpr int R = CH / 4;        // 16-byte fp32 pieces per corner contribution
+    static_assert(!PAIR || (R % 2 == 0), "pair exchange needs an even number of pieces");
+    unsigned t = blockIdx.x * kBwdThreads + threadIdx.x;
+    // whole lane-groups are live or not (thr_per_image is a multiple of thr_per_group, which
+    // divides 32); dead lanes still take part in the shuffles but touch no memory
+    const bool live = t < thr_per_image;
+    if (!live) t = thr_per_image - 1;
+    const int n = n0 + blockIdx.y;
+    const unsigned part = t % thr_per_group;
+    const unsigned pgl = t / thr_per_group;
+    const unsigned g = pgl % q.G;
+    const unsigned pix = pgl / q.G;
+    const int wo = pix % q.Wo, ho = pix / q.Wo;
 
     if constexpr (sizeof(accum.buf[0]) == 8) accum.scale = fixed_scale(amax_bits);
 
     const int kh = KH ? KH : q.kh, kw = KW ? KW : q.kw;
     const int P = kh * kw;
     const int C = q.G * q.gc;
-    const size_t img_base = (size_t)n * q.H * q.W * C + g * q.gc + cv * VEC;
+    const int row_stride = q.W * C;
+    const size_t pg = (size_t)n * ((size_t)q.Ho * q.Wo * q.G) + pgl;
+    const size_t img_base = (size_t)n * q.H * row_stride + g * q.gc + part * CH;
     const T *img = value + img_base;
-    const T *off = offset + pg * P * 2;
+    const T *off = offset + pg * (P * 2);
     const T *msk = mask + pg * P;
-    T *goff = grad_offset + pg * P * 2;
+    T *goff = grad_offset + pg * (P * 2);
     T *gmsk = grad_mask + pg * P;
 
-    float go[VEC];
-    ChanVec<T, VEC>::load(grad_out + pg * q.gc + cv * VEC, live, go);
+    uint4 gq[NV];   // upstream gradient, packed (for the exact corner dot products)
+    float gf[CH];   // and in fp32 (for the grad_value contributions)
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        gq[k] = ldg16(grad_out + pg * q.gc + part * CH + k * E, live);
+        unpack<T>(gq[k], gf + k * E);
+    }
+    // PAIR: the 16-byte pieces of parity (lane & 1) of BOTH lanes' gradients -- `g_even` for the
+    // point owned by the even lane of the pair, `g_odd` for the odd lane's point
+    float g_even[PAIR ? CH / 2 : 1], g_odd[PAIR ? CH / 2 : 1];
+    const int odd = threadIdx.x & 1;
+    if constexpr (PAIR) {
+#pragma unroll
+        for (int r = 0; r < R; r += 2)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                // I keep my piece r+odd and need the partner's piece r+odd; the partner needs my r+!odd
+                const float mine = odd ? gf[(r + 1) * 4 + e] : gf[r * 4 + e];
+                const float send = odd ? gf[r * 4 + e] : gf[(r + 1) * 4 + e];
+                const float theirs = __shfl_xor_sync(0xffffffffu, send, 1);
+                g_even[(r / 2) * 4 + e] = odd ? theirs : mine;
+                g_odd[(r / 2) * 4 + e] = odd ? mine : theirs;
+            }
+    }
 
     const float base_w = axis_base(wo, kw, q.sw, q.pw, q.dw, q.sigma);
     const float base_h = axis_base(ho, kh, q.sh, q.ph, q.dh, q.sigma);
@@ -150,60 +183,83 @@ bwd_scatter(const T *__restrict__ value, const T *__restrict__ offset, const T *
             const float m = to_f32(__ldg(msk + p));
             const float loc_w = base_w + ((float)(i * q.dw) + d.x) * q.sigma;
             const float loc_h = base_h + ((float)(j * q.dh) + d.y) * q.sigma;
-            const Tap tp = make_tap(loc_h, loc_w, q.H, q.W);
+            const ClampedTap tp = make_clamped_tap(loc_h, loc_w, q.H, q.W);
 
             float gm = 0.f, gx = 0.f, gy = 0.f;
+            float coef[4] = {0.f, 0.f, 0.f, 0.f};   // w_k * m per corner; 0 = nothing to add
+            int at[4] = {0, 0, 0, 0};               // corner offsets inside the image (elements)
             if (tp.inside) {
-                const ptrdiff_t at = ((ptrdiff_t)tp.h0 * q.W + tp.w0) * C;
-                const ptrdiff_t down = (ptrdiff_t)q.W * C;
-                float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
-                ChanVec<T, VEC>::load(img + at, tp.tl, v1);
-                ChanVec<T, VEC>::load(img + at + C, tp.tr, v2);
-                ChanVec<T, VEC>::load(img + at + down, tp.bl, v3);
-                ChanVec<T, VEC>::load(img + at + down + C, tp.br, v4);
+                const int r_lo = tp.row_lo * row_stride, r_hi = tp.row_hi * row_stride;
+                const int c_lo = tp.col_lo * C, c_hi = tp.col_hi * C;
+                at[0] = r_lo + c_lo; at[1] = r_lo + c_hi; at[2] = r_hi + c_lo; at[3] = r_hi + c_hi;
                 float d1 = 0.f, d2 = 0.f, d3 = 0.f, d4 = 0.f;
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) {
-                    d1 += go[v] * v1[v];
-                    d2 += go[v] * v2[v];
-                    d3 += go[v] * v3[v];
-                    d4 += go[v] * v4[v];
+                for (int k = 0; k < NV; ++k) {
+                    const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(img + at[0] + k * E));
+                    const uint4 v2 = __ldg(reinterpret_cast<const uint4 *>(img + at[1] + k * E));
+                    const uint4 v3 = __ldg(reinterpret_cast<const uint4 *>(img + at[2] + k * E));
+                    const uint4 v4 = __ldg(reinterpret_cast<const uint4 *>(img + at[3] + k * E));
+                    d1 = dot<T>(gq[k], v1, d1);
+                    d2 = dot<T>(gq[k], v2, d2);
+                    d3 = dot<T>(gq[k], v3, d3);
+                    d4 = dot<T>(gq[k], v4, d4);
                 }
-                const float w1 = tp.hh * tp.hw, w2 = tp.hh * tp.lw, w3 = tp.lh * tp.hw, w4 = tp.lh * tp.lw;
+                // zero padding lives in the 1-D factors (see ClampedTap)
+                const float fy_lo = tp.hh * tp.top, fy_hi = tp.lh * tp.bot;
+                const float fx_lo = tp.hw * tp.lef, fx_hi = tp.lw * tp.rig;
+                const float w1 = fy_lo * fx_lo, w2 = fy_lo * fx_hi, w3 = fy_hi * fx_lo, w4 = fy_hi * fx_hi;
                 gm = w1 * d1 + w2 * d2 + w3 * d3 + w4 * d4;
-                gx = m * (tp.hh * (d2 - d1) + tp.lh * (d4 - d3));
-                gy = m * (tp.hw * (d3 - d1) + tp.lw * (d4 - d2));
-                if (live) {
-                    float c[VEC];
-                    if (tp.tl) {
+                gx = m * (fy_lo * (tp.rig * d2 - tp.lef * d1) + fy_hi * (tp.rig * d4 - tp.lef * d3));
+                gy = m * (fx_lo * (tp.bot * d3 - tp.top * d1) + fx_hi * (tp.bot * d4 - tp.top * d2));
+                if (live) { coef[0] = w1 * m; coef[1] = w2 * m; coef[2] = w3 * m; coef[3] = w4 * m; }
+            }
+            if constexpr (PAIR) {
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) c[v] = (w1 * m) * go[v];
-                        accum.template add<VEC>(img_base + at, c);
+                for (int k = 0; k < 4; ++k) {
+                    const size_t mine = img_base + (size_t)at[k];
+                    const size_t theirs = (size_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)mine, 1);
+                    const float coef_theirs = __shfl_xor_sync(0xffffffffu, coef[k], 1);
+                    const float c_even = odd ? coef_theirs : coef[k];   // point owned by the even lane
+                    const float c_odd = odd ? coef[k] : coef_theirs;    // point owned by the odd lane
+                    const size_t a_even = (odd ? theirs : mine) + odd * 4;
+                    const size_t a_odd = (odd ? mine : theirs) + odd * 4;
+                    if (c_even != 0.f) {
+#pragma unroll
+                        for (int r = 0; r < R; r += 2) {
+                            float c[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) c[e] = c_even * g_even[(r / 2) * 4 + e];
+                            accum.template add<4>(a_even + r * 4, c);
+                        }
                     }
-                    if (tp.tr) {
+                    if (c_odd != 0.f) {
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) c[v] = (w2 * m) * go[v];
-                        accum.template add<VEC>(img_base + at + C, c);
+                        for (int r = 0; r < R; r += 2) {
+                            float c[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) c[e] = c_odd * g_odd[(r / 2) * 4 + e];
+                            accum.template add<4>(a_odd + r * 4, c);
+                        }
                     }
-                    if (tp.bl) {
+                }
+            } else {
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) c[v] = (w3 * m) * go[v];
-                        accum.template add<VEC>(img_base + at + down, c);
-                    }
-                    if (tp.br) {
+                for (int k = 0; k < 4; ++k) {
+                    if (coef[k] != 0.f) {
+                        float c[CH];
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) c[v] = (w4 * m) * go[v];
-                        accum.template add<VEC>(img_base + at + down + C, c);
+                        for (int v = 0; v < CH; ++v) c[v] = coef[k] * gf[v];
+                        accum.template add<CH>(img_base + (size_t)at[k], c);
                     }
                 }
             }
             // fold the channel sums across the lanes of this (pixel, group)
-            for (int s = vec_per_group >> 1; s > 0; s >>= 1) {
+            for (int s = thr_per_group >> 1; s > 0; s >>= 1) {
                 gm += __shfl_xor_sync(0xffffffffu, gm, s);
                 gx += __shfl_xor_sync(0xffffffffu, gx, s);
                 gy += __shfl_xor_sync(0xffffffffu, gy, s);
             }
-            if (live && cv == 0) {
+            if (live && part == 0) {
                 store_pair(goff + 2 * p, q.sigma * gx, q.sigma * gy);
                 gmsk[p] = from_f32<T>(gm);
             }
@@ -293,33 +349,64 @@ size_t backward_workspace_bytes(const Geom &q, int dtype, unsigned flags) {
     return 0;
 }
 
-template <typename T, int VEC, typename Accum>
-static cudaError_t launch_scatter(const T *v, const T *o, const T *m, const T *go, Accum accum,
-                                  const unsigned *amax_bits, T *goff, T *gmsk, const Geom &q,
-                                  bool vec_ok, cudaStream_t stream) {
-    const long long n_groups = (long long)q.N * q.Ho * q.Wo * q.G;
-    if (n_groups == 0) return cudaSuccess;
-    const int vec_per_group = q.gc / VEC;
-    if (vec_ok && q.gc % VEC == 0 && is_pow2(vec_per_group) && vec_per_group <= 32) {
-        const long long n_threads = n_groups * vec_per_group;
-        const long long blocks = (n_threads + kBwdThreads - 1) / kBwdThreads;
-        if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+int bwd_variant_requested() {
+    // development knob: DCNV3_BWD_PAIR=0 disables the sector-coalescing lane-pair exchange
+    const char *e = std::getenv("DCNV3_BWD_PAIR");
+    return (e && e[0] == '0') ? 0 : 1;
+}
+
+template <typename T, int NV, typename Accum, bool PAIR>
+static cudaError_t launch_vec(const T *v, const T *o, const T *m, const T *go, Accum accum,
+                              const unsigned *amax_bits, T *goff, T *gmsk, const Geom &q,
+                              cudaStream_t stream) {
+    constexpr int E = Chunk<T>::kElems;
+    const unsigned thr_per_group = q.gc / (NV * E);
+    const long long per_image = (long long)q.Ho * q.Wo * q.G * thr_per_group;  // < 2^31 (C ABI check)
+    const unsigned blocks = (unsigned)((per_image + kBwdThreads - 1) / kBwdThreads);
+    for (int n0 = 0; n0 < q.N; n0 += 65535) {  // gridDim.y limit
+        const dim3 grid(blocks, (unsigned)std::min(65535, q.N - n0));
         if (q.kh == 3 && q.kw == 3)
-            bwd_scatter<T, VEC, 3, 3, Accum><<<(unsigned)blocks, kBwdThreads, 0, stream>>>(
-                v, o, m, go, accum, amax_bits, goff, gmsk, q, n_threads, vec_per_group);
+            bwd_scatter<T, NV, 3, 3, Accum, PAIR><<<grid, kBwdThreads, 0, stream>>>(
+                v, o, m, go, accum, amax_bits, goff, gmsk, q, (unsigned)per_image, thr_per_group, n0);
         else
-            bwd_scatter<T, VEC, 0, 0, Accum><<<(unsigned)blocks, kBwdThreads, 0, stream>>>(
-                v, o, m, go, accum, amax_bits, goff, gmsk, q, n_threads, vec_per_group);
-    } else {
-        const long long blocks = (n_groups * 32 + kBwdThreads - 1) / kBwdThreads;
-        if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-        bwd_scatter_warp<T, Accum><<<(unsigned)blocks, kBwdThreads, 0, stream>>>(
-            v, o, m, go, accum, amax_bits, goff, gmsk, q, n_groups);
+            bwd_scatter<T, NV, 0, 0, Accum, PAIR><<<grid, kBwdThreads, 0, stream>>>(
+                v, o, m, go, accum, amax_bits, goff, gmsk, q, (unsigned)per_image, thr_per_group, n0);
     }
     return cudaGetLastError();
 }
 
-template <typename T, int VEC>
+template <typename T, typename Accum>
+static cudaError_t launch_scatter(const T *v, const T *o, const T *m, const T *go, Accum accum,
+                                  const unsigned *amax_bits, T *goff, T *gmsk, const Geom &q,
+                                  bool vec_ok, cudaStream_t stream) {
+    constexpr int E = Chunk<T>::kElems;
+    constexpr bool kF32Accum = sizeof(accum.buf[0]) == 4;
+    const long long n_groups = (long long)q.N * q.Ho * q.Wo * q.G;
+    if (n_groups == 0) return cudaSuccess;
+    const int chunks = q.gc / E;
+    // one 16-byte chunk per lane by default (sector-efficient gathers); DCNV3_NV=2: two chunks
+    const char *nv_env = std::getenv("DCNV3_NV");
+    const int nv = (nv_env && nv_env[0] == '2' && chunks % 2 == 0) ? 2 : 1;
+    const int thr_per_group = chunks / nv;
+    if (vec_ok && q.gc % E == 0 && is_pow2(thr_per_group) && thr_per_group <= 32) {
+        const bool pair = kF32Accum && bwd_variant_requested();
+        if (nv == 2) {
+            if constexpr (kF32Accum)
+                if (pair) return launch_vec<T, 2, Accum, true>(v, o, m, go, accum, amax_bits, goff, gmsk, q, stream);
+            return launch_vec<T, 2, Accum, false>(v, o, m, go, accum, amax_bits, goff, gmsk, q, stream);
+        }
+        if constexpr (kF32Accum && E == 8)
+            if (pair) return launch_vec<T, 1, Accum, true>(v, o, m, go, accum, amax_bits, goff, gmsk, q, stream);
+        return launch_vec<T, 1, Accum, false>(v, o, m, go, accum, amax_bits, goff, gmsk, q, stream);
+    }
+    const long long blocks = (n_groups * 32 + kBwdThreads - 1) / kBwdThreads;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    bwd_scatter_warp<T, Accum><<<(unsigned)blocks, kBwdThreads, 0, stream>>>(
+        v, o, m, go, accum, amax_bits, goff, gmsk, q, n_groups);
+    return cudaGetLastError();
+}
+
+template <typename T>
 static cudaError_t backward_typed(const void *value, const void *offset, const void *mask,
                                   const void *grad_out, void *grad_value, void *grad_offset,
                                   void *grad_mask, void *workspace, const Geom &q, unsigned flags,
@@ -344,17 +431,17 @@ static cudaError_t backward_typed(const void *value, const void *offset, const v
             absmax_kernel<T><<<aux_blocks, 256, 0, stream>>>(go, n_out, amax_bits);
             if ((err = cudaGetLastError()) != cudaSuccess) return err;
         }
-        if ((err = launch_scatter<T, VEC>(v, o, m, go, AccumFixed{acc, 1.f}, amax_bits, goff, gmsk, q, vec_ok, stream)) != cudaSuccess) return err;
+        if ((err = launch_scatter<T>(v, o, m, go, AccumFixed{acc, 1.f}, amax_bits, goff, gmsk, q, vec_ok, stream)) != cudaSuccess) return err;
         narrow_fixed_kernel<T><<<aux_blocks, 256, 0, stream>>>(acc, amax_bits, gv, plane);
         return cudaGetLastError();
     }
     if constexpr (sizeof(T) == 4) {  // fp32 I/O: accumulate straight into grad_value
         if ((err = cudaMemsetAsync(gv, 0, plane * sizeof(float), stream)) != cudaSuccess) return err;
-        return launch_scatter<T, VEC>(v, o, m, go, AccumF32{reinterpret_cast<float *>(gv)}, nullptr, goff, gmsk, q, vec_ok, stream);
+        return launch_scatter<T>(v, o, m, go, AccumF32{reinterpret_cast<float *>(gv)}, nullptr, goff, gmsk, q, vec_ok, stream);
     } else {  // 16-bit I/O: fp32 scratch plane, then one narrowing pass
         float *acc = reinterpret_cast<float *>(static_cast<char *>(workspace) + kWorkspaceHeader);
         if ((err = cudaMemsetAsync(acc, 0, plane * sizeof(float), stream)) != cudaSuccess) return err;
-        if ((err = launch_scatter<T, VEC>(v, o, m, go, AccumF32{acc}, nullptr, goff, gmsk, q, vec_ok, stream)) != cudaSuccess) return err;
+        if ((err = launch_scatter<T>(v, o, m, go, AccumF32{acc}, nullptr, goff, gmsk, q, vec_ok, stream)) != cudaSuccess) return err;
         narrow_f32_kernel<T><<<aux_blocks, 256, 0, stream>>>(acc, gv, plane);
         return cudaGetLastError();
     }
@@ -365,9 +452,9 @@ cudaError_t launch_backward(const void *value, const void *offset, const void *m
                             void *grad_mask, void *workspace, const Geom &q, int dtype,
                             unsigned flags, cudaStream_t stream) {
     switch (dtype) {
-    case 0: return backward_typed<float, 4>(value, offset, mask, grad_out, grad_value, grad_offset, grad_mask, workspace, q, flags, stream);
-    case 1: return backward_typed<__half, 8>(value, offset, mask, grad_out, grad_value, grad_offset, grad_mask, workspace, q, flags, stream);
-    default: return backward_typed<__nv_bfloat16, 8>(value, offset, mask, grad_out, grad_value, grad_offset, grad_mask, workspace, q, flags, stream);
+    case 0: return backward_typed<float>(value, offset, mask, grad_out, grad_value, grad_offset, grad_mask, workspace, q, flags, stream);
+    case 1: return backward_typed<__half>(value, offset, mask, grad_out, grad_value, grad_offset, grad_mask, workspace, q, flags, stream);
+    default: return backward_typed<__nv_bfloat16>(value, offset, mask, grad_out, grad_value, grad_offset, grad_mask, workspace, q, flags, stream);
     }
 }
 

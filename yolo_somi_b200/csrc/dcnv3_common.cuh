@@ -111,6 +111,114 @@ __device__ __forceinline__ void store_pair(__nv_bfloat16 *p, float a, float b) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Packed 16-byte channel chunks (uint4 = 4 fp32 or 8 bf16/fp16) and the math on them.
+//
+// 16-bit types never get unpacked: sm_100a has a mixed-precision FMA (PTX fma.rn.f32.bf16 /
+// fma.rn.f32.f16 -> SASS FHFMA) that multiplies two 16-bit operands -- either half of a 32-bit
+// register, selected in the instruction -- exactly and accumulates in fp32 with one rounding.
+//   * products of two DATA values (grad_out * value in the backward) are therefore exact;
+//   * products weight * value need the fp32 weight as 16-bit operands: `Weight` splits it into
+//     hi + lo (w = hi + lo up to 2^-17 relative), two FHFMAs per element.  With kFastWeights the
+//     lo term is dropped (weight rounded to the I/O dtype, 2^-9 relative for bf16).
+template <typename T> struct Chunk { static constexpr int kElems = 16 / sizeof(T); };
+
+__device__ __forceinline__ uint4 ldg16(const void *p, bool pred) {
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (pred) v = __ldg(reinterpret_cast<const uint4 *>(p));
+    return v;
+}
+
+__device__ __forceinline__ float mix_fma(uint16_t a, uint16_t b, float c, __nv_bfloat16) {
+    float d;
+    asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float mix_fma(uint16_t a, uint16_t b, float c, __half) {
+    float d;
+    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ uint16_t lo16(uint32_t w) { return (uint16_t)(w & 0xffffu); }
+__device__ __forceinline__ uint16_t hi16(uint32_t w) { return (uint16_t)(w >> 16); }
+
+__device__ __forceinline__ uint16_t bits16(float v, __nv_bfloat16) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ uint16_t bits16(float v, __half) { return __half_as_ushort(__float2half_rn(v)); }
+__device__ __forceinline__ float f32_of(uint16_t b, __nv_bfloat16) { return __uint_as_float((uint32_t)b << 16); }
+__device__ __forceinline__ float f32_of(uint16_t b, __half) { return __half2float(__ushort_as_half(b)); }
+
+// fp32 weight prepared for `axpy`
+template <typename T, bool FAST> struct Weight {
+    uint16_t hi, lo;
+    __device__ __forceinline__ explicit Weight(float w) {
+        hi = bits16(w, T());
+        lo = FAST ? (uint16_t)0 : bits16(w - f32_of(hi, T()), T());
+    }
+};
+template <bool FAST> struct Weight<float, FAST> {
+    float w;
+    __device__ __forceinline__ explicit Weight(float w_) : w(w_) {}
+};
+
+// acc[0..kElems) += w * chunk
+template <typename T, bool FAST>
+__device__ __forceinline__ void axpy(float *acc, const uint4 &q, const Weight<T, FAST> &w) {
+    if constexpr (sizeof(T) == 4) {
+        acc[0] += w.w * __uint_as_float(q.x);
+        acc[1] += w.w * __uint_as_float(q.y);
+        acc[2] += w.w * __uint_as_float(q.z);
+        acc[3] += w.w * __uint_as_float(q.w);
+    } else {
+        const uint32_t r[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            acc[2 * i] = mix_fma(lo16(r[i]), w.hi, acc[2 * i], T());
+            acc[2 * i + 1] = mix_fma(hi16(r[i]), w.hi, acc[2 * i + 1], T());
+            if (!FAST) {
+                acc[2 * i] = mix_fma(lo16(r[i]), w.lo, acc[2 * i], T());
+                acc[2 * i + 1] = mix_fma(hi16(r[i]), w.lo, acc[2 * i + 1], T());
+            }
+        }
+    }
+}
+
+// sum_i a_i * b_i + init, both chunks of the same type (exact products for 16-bit types)
+template <typename T> __device__ __forceinline__ float dot(const uint4 &a, const uint4 &b, float init) {
+    const uint32_t x[4] = {a.x, a.y, a.z, a.w}, y[4] = {b.x, b.y, b.z, b.w};
+    float s0 = init, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        s0 = mix_fma(lo16(x[i]), lo16(y[i]), s0, T());
+        s1 = mix_fma(hi16(x[i]), hi16(y[i]), s1, T());
+    }
+    return s0 + s1;
+}
+template <> __device__ __forceinline__ float dot<float>(const uint4 &a, const uint4 &b, float init) {
+    float s = init;
+    s += __uint_as_float(a.x) * __uint_as_float(b.x);
+    s += __uint_as_float(a.y) * __uint_as_float(b.y);
+    s += __uint_as_float(a.z) * __uint_as_float(b.z);
+    s += __uint_as_float(a.w) * __uint_as_float(b.w);
+    return s;
+}
+
+// chunk -> fp32 values
+template <typename T> __device__ __forceinline__ void unpack(const uint4 &q, float *f) {
+    const float2 a = unpack2(q.x, T()), b = unpack2(q.y, T()), c = unpack2(q.z, T()), d = unpack2(q.w, T());
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+template <> __device__ __forceinline__ void unpack<float>(const uint4 &q, float *f) {
+    f[0] = __uint_as_float(q.x); f[1] = __uint_as_float(q.y);
+    f[2] = __uint_as_float(q.z); f[3] = __uint_as_float(q.w);
+}
+// fp32 values -> chunk
+template <typename T> __device__ __forceinline__ uint4 pack(const float *f) {
+    return make_uint4(pack2(f[0], f[1], T()), pack2(f[2], f[3], T()), pack2(f[4], f[5], T()), pack2(f[6], f[7], T()));
+}
+template <> __device__ __forceinline__ uint4 pack<float>(const float *f) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+}
+
+// ---------------------------------------------------------------------------------------------
 // One bilinear tap: location -> corner predicates and weights.
 struct Tap {
     bool inside;         // range test (:262-263); nothing is read or written when false
@@ -135,6 +243,38 @@ __device__ __forceinline__ Tap make_tap(float loc_h, float loc_w, int H, int W) 
     t.tr = t.inside && top && rig;
     t.bl = t.inside && bot && lef;
     t.br = t.inside && bot && rig;
+    return t;
+}
+
+// Branch-free form used by the vector kernels (valid only when `inside`): corner rows/columns are
+// clamped into the map so that every corner read is unconditional, and the zero padding of the
+// reference (:56-75) is applied to the 1-D interpolation factors instead: a factor is 0 when its
+// row / column lies outside.  A clamped read always lands on the tap's OTHER row / column, whose
+// factor is non-zero, so NaN/Inf propagate exactly as they do in the reference.
+struct ClampedTap {
+    bool inside;
+    int row_lo, row_hi, col_lo, col_hi;  // clamped corner coordinates
+    float top, bot, lef, rig;            // 1.0 if that row / column is inside the map, else 0.0
+    float hh, lh, hw, lw;                // raw factors (hh = 1 - lh, hw = 1 - lw)
+};
+
+__device__ __forceinline__ ClampedTap make_clamped_tap(float loc_h, float loc_w, int H, int W) {
+    ClampedTap t;
+    t.inside = loc_h > -1.f && loc_w > -1.f && loc_h < (float)H && loc_w < (float)W;
+    const float fh = floorf(loc_h), fw = floorf(loc_w);
+    const int h0 = (int)fh, w0 = (int)fw;
+    t.lh = loc_h - fh;
+    t.lw = loc_w - fw;
+    t.hh = 1.f - t.lh;
+    t.hw = 1.f - t.lw;
+    t.top = h0 >= 0 ? 1.f : 0.f;
+    t.bot = h0 + 1 <= H - 1 ? 1.f : 0.f;
+    t.lef = w0 >= 0 ? 1.f : 0.f;
+    t.rig = w0 + 1 <= W - 1 ? 1.f : 0.f;
+    t.row_lo = max(h0, 0);
+    t.row_hi = min(h0 + 1, H - 1);
+    t.col_lo = max(w0, 0);
+    t.col_hi = min(w0 + 1, W - 1);
     return t;
 }
 
