@@ -252,7 +252,9 @@ def test_cfg2_full_size_against_direct_oracle(dt):
     rtol = 1e-5 if dt == "f32" else 1e-2
     for name, a, w in zip(WHAT, got, (out, gv, goff, gm)):
         rms = float(np.sqrt(np.mean(w ** 2)))
-        frac = allclose_frac(a, w, rtol=rtol, atol=(2e-5 if dt == "f32" else 1e-2) * rms)
+        # fp32: sampling coordinates near 80 px carry an ulp of 7.6e-6 px, which moves a sample by
+        # up to ~1e-5 x the local value difference; hence the absolute floor of 1e-4 x RMS
+        frac = allclose_frac(a, w, rtol=rtol, atol=(1e-4 if dt == "f32" else 1e-2) * rms)
         assert frac <= (1e-4 if name == "go" else 1e-6), (name, frac, max_abs(a, w), rms)
 
 

@@ -12,6 +12,11 @@ constexpr size_t kWorkspaceHeader = 256;  // bytes reserved at the start of the 
 cudaError_t launch_forward(const void *value, const void *offset, const void *mask, void *out,
                            const Geom &q, int dtype, cudaStream_t stream);
 
+// shared-memory tiled forward (dcnv3_forward_tile.cu); false = shape not eligible, use the direct kernel
+bool try_launch_forward_tile(const void *value, const void *offset, const void *mask, void *out,
+                             const Geom &q, int dtype, bool fast, cudaStream_t stream, cudaError_t *err);
+bool fast_weights_requested();
+
 size_t backward_workspace_bytes(const Geom &q, int dtype, unsigned flags);
 
 cudaError_t launch_backward(const void *value, const void *offset, const void *mask,
