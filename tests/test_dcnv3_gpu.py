@@ -108,6 +108,38 @@ def test_half_precision_vs_oracle(case, dt):
         assert frac <= (2e-3 if name == "go" else 1e-4), (name, frac, max_abs(a, w), rms)
 
 
+# ----------------------------------------------------------------------------- tiled kernels
+_TILE_CASES = [
+    # name                         N  H   W   G  gc  extra
+    cases.Case("tile_bf16_partial", N=2, H=37, W=45, G=3, gc=16, seed=201),
+    cases.Case("tile_f32_gc8", N=2, H=21, W=50, G=4, gc=8, seed=202),
+    cases.Case("tile_sigma2", N=1, H=33, W=18, G=2, gc=16, sigma=2.0, seed=203),
+    cases.Case("tile_k5", N=1, H=20, W=27, G=2, gc=16, kh=5, kw=5, ph=2, pw=2, seed=204),
+    cases.Case("tile_dil2", N=1, H=19, W=23, G=2, gc=16, ph=2, pw=2, dh=2, dw=2, seed=205),
+    cases.Case("tile_gc32_two_slices", N=1, H=18, W=20, G=2, gc=32, seed=206),
+]
+
+
+@pytest.mark.parametrize("spread", [1.0, 4.0], ids=["near", "far"])
+@pytest.mark.parametrize("case", _TILE_CASES, ids=lambda c: c.name)
+def test_tiled_kernels_vs_oracle(case, spread):
+    """Shapes that take the shared-memory tiled kernels (16-bit gc%16==0, fp32 gc%8==0), with
+    partial tiles, several groups/images; `far` scales the offsets x4 so that most points leave the
+    staged window and exercise the global fallback inside the tiled kernels."""
+    from oracle import dcnv3_oracle as orc
+    dt = torch.float32 if "f32" in case.name else torch.bfloat16
+    v, o, m, g = cases.make_inputs(case)
+    arrs = rounded((v, o * spread, m, g), dt)
+    got = run_cuda(arrs, case.geom, dtype=dt)
+    out = orc.direct_forward(*arrs[:3], *case.geom)
+    gv, go, gm = orc.direct_backward(*arrs, *case.geom)
+    rtol = 1e-5 if dt == torch.float32 else 1e-2
+    for name, a, w in zip(WHAT, got, (out, gv, go, gm)):
+        rms = float(np.sqrt(np.mean(w ** 2))) + 1e-30
+        frac = allclose_frac(a, w, rtol=rtol, atol=(1e-4 if dt == torch.float32 else 1e-2) * rms)
+        assert frac <= (2e-3 if name == "go" else 1e-4), (name, frac, max_abs(a, w), rms)
+
+
 # ----------------------------------------------------------------------------- edge cases
 def test_empty_batch():
     c = cases.Case("empty", N=0, H=5, W=6, G=2, gc=8)

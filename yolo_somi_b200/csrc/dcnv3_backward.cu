@@ -31,6 +31,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 namespace dcnv3 {
 
@@ -437,11 +438,16 @@ static cudaError_t backward_typed(const void *value, const void *offset, const v
     }
     if constexpr (sizeof(T) == 4) {  // fp32 I/O: accumulate straight into grad_value
         if ((err = cudaMemsetAsync(gv, 0, plane * sizeof(float), stream)) != cudaSuccess) return err;
+        if (vec_ok && try_launch_backward_tile(value, offset, mask, grad_out, reinterpret_cast<float *>(gv), grad_offset, grad_mask, q, 0, stream, &err))
+            return err;
         return launch_scatter<T>(v, o, m, go, AccumF32{reinterpret_cast<float *>(gv)}, nullptr, goff, gmsk, q, vec_ok, stream);
     } else {  // 16-bit I/O: fp32 scratch plane, then one narrowing pass
         float *acc = reinterpret_cast<float *>(static_cast<char *>(workspace) + kWorkspaceHeader);
         if ((err = cudaMemsetAsync(acc, 0, plane * sizeof(float), stream)) != cudaSuccess) return err;
-        if ((err = launch_scatter<T>(v, o, m, go, AccumF32{acc}, nullptr, goff, gmsk, q, vec_ok, stream)) != cudaSuccess) return err;
+        const int dtype_tag = std::is_same<T, __half>::value ? 1 : 2;
+        if (!(vec_ok && try_launch_backward_tile(value, offset, mask, grad_out, acc, grad_offset, grad_mask, q, dtype_tag, stream, &err)))
+            err = launch_scatter<T>(v, o, m, go, AccumF32{acc}, nullptr, goff, gmsk, q, vec_ok, stream);
+        if (err != cudaSuccess) return err;
         narrow_f32_kernel<T><<<aux_blocks, 256, 0, stream>>>(acc, gv, plane);
         return cudaGetLastError();
     }

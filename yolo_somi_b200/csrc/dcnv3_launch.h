@@ -17,6 +17,12 @@ bool try_launch_forward_tile(const void *value, const void *offset, const void *
                              const Geom &q, int dtype, bool fast, cudaStream_t stream, cudaError_t *err);
 bool fast_weights_requested();
 
+// shared-memory tiled backward (dcnv3_backward_tile.cu); gv_acc = zeroed fp32 accumulator
+bool try_launch_backward_tile(const void *value, const void *offset, const void *mask,
+                              const void *grad_out, float *gv_acc, void *grad_offset,
+                              void *grad_mask, const Geom &q, int dtype, cudaStream_t stream,
+                              cudaError_t *err);
+
 size_t backward_workspace_bytes(const Geom &q, int dtype, unsigned flags);
 
 cudaError_t launch_backward(const void *value, const void *offset, const void *mask,
