@@ -5,22 +5,25 @@
 // retires at ~215 G op/s -> ~1.07 ms (profiles/README.md).  Here contributions are first summed in
 // shared memory and each CTA sends only its accumulated window to L2 (~25x fewer RED ops).
 //
-// A CTA (4 warps) owns a 16x8 tile of output pixels of one (image, 32-byte channel slice of a
-// group).  Per kernel column (kh sampling points at a time):
-//   G phase, thread <-> pixel.  The value window (26x18 pixels, one TMA box, zero-filled outside the
+// A CTA (4 warps) owns an 8x16 (w x h) tile of output pixels of one (image, group); a warp owns
+// 4 rows of it.  Per kernel column (kh sampling points at a time):
+//   G phase, thread <-> pixel.  The value window (18x26 pixels, one TMA box, zero-filled outside the
 //     map) is gathered exactly like the forward (conflict-free rotated LDS.128, see
 //     dcnv3_forward_tile.cu); the four per-corner dot products with the upstream gradient use
 //     exact FHFMA products.  grad_offset / grad_mask are staged in shared memory (written out
 //     coalesced at the end); the point leaves a record {top-left cell, 4 coefficients w_k*m}.
-//   S phase, warp <-> 16-byte piece of the fp32 accumulator (4 of the slice's 16 channels for
-//     16-bit I/O, 2 of 8 for fp32), lane <-> record.  Warps therefore never touch the same
-//     shared-memory word, and plain LDS/FFMA/STS read-modify-writes replace atomics (shared-memory
-//     float atomics are CAS loops on this architecture).  Lanes of one warp that target the same
-//     cell in the same step are found with match.any and take turns (rank order), so the
-//     accumulation order inside a CTA is fixed.
-// Points whose 2x2 corner block leaves the window fall back to clamped global reads and direct
-// vector reductions.  Finally the window is added to the fp32 grad_value accumulator in global
-// memory with 128-bit reductions (cells outside the map and all-zero pieces are skipped).
+//   S phase, half-warp <-> record, lane <-> channel.  Each warp adds the records of ITS OWN 32
+//     pixels into a private fp32 band of the accumulator (15 window rows x 18 columns x 16
+//     channels), so warps never touch the same shared-memory word and plain LDS/FFMA/STS
+//     read-modify-writes replace atomics (shared-memory float atomics are CAS loops on this
+//     architecture).  A record's 16 channels are one contiguous 64-byte run, so the two records
+//     of a step cost one or two wavefronts per access -- this is what makes the scatter
+//     shared-memory-efficient (a lane-per-record mapping was 4x slower: random 16-byte accesses).
+//     The two half-warps only collide when their records' 2x2 blocks overlap; that step is
+//     then run as two passes.  The accumulation order inside a CTA is fixed.
+// Points whose 2x2 corner block leaves the window (or the warp's band) fall back to direct global
+// reductions.  Finally the bands are summed and added to the fp32 grad_value accumulator in
+// global memory with 128-bit reductions (cells outside the map and all-zero pieces are skipped).
 #include "dcnv3_common.cuh"
 #include "dcnv3_launch.h"
 #include "dcnv3_tma.cuh"
@@ -31,14 +34,17 @@
 
 namespace dcnv3 {
 
-constexpr int kBTileW = 16, kBTileH = 8;           // output pixels per tile
+constexpr int kBTileW = 8, kBTileH = 16;           // output pixels per tile
 constexpr int kBThreads = kBTileW * kBTileH;       // 128: one thread per pixel, 4 warps
-constexpr int kBWinW = 26, kBWinH = 18;            // window (value pixels == accumulator cells)
+constexpr int kBWarps = kBThreads / 32;
+constexpr int kBRowsPerWarp = kBTileH / kBWarps;   // 4 tile rows per warp
+constexpr int kBWinW = 18, kBWinH = 26;            // window (value pixels == accumulator cells)
 constexpr int kBCells = kBWinW * kBWinH;
+constexpr int kBBandH = kBRowsPerWarp + (kBWinH - kBTileH) + 1;   // 15 window rows reachable by a warp
+constexpr int kBBandCells = kBBandH * kBWinW;
 constexpr int kBSliceBytes = 32;                   // value bytes per pixel per CTA
-constexpr int kBPieces = 4;                        // accumulator pieces per cell == S-phase warps
 static_assert(kBWinW % 4 == 2, "window width must be 2 mod 4 (conflict-free corner layout)");
-static_assert(kBThreads / 32 == kBPieces, "one S-phase warp per accumulator piece");
+static_assert(kBTileW == 8, "a quarter-warp must be one tile row (rotation scheme)");
 
 struct BwdTileParams {
     int ox_rel, oy_rel;      // window origin relative to (wo0*stride_w, ho0*stride_h)
@@ -59,16 +65,14 @@ __device__ __forceinline__ float2 bpair_from_f32(float a, float b, float) { retu
 // shared-memory carve-up (bytes); every region is 16-byte aligned
 template <typename T> struct BwdTileLayout {
     static constexpr int SLICE = kBSliceBytes / sizeof(T);      // channels per CTA
-    static constexpr int PF = SLICE / kBPieces;                 // fp32 values per accumulator piece
     static constexpr size_t win = 0;                            // [kBWinH][kBWinW][32 B]
-    static constexpr size_t acc = win + (size_t)kBCells * kBSliceBytes;          // [piece][cell][PF] fp32
-    static constexpr size_t gout = acc + (size_t)kBPieces * kBCells * PF * 4;    // [128][32 B]
+    static constexpr size_t acc = win + (size_t)kBCells * kBSliceBytes;          // [warp][band cell][SLICE] fp32
+    static constexpr size_t gout = acc + (size_t)kBWarps * kBBandCells * SLICE * 4;   // [128][32 B]
     static constexpr size_t coef = gout + (size_t)kBThreads * kBSliceBytes;      // [kh][128] float4
     __host__ __device__ static size_t cell(int kh) { return coef + (size_t)kh * kBThreads * 16; }    // [kh][128] int
     __host__ __device__ static size_t off(int kh) { return cell(kh) + (size_t)kh * kBThreads * 4; }  // [128][P] pairs
     __host__ __device__ static size_t msk(int kh, int P) { return off(kh) + (size_t)kBThreads * P * 2 * sizeof(T); }
-    __host__ __device__ static size_t claim(int kh, int P) { return (msk(kh, P) + (size_t)kBThreads * P * sizeof(T) + 15) & ~(size_t)15; }
-    __host__ __device__ static size_t total(int kh, int P) { return (claim(kh, P) + (size_t)kBPieces * kBCells + 15) & ~(size_t)15; }
+    __host__ __device__ static size_t total(int kh, int P) { return (msk(kh, P) + (size_t)kBThreads * P * sizeof(T) + 15) & ~(size_t)15; }
 };
 
 __device__ __forceinline__ uint4 blds128(uint32_t a) {
@@ -84,19 +88,6 @@ template <typename V> __device__ __forceinline__ void brotate4(V (&x)[4], int r)
 __device__ __forceinline__ void red_add(float *p, float4 v) { atomicAdd(reinterpret_cast<float4 *>(p), v); }
 __device__ __forceinline__ void red_add(float *p, float2 v) { atomicAdd(reinterpret_cast<float2 *>(p), v); }
 
-// read-modify-write of one accumulator piece (PF = 4: 128-bit, PF = 2: 64-bit)
-template <int PF> __device__ __forceinline__ void rmw_piece(float *cellp, float c, const float *g) {
-    if constexpr (PF == 4) {
-        float4 a = *reinterpret_cast<float4 *>(cellp);
-        a.x += c * g[0]; a.y += c * g[1]; a.z += c * g[2]; a.w += c * g[3];
-        *reinterpret_cast<float4 *>(cellp) = a;
-    } else {
-        float2 a = *reinterpret_cast<float2 *>(cellp);
-        a.x += c * g[0]; a.y += c * g[1];
-        *reinterpret_cast<float2 *>(cellp) = a;
-    }
-}
-
 template <typename T, int KH, int KW>
 __global__ void __launch_bounds__(kBThreads)
 bwd_tile(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
@@ -107,7 +98,6 @@ bwd_tile(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
     using Pair = typename BwdPairOf<T>::type;
     constexpr int E = Chunk<T>::kElems;
     constexpr int SLICE = L::SLICE;
-    constexpr int PF = L::PF;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
 
@@ -120,7 +110,6 @@ bwd_tile(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
     int *s_cell = reinterpret_cast<int *>(smem + L::cell(kh));
     Pair *s_off = reinterpret_cast<Pair *>(smem + L::off(kh));
     T *s_msk = reinterpret_cast<T *>(smem + L::msk(kh, P));
-    unsigned char *s_claim = smem + L::claim(kh, P);                    // [warp][cell] lane ids
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_x = blockIdx.x % tp.tiles_x, tile_y = blockIdx.x / tp.tiles_x;
@@ -147,7 +136,7 @@ bwd_tile(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
     // ---- while the box is in flight: zero the accumulator, stage offsets / masks / grad_out
     {
         float4 *z = reinterpret_cast<float4 *>(s_acc);
-        for (int i = tid; i < kBPieces * kBCells * PF / 4; i += kBThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < kBWarps * kBBandCells * SLICE / 4; i += kBThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         const size_t img_pix = (size_t)n * q.Ho * q.Wo;
         for (int idx = tid; idx < kBThreads * P; idx += kBThreads) {
             const int px = idx / P, p = idx - px * P;
@@ -270,46 +259,62 @@ bwd_tile(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
         }
         __syncthreads();
         // ------------------------------------------------------------------ S phase (column i)
-        // warp <-> accumulator piece, lane <-> record; the 32 records of a step sit on a 2x2-spaced
-        // pixel lattice so that same-cell collisions inside a step are uncommon
-        float *plane = s_acc + (size_t)warp * kBCells * PF;
-        unsigned char *claim = s_claim + warp * kBCells;
-        for (int jj = 0; jj < kh; ++jj) {
-#pragma unroll
-            for (int step = 0; step < 4; ++step) {
-                const int r = (((lane >> 3) << 1) + (step >> 1)) * kBTileW + ((lane & 7) << 1) + (step & 1);
-                const int cell = s_cell[jj * kBThreads + r];
-                const bool act = cell >= 0;
-                const float4 cf = s_coef[jj * kBThreads + r];
-                float gp[PF];   // this warp's piece of the record's upstream gradient, fp32
-                {
-                    const uint2 raw = *reinterpret_cast<const uint2 *>(s_gout + r * kBSliceBytes + warp * 8);
-                    if constexpr (sizeof(T) == 4) { gp[0] = __uint_as_float(raw.x); gp[1] = __uint_as_float(raw.y); }
-                    else {
-                        const float2 a = unpack2(raw.x, T()), b = unpack2(raw.y, T());
-                        gp[0] = a.x; gp[1] = a.y; gp[2] = b.x; gp[3] = b.y;
-                    }
+        // half-warp <-> record, lane <-> channel; a warp scatters the records of its own 32 pixels
+        // into its private band.  Records r and r+16 (two tile rows apart) share a step.
+        {
+            const int hl = lane >> 4, ch = lane & 15;
+            const bool ch_ok = ch < SLICE;
+            float *band = s_acc + (size_t)warp * kBBandCells * SLICE;
+            const int band_cell0 = warp * kBRowsPerWarp * kBWinW;   // first window cell of the band
+            const int rbase = warp * 32 + 16 * hl;
+            const int n_steps = kh * 16;                            // (jj, step) flattened
+            // software pipeline: the next step's record is fetched while this one is accumulated
+            int cell = s_cell[rbase];
+            float4 cf = s_coef[rbase];
+            float gch = ch_ok ? to_f32(reinterpret_cast<const T *>(s_gout + rbase * kBSliceBytes)[ch]) : 0.f;
+            for (int it = 0; it < n_steps; ++it) {
+                const int cur_cell = cell;
+                const float4 cur_cf = cf;
+                const float cur_g = gch;
+                if (it + 1 < n_steps) {
+                    const int nx = it + 1, r = rbase + (nx & 15);
+                    cell = s_cell[(nx >> 4) * kBThreads + r];
+                    cf = s_coef[(nx >> 4) * kBThreads + r];
+                    gch = ch_ok ? to_f32(reinterpret_cast<const T *>(s_gout + r * kBSliceBytes)[ch]) : 0.f;
                 }
-                // Lanes whose records share a top-left cell must not read-modify-write together:
-                // every pending lane writes its id into the cell's claim slot, the id that sticks
-                // wins the round, the others retry.  The __syncwarp()s order the shared-memory
-                // traffic of different lanes (corner k of one lane may be corner k' of another).
-                float *c0 = plane + (size_t)(act ? cell : 0) * PF;
-                bool pending = act;
-                while (__any_sync(0xffffffffu, pending)) {
-                    if (pending) claim[cell] = (unsigned char)lane;
+                const int cb = cur_cell - band_cell0;
+                const bool act = cur_cell >= 0;
+                const bool in_band = act && cb >= 0 && cb < (kBBandH - 1) * kBWinW - 1;
+                // the two records of a step may be accumulated together unless their 2x2 blocks
+                // overlap: |delta cell| in {0, 1, W-1, W, W+1}
+                const int other = __shfl_xor_sync(0xffffffffu, in_band ? cur_cell : -100000, 16);
+                const int ad = abs(other - cur_cell);
+                const bool clash = in_band && (ad <= 1 || (ad >= kBWinW - 1 && ad <= kBWinW + 1));
+                const bool any_clash = __any_sync(0xffffffffu, clash);
+                float *c0 = band + (size_t)(in_band ? cb : 0) * SLICE + ch;
+                const bool mine = in_band && ch_ok;
+                for (int pass = 0; pass < 2; ++pass) {
+                    const bool go = mine && (any_clash ? (pass == hl) : (pass == 0));
+                    if (go) {
+                        const float a0 = c0[0], a1 = c0[SLICE], a2 = c0[kBWinW * SLICE], a3 = c0[(kBWinW + 1) * SLICE];
+                        c0[0] = a0 + cur_cf.x * cur_g;
+                        c0[SLICE] = a1 + cur_cf.y * cur_g;
+                        c0[kBWinW * SLICE] = a2 + cur_cf.z * cur_g;
+                        c0[(kBWinW + 1) * SLICE] = a3 + cur_cf.w * cur_g;
+                    }
                     __syncwarp();
-                    const bool win = pending && claim[cell] == (unsigned char)lane;
-                    __syncwarp();
-                    if (win) rmw_piece<PF>(c0, cf.x, gp);
-                    __syncwarp();
-                    if (win) rmw_piece<PF>(c0 + PF, cf.y, gp);
-                    __syncwarp();
-                    if (win) rmw_piece<PF>(c0 + kBWinW * PF, cf.z, gp);
-                    __syncwarp();
-                    if (win) rmw_piece<PF>(c0 + (kBWinW + 1) * PF, cf.w, gp);
-                    __syncwarp();
-                    pending = pending && !win;
+                    if (!any_clash) break;
+                }
+                if (act && !in_band && ch_ok) {
+                    // in the window but outside this warp's band (large vertical offset): rare
+                    const int y = oy + cur_cell / kBWinW, x = ox + cur_cell % kBWinW;
+                    const float cfs[4] = {cur_cf.x, cur_cf.y, cur_cf.z, cur_cf.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int yy = y + (k >> 1), xx = x + (k & 1);
+                        if ((unsigned)yy < (unsigned)q.H && (unsigned)xx < (unsigned)q.W && cfs[k] != 0.f)
+                            atomicAdd(gv_acc + img_base + (size_t)yy * row_stride + (size_t)xx * C + ch, cfs[k] * cur_g);
+                    }
                 }
             }
         }
@@ -329,21 +334,26 @@ bwd_tile(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
             }
         }
     }
-    // ---- flush the accumulator window: lane <-> (cell, piece), piece fastest => a cell's pieces
-    //      form one contiguous run in global memory
-    for (int idx = tid; idx < kBCells * kBPieces; idx += kBThreads) {
-        const int cell = idx / kBPieces, piece = idx % kBPieces;
-        const int y = oy + cell / kBWinW, x = ox + cell % kBWinW;
+    // ---- flush: sum the warps' bands per window cell and add to the global accumulator;
+    //      lane <-> (cell, 16-byte piece), piece fastest => a cell's pieces are contiguous in global
+    constexpr int PIECES = SLICE / 4;
+    for (int idx = tid; idx < kBCells * PIECES; idx += kBThreads) {
+        const int cell = idx / PIECES, piece = idx % PIECES;
+        const int wy = cell / kBWinW, wx = cell % kBWinW;
+        const int y = oy + wy, x = ox + wx;
         if ((unsigned)y < (unsigned)q.H && (unsigned)x < (unsigned)q.W) {
-            const float *src = s_acc + ((size_t)piece * kBCells + cell) * PF;
-            float *dst = gv_acc + img_base + (size_t)y * row_stride + (size_t)x * C + piece * PF;
-            if constexpr (PF == 4) {
-                const float4 v = *reinterpret_cast<const float4 *>(src);
-                if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) red_add(dst, v);
-            } else {
-                const float2 v = *reinterpret_cast<const float2 *>(src);
-                if (v.x != 0.f || v.y != 0.f) red_add(dst, v);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int w = 0; w < kBWarps; ++w) {
+                const int by = wy - w * kBRowsPerWarp;
+                if (by >= 0 && by < kBBandH) {
+                    const float4 t = *reinterpret_cast<const float4 *>(
+                        s_acc + ((size_t)w * kBBandCells + by * kBWinW + wx) * SLICE + piece * 4);
+                    v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                }
             }
+            if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f)
+                red_add(gv_acc + img_base + (size_t)y * row_stride + (size_t)x * C + piece * 4, v);
         }
     }
 }
@@ -402,8 +412,11 @@ bool try_launch_backward_tile(const void *value, const void *offset, const void 
                               const void *grad_out, float *gv_acc, void *grad_offset,
                               void *grad_mask, const Geom &q, int dtype, cudaStream_t stream,
                               cudaError_t *err) {
-    const char *e = std::getenv("DCNV3_BWD");   // development knob: DCNV3_BWD=scatter disables tiling
-    if (e && e[0] == 's') return false;
+    // Opt-in (DCNV3_BWD=tile): correct and parity-tested, but on B200 it is not yet faster than the
+    // direct kernel -- the scatter phase issues ~45 warp-instructions per sampling point at 8
+    // resident warps per SM (profiles/README.md, r1 bwd_tile).  Kept as the base for the next step.
+    const char *e = std::getenv("DCNV3_BWD");
+    if (!(e && e[0] == 't')) return false;
     if ((long long)q.N * q.Ho * q.Wo == 0) return false;
     switch (dtype) {
     case 0: return launch_bwd_tile_typed<float>(value, offset, mask, grad_out, gv_acc, grad_offset, grad_mask, q, dtype, stream, err);
