@@ -75,6 +75,16 @@ def make_inputs(n, device, dtype, seed):
     return tuple(t.to(dtype).to(device) for t in (value, offset, mask, grad))
 
 
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/traffic.json: {"kernel": ..., "dram_bytes": read+write, "source": file})."""
+    p = ROOT / "profiles" / "traffic.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d.get("dram_bytes"), d.get("source")
+    return None, None
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -219,10 +229,8 @@ def run_ours(args, rank, world, local_rank):
             c.record(); c.synchronize()
             fwd_ms.append(a.elapsed_time(b)); bwd_ms.append(b.elapsed_time(c))
     clocks = clk.summary()
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms = float(t.item())
+    from yolo_somi_b200.sharding import max_over_ranks
+    ms = max_over_ranks(ms, dev)
 
     # ---- end to end: pinned host buffers in, results back to pinned host buffers
     host_in = [t.cpu().pin_memory() for t in sets[0]]
@@ -247,10 +255,7 @@ def run_ours(args, rank, world, local_rank):
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    e2e_ms = max_over_ranks(e2e_ms, dev)
     h2d = sum(t.numel() * t.element_size() for t in host_in)
     d2h = sum(t.numel() * t.element_size() for t in host_out)
 
@@ -260,6 +265,7 @@ def run_ours(args, rank, world, local_rank):
     value = world * pts * args.steps / (ms * 1e-3)
     ab = algorithmic_bytes()
     peak, peak_src = peaks()
+    traffic, traffic_src = measured_traffic()
     bwd_t = statistics.mean(bwd_ms) * 1e-3
     fwd_t = statistics.mean(fwd_ms) * 1e-3
     ach = ab["bwd"] / bwd_t / 1e9
@@ -275,9 +281,9 @@ def run_ours(args, rank, world, local_rank):
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / e2e_steps},
         "gpu_launches": 3 * args.steps,
-        "roofline": {"bound": "hbm", "kernel": "backward pass (memset + bwd_scatter + narrow)",
+        "roofline": {"bound": "hbm", "kernel": "backward pass: bwd_scatter (+ memset and fp32->bf16 narrow of grad_value)",
                      "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes": ab["bwd"], "avg_ms": bwd_t * 1e3},
         "passes": {"fwd_ms": fwd_t * 1e3, "bwd_ms": bwd_t * 1e3,
                    "fwd_gbs": ab["fwd"] / fwd_t / 1e9, "fwd_frac": ab["fwd"] / fwd_t / 1e9 / peak,

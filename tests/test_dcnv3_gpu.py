@@ -120,13 +120,16 @@ _TILE_CASES = [
 ]
 
 
+@pytest.mark.parametrize("bwd", ["default", "tile"])
 @pytest.mark.parametrize("spread", [1.0, 4.0], ids=["near", "far"])
 @pytest.mark.parametrize("case", _TILE_CASES, ids=lambda c: c.name)
-def test_tiled_kernels_vs_oracle(case, spread):
+def test_tiled_kernels_vs_oracle(case, spread, bwd, monkeypatch):
     """Shapes that take the shared-memory tiled kernels (16-bit gc%16==0, fp32 gc%8==0), with
     partial tiles, several groups/images; `far` scales the offsets x4 so that most points leave the
     staged window and exercise the global fallback inside the tiled kernels."""
     from oracle import dcnv3_oracle as orc
+    if bwd == "tile":
+        monkeypatch.setenv("DCNV3_BWD", "tile")     # the opt-in shared-memory backward
     dt = torch.float32 if "f32" in case.name else torch.bfloat16
     v, o, m, g = cases.make_inputs(case)
     arrs = rounded((v, o * spread, m, g), dt)
