@@ -120,7 +120,7 @@ _TILE_CASES = [
 ]
 
 
-@pytest.mark.parametrize("bwd", ["default", "tile"])
+@pytest.mark.parametrize("bwd", ["default", "tile", "scatter"])
 @pytest.mark.parametrize("spread", [1.0, 4.0], ids=["near", "far"])
 @pytest.mark.parametrize("case", _TILE_CASES, ids=lambda c: c.name)
 def test_tiled_kernels_vs_oracle(case, spread, bwd, monkeypatch):
@@ -128,8 +128,8 @@ def test_tiled_kernels_vs_oracle(case, spread, bwd, monkeypatch):
     partial tiles, several groups/images; `far` scales the offsets x4 so that most points leave the
     staged window and exercise the global fallback inside the tiled kernels."""
     from oracle import dcnv3_oracle as orc
-    if bwd == "tile":
-        monkeypatch.setenv("DCNV3_BWD", "tile")     # the opt-in shared-memory backward
+    if bwd != "default":
+        monkeypatch.setenv("DCNV3_BWD", bwd)        # opt-in shared-memory SIMT backward / direct kernel
     dt = torch.float32 if "f32" in case.name else torch.bfloat16
     v, o, m, g = cases.make_inputs(case)
     arrs = rounded((v, o * spread, m, g), dt)
@@ -140,7 +140,12 @@ def test_tiled_kernels_vs_oracle(case, spread, bwd, monkeypatch):
     for name, a, w in zip(WHAT, got, (out, gv, go, gm)):
         rms = float(np.sqrt(np.mean(w ** 2))) + 1e-30
         frac = allclose_frac(a, w, rtol=rtol, atol=(1e-4 if dt == torch.float32 else 1e-2) * rms)
-        assert frac <= (2e-3 if name == "go" else 1e-4), (name, frac, max_abs(a, w), rms)
+        # grad_value of the tensor-core backward carries the bf16 rounding of the per-pixel
+        # coefficient sums (up to 25 taps x 4 corners at K=5): allow 1e-3 of the elements to sit
+        # between 1x and 5x the bound
+        lim = 2e-3 if name == "go" else (1e-3 if name == "gv" and dt != torch.float32 else 1e-4)
+        assert frac <= lim, (name, frac, max_abs(a, w), rms)
+        assert max_abs(a, w) <= 5e-2 * max(rms, float(np.abs(w).max()) * 0.2) or name == "go"
 
 
 # ----------------------------------------------------------------------------- edge cases
@@ -260,8 +265,10 @@ def test_deterministic_backward_is_bit_reproducible(dt, monkeypatch):
         for a, b in zip(runs[0], r):
             assert np.array_equal(a, b)
     tol = 1e-5 if dt == "f32" else 1e-2
-    for a, b in zip(runs[0], base):
-        assert allclose_frac(a, b, rtol=tol, atol=tol * 0.1 * (np.abs(b).max() + 1e-30)) == 0.0
+    for name, a, b in zip(WHAT, runs[0], base):
+        # 16-bit default backward = tensor-core path: grad_value carries bf16-rounded coefficients
+        lim = 1e-3 if (name == "gv" and dt != "f32") else 0.0
+        assert allclose_frac(a, b, rtol=tol, atol=tol * 0.1 * (np.abs(b).max() + 1e-30)) <= lim, name
 
 
 # ----------------------------------------------------------------------------- BASELINE sizes
@@ -290,7 +297,8 @@ def test_cfg2_full_size_against_direct_oracle(dt):
         # fp32: sampling coordinates near 80 px carry an ulp of 7.6e-6 px, which moves a sample by
         # up to ~1e-5 x the local value difference; hence the absolute floor of 1e-4 x RMS
         frac = allclose_frac(a, w, rtol=rtol, atol=(1e-4 if dt == "f32" else 1e-2) * rms)
-        assert frac <= (1e-4 if name == "go" else 1e-6), (name, frac, max_abs(a, w), rms)
+        lim = 1e-4 if name == "go" else (1e-3 if (name == "gv" and dt != "f32") else 1e-6)
+        assert frac <= lim, (name, frac, max_abs(a, w), rms)
 
 
 @pytest.mark.parametrize("dt", ["f32", "bf16"])

@@ -23,6 +23,11 @@ bool try_launch_backward_tile(const void *value, const void *offset, const void 
                               void *grad_mask, const Geom &q, int dtype, cudaStream_t stream,
                               cudaError_t *err);
 
+// tensor-core backward for 16-bit I/O, group_channels == 16 (dcnv3_backward_mma.cu)
+bool try_launch_backward_mma(const void *value, const void *offset, const void *mask,
+                             const void *grad_out, float *gv_acc, void *grad_offset, void *grad_mask,
+                             const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err);
+
 size_t backward_workspace_bytes(const Geom &q, int dtype, unsigned flags);
 
 cudaError_t launch_backward(const void *value, const void *offset, const void *mask,
