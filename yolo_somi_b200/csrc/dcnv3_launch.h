@@ -28,6 +28,10 @@ bool try_launch_backward_mma(const void *value, const void *offset, const void *
                              const void *grad_out, float *gv_acc, void *grad_offset, void *grad_mask,
                              const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err);
 
+bool try_launch_backward_mma2(const void *value, const void *offset, const void *mask,
+                              const void *grad_out, float *gv_acc, void *grad_offset, void *grad_mask,
+                              const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err);
+
 size_t backward_workspace_bytes(const Geom &q, int dtype, unsigned flags);
 
 cudaError_t launch_backward(const void *value, const void *offset, const void *mask,
