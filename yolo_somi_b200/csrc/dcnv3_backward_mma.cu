@@ -28,6 +28,7 @@
 // window / the band fall back to clamped global reads and direct reductions.
 #include "dcnv3_common.cuh"
 #include "dcnv3_launch.h"
+#include "dcnv3_stage.cuh"
 #include "dcnv3_tma.cuh"
 
 #include <algorithm>
@@ -146,15 +147,7 @@ bwd_mma(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
         uint4 *z = reinterpret_cast<uint4 *>(s_buf);
         for (int i = tid; i < kWarps * kBufCells * 4; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
         const size_t img_pix = (size_t)n * q.Ho * q.Wo;
-        for (int idx = tid; idx < kThreads * P; idx += kThreads) {
-            const int px = idx / P, p = idx - px * P;
-            const int w = wo0 + (px % kTileW), h = ho0 + (px / kTileW);
-            if (w < q.Wo && h < q.Ho) {
-                const size_t pgi = (img_pix + (size_t)h * q.Wo + w) * q.G + g;
-                s_off[idx] = __ldg(reinterpret_cast<const uint32_t *>(offset) + pgi * P + p);
-                s_msk[idx] = __ldg(mask + pgi * P + p);
-            }
-        }
+        stage_offsets_masks<T, KH * KW, kThreads, kTileW>(offset, mask, s_off, s_msk, P, tid, wo0, ho0, q.Wo, q.Ho, q.G, g, img_pix);
         for (int idx = tid; idx < kThreads * 2; idx += kThreads) {   // 2 x 16-byte chunks per pixel
             const int px = idx >> 1, c = idx & 1;
             const int w = wo0 + (px % kTileW), h = ho0 + (px / kTileW);

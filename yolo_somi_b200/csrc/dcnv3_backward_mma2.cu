@@ -12,6 +12,7 @@
 // See dcnv3_backward_mma.cu for the derivation and the precision note (A is stored in the I/O dtype).
 #include "dcnv3_common.cuh"
 #include "dcnv3_launch.h"
+#include "dcnv3_stage.cuh"
 #include "dcnv3_tma.cuh"
 
 #include <algorithm>
@@ -99,15 +100,7 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
         tma_load_4d(win, &tmap, &bar, ch0, ox, oy, n);
     }
     const size_t img_pix = (size_t)n * q.Ho * q.Wo;
-    for (int idx = tid; idx < kThreads * P; idx += kThreads) {
-        const int px = idx / P, p = idx - px * P;
-        const int w = wo0 + (px % kTile), h = ho0 + (px / kTile);
-        if (w < q.Wo && h < q.Ho) {
-            const size_t pgi = (img_pix + (size_t)h * q.Wo + w) * q.G + g;
-            s_off[idx] = __ldg(reinterpret_cast<const uint32_t *>(offset) + pgi * P + p);
-            s_msk[idx] = __ldg(mask + pgi * P + p);
-        }
-    }
+    stage_offsets_masks<T, KH * KW, kThreads, kTile>(offset, mask, s_off, s_msk, P, tid, wo0, ho0, q.Wo, q.Ho, q.G, g, img_pix);
     const int j = tid & 7, half = j & 1;
     // upstream gradient of this thread's pixel: chunk `half` first
     uint4 gq_a = make_uint4(0u, 0u, 0u, 0u), gq_b = gq_a;
@@ -238,15 +231,7 @@ bwd_value_mma(const T *__restrict__ offset, const T *__restrict__ mask, const T 
     {
         uint4 *z = reinterpret_cast<uint4 *>(s_buf);
         for (int i = tid; i < kWarps * kBufCells * 4; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
-        for (int idx = tid; idx < kThreads * P; idx += kThreads) {
-            const int px = idx / P, p = idx - px * P;
-            const int w = wo0 + (px % kTileW), h = ho0 + (px / kTileW);
-            if (w < q.Wo && h < q.Ho) {
-                const size_t pgi = (img_pix + (size_t)h * q.Wo + w) * q.G + g;
-                s_off[idx] = __ldg(reinterpret_cast<const uint32_t *>(offset) + pgi * P + p);
-                s_msk[idx] = __ldg(mask + pgi * P + p);
-            }
-        }
+        stage_offsets_masks<T, KH * KW, kThreads, kTileW>(offset, mask, s_off, s_msk, P, tid, wo0, ho0, q.Wo, q.Ho, q.G, g, img_pix);
         for (int idx = tid; idx < kThreads * 2; idx += kThreads) {
             const int px = idx >> 1, c = idx & 1;
             const int w = wo0 + (px % kTileW), h = ho0 + (px / kTileW);

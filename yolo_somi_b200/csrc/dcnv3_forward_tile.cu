@@ -27,6 +27,7 @@
 // 16-bit data is never unpacked (FHFMA, see dcnv3_common.cuh); accumulation is fp32.
 #include "dcnv3_common.cuh"
 #include "dcnv3_launch.h"
+#include "dcnv3_stage.cuh"
 #include "dcnv3_tma.cuh"
 
 #include <algorithm>
@@ -114,18 +115,8 @@ fwd_tile(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
     // While the box is in flight: stage the tile's offsets and masks.  A pixel's P (dx,dy) pairs
     // are contiguous but pixels are G*P pairs apart, so consecutive threads take consecutive
     // pairs of the same pixel (coalesced) instead of each thread walking its own pixel.
-    {
-        const size_t img_pix = (size_t)n * q.Ho * q.Wo;
-        for (int idx = tid; idx < kTileThreads * P; idx += kTileThreads) {
-            const int px = idx / P, p = idx - px * P;
-            const int w = wo0 + (px % kTile), h = ho0 + (px / kTile);
-            if (w < q.Wo && h < q.Ho) {
-                const size_t pgi = (img_pix + (size_t)h * q.Wo + w) * q.G + g;
-                s_off[idx] = __ldg(reinterpret_cast<const Pair *>(offset) + pgi * P + p);
-                s_msk[idx] = __ldg(mask + pgi * P + p);
-            }
-        }
-    }
+    stage_offsets_masks<T, KH * KW, kTileThreads, kTile>(offset, mask, s_off, s_msk, P, tid, wo0, ho0, q.Wo, q.Ho,
+                                                         q.G, g, (size_t)n * q.Ho * q.Wo);
     const size_t pg = (((size_t)n * q.Ho + (live ? ho : 0)) * q.Wo + (live ? wo : 0)) * q.G + g;
     const int j = tid & 7;                        // lane within the quarter-warp
     const int half = j & 1;                       // which 16-byte chunk this lane reads FIRST

@@ -16,6 +16,9 @@ cudaError_t launch_forward(const void *value, const void *offset, const void *ma
 bool try_launch_forward_tile(const void *value, const void *offset, const void *mask, void *out,
                              const Geom &q, int dtype, bool fast, cudaStream_t stream, cudaError_t *err);
 bool fast_weights_requested();
+// tensor-core forward for 16-bit I/O, group_channels == 16 (dcnv3_forward_mma.cu)
+bool try_launch_forward_mma(const void *value, const void *offset, const void *mask, void *out,
+                            const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err);
 
 // shared-memory tiled backward (dcnv3_backward_tile.cu); gv_acc = zeroed fp32 accumulator
 bool try_launch_backward_tile(const void *value, const void *offset, const void *mask,
