@@ -120,7 +120,7 @@ _TILE_CASES = [
 ]
 
 
-@pytest.mark.parametrize("fwd", ["default", "tile"])
+@pytest.mark.parametrize("fwd", ["default", "mma"])
 @pytest.mark.parametrize("bwd", ["default", "tile", "scatter", "mma2"])
 @pytest.mark.parametrize("spread", [1.0, 4.0], ids=["near", "far"])
 @pytest.mark.parametrize("case", _TILE_CASES, ids=lambda c: c.name)
@@ -134,7 +134,7 @@ def test_tiled_kernels_vs_oracle(case, spread, bwd, fwd, monkeypatch):
     if fwd != "default":
         if bwd not in ("default", "scatter"):
             pytest.skip("forward variants are crossed with two backward variants only")
-        monkeypatch.setenv("DCNV3_FWD", fwd)        # SIMT tiled forward instead of the tensor-core one
+        monkeypatch.setenv("DCNV3_FWD", fwd)        # opt-in tensor-core forward
     dt = torch.float32 if "f32" in case.name else torch.bfloat16
     v, o, m, g = cases.make_inputs(case)
     arrs = rounded((v, o * spread, m, g), dt)

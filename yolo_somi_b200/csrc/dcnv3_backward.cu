@@ -93,7 +93,22 @@ absmax_kernel(const T *__restrict__ x, size_t n, unsigned *__restrict__ out_bits
 template <typename T>
 __global__ void __launch_bounds__(256)
 narrow_f32_kernel(const float *__restrict__ src, T *__restrict__ dst, size_t n) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    // 8 elements per thread per step: two 128-bit loads, one 128-bit store (src/dst 16-byte aligned)
+    const size_t n8 = n / 8;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 a = __ldcs(reinterpret_cast<const float4 *>(src) + 2 * i);
+        const float4 b = __ldcs(reinterpret_cast<const float4 *>(src) + 2 * i + 1);
+        if constexpr (sizeof(T) == 2) {
+            uint4 o;
+            o.x = pack2(a.x, a.y, T()); o.y = pack2(a.z, a.w, T());
+            o.z = pack2(b.x, b.y, T()); o.w = pack2(b.z, b.w, T());
+            reinterpret_cast<uint4 *>(dst)[i] = o;
+        } else {
+            reinterpret_cast<float4 *>(dst)[2 * i] = a;
+            reinterpret_cast<float4 *>(dst)[2 * i + 1] = b;
+        }
+    }
+    for (size_t i = n8 * 8 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         dst[i] = from_f32<T>(src[i]);
 }
 

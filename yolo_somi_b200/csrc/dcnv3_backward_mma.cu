@@ -282,7 +282,7 @@ bwd_mma(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
         }
         const int r_in = (lane & 7) + ((lane >> 3) & 1) * 8;   // row inside an m-tile this lane addresses
         const int kc_in = lane >> 4;                            // 16-byte k chunk (0/1) inside a k-step
-#pragma unroll 1
+#pragma unroll 4
         for (int mt = 0; mt < kMTiles; ++mt) {
             float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
             const int row = mt * 16 + r_in;

@@ -312,7 +312,7 @@ bwd_value_mma(const T *__restrict__ offset, const T *__restrict__ mask, const T 
             ldmatrix_x4_trans(bf[ks], smem_u32(s_gout) + px * kSliceBytes + (lane >> 4) * 16);
         }
         const int r_in = (lane & 7) + ((lane >> 3) & 1) * 8, kc_in = lane >> 4;
-#pragma unroll 1
+#pragma unroll 4
         for (int mt = 0; mt < kMTiles; ++mt) {
             float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
             const int row = mt * 16 + r_in;

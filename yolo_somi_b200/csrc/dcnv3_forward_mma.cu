@@ -195,7 +195,7 @@ fwd_mma(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
         const int r_in = (lane & 7) + ((lane >> 3) & 1) * 8, kc_in = lane >> 4;
         const uint32_t a_addr = smem_u32(s_a) + (uint32_t)(warp * 32 + r_in) * kAPitch + kc_in * 16;
         const uint32_t b_addr = smem_u32(win) + (uint32_t)(band_cell0 + r_in) * kSliceBytes + kc_in * 16;
-#pragma unroll 1
+#pragma unroll
         for (int ks = 0; ks < kKSteps; ++ks) {
             uint32_t a0[4], a1[4], b[4];
             ldmatrix_x4(a0, a_addr + ks * 32);                               // pixels 0-15, cells 16ks..
@@ -271,10 +271,10 @@ static bool launch_typed(const void *value, const void *offset, const void *mask
 // 16-bit I/O with group_channels == 16; false = not eligible (caller uses the SIMT kernels).
 bool try_launch_forward_mma(const void *value, const void *offset, const void *mask, void *out,
                             const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err) {
-    const char *e = std::getenv("DCNV3_FWD");   // DCNV3_FWD=tile|gather selects the SIMT kernels
-    if (e && (e[0] == 't' || e[0] == 'g')) return false;
-    const char *w = std::getenv("DCNV3_WEIGHTS");   // split = fp32-exact weights -> SIMT kernel
-    if (w && w[0] == 's') return false;
+    // Opt-in (DCNV3_FWD=mma): parity-tested, but at 2 CTAs/SM (72 KB of A tiles per CTA) it is
+    // latency-bound and slower than the SIMT tiled kernel on B200 (262 vs 168 us, profiles/README.md)
+    const char *e = std::getenv("DCNV3_FWD");
+    if (!(e && e[0] == 'm')) return false;
     if ((long long)q.N * q.Ho * q.Wo == 0) return false;
     if (dtype == 1) return fmma::launch_typed<__half>(value, offset, mask, out, q, dtype, stream, err);
     if (dtype == 2) return fmma::launch_typed<__nv_bfloat16>(value, offset, mask, out, q, dtype, stream, err);

@@ -247,8 +247,8 @@ static bool launch_tile_typed(const void *value, const void *offset, const void 
 // eligible and the caller should use the direct kernel.
 bool try_launch_forward_tile(const void *value, const void *offset, const void *mask, void *out,
                              const Geom &q, int dtype, bool fast, cudaStream_t stream, cudaError_t *err) {
-    const char *e = std::getenv("DCNV3_FWD");   // development knob: DCNV3_FWD=gather disables tiling
-    if (e && e[0] == 'g') return false;
+    const char *e = std::getenv("DCNV3_FWD");   // development knob: DCNV3_FWD=gather|mma select other kernels
+    if (e && (e[0] == 'g' || e[0] == 'm')) return false;
     if ((long long)q.N * q.Ho * q.Wo == 0) return false;
     switch (dtype) {
     case 0: return launch_tile_typed<float>(value, offset, mask, out, q, dtype, false, stream, err);
