@@ -153,6 +153,28 @@ def test_tiled_kernels_vs_oracle(case, spread, bwd, fwd, monkeypatch):
         assert max_abs(a, w) <= 5e-2 * max(rms, float(np.abs(w).max()) * 0.2) or name == "go"
 
 
+@pytest.mark.parametrize("dt", ["bf16", "f16"])
+def test_split_weights_forward_is_fp32_accurate(dt, monkeypatch):
+    """DCNV3_WEIGHTS=split keeps the bilinear*mask coefficients fp32-accurate: the only error left
+    is the final rounding of the output to the I/O dtype (half an ulp <= 2^-8 |x| bf16 / 2^-11 |x|
+    fp16, plus fp32 accumulation noise).  The default rounds the coefficients to the I/O dtype."""
+    from oracle import dcnv3_oracle as orc
+    case = cases.Case("split", N=2, H=30, W=26, G=2, gc=16, seed=321)
+    arrs = rounded(cases.make_inputs(case), TDT[dt])
+    want = orc.direct_forward(*arrs[:3], *case.geom)
+    half_ulp = 2.0 ** -8 if dt == "bf16" else 2.0 ** -11
+    err = {}
+    for mode in ("split", "fast"):
+        monkeypatch.setenv("DCNV3_WEIGHTS", mode)
+        got = run_cuda(arrs, case.geom, dtype=TDT[dt])[0]
+        err[mode] = np.abs(got - want)
+    rms = float(np.sqrt(np.mean(want ** 2)))
+    assert np.all(err["split"] <= 1.02 * half_ulp * np.abs(want) + 2e-5 * rms + 1e-30)
+    # the default stays inside the 1e-2 contract with a wide margin
+    assert np.mean(err["fast"] > 1e-2 * np.abs(want) + 1e-2 * rms) == 0.0
+    assert float(err["fast"].max()) <= 5e-2 * max(rms, float(np.abs(want).max()) * 0.2)
+
+
 # ----------------------------------------------------------------------------- edge cases
 def test_empty_batch():
     c = cases.Case("empty", N=0, H=5, W=6, G=2, gc=8)

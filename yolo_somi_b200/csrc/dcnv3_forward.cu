@@ -150,10 +150,11 @@ fwd_gather_scalar(const T *__restrict__ value, const T *__restrict__ offset,
 
 // ---------------------------------------------------------------------------------------------
 bool fast_weights_requested() {
-    // DCNV3_WEIGHTS=split|fast : 16-bit I/O only.  "split" (default) keeps fp32-exact bilinear
-    // weights (two FHFMA per element); "fast" rounds them to the I/O dtype (one FHFMA).
+    // 16-bit I/O only.  Default ("fast"): the bilinear*mask coefficient of a corner is rounded to the
+    // I/O dtype (2^-9 relative for bf16, 2^-12 for fp16) and folded with ONE FHFMA per element.
+    // DCNV3_WEIGHTS=split keeps it fp32-accurate (hi+lo parts, two FHFMA per element).
     const char *e = std::getenv("DCNV3_WEIGHTS");
-    return e && e[0] == 'f';
+    return !(e && e[0] == 's');
 }
 
 template <typename T, int NV, bool FAST>

@@ -22,20 +22,24 @@ __device__ __forceinline__ void stage_offsets_masks(const T *__restrict__ offset
                                                     int tid, int wo0, int ho0, int Wo, int Ho, int G, int g,
                                                     size_t img_pix) {
     using Pair = typename StagePair<T>::type;
+    // 64-bit base once per thread; everything per element is 32-bit (per-image extents < 2^31)
+    const size_t base = (img_pix * G + g) * (size_t)(PCT > 0 ? PCT : P);
+    const Pair *obase = reinterpret_cast<const Pair *>(offset) + base;
+    const T *mbase = mask + base;
     if constexpr (PCT > 0) {
         Pair po[PCT];
         T pm[PCT];
         bool ok[PCT];
 #pragma unroll
         for (int it = 0; it < PCT; ++it) {
-            const int idx = tid + it * NTHREADS;
-            const int px = idx / PCT, p = idx - px * PCT;
-            const int w = wo0 + (px % TILE_W), h = ho0 + (px / TILE_W);
-            ok[it] = w < Wo && h < Ho;
+            const unsigned idx = tid + it * NTHREADS;
+            const unsigned px = idx / PCT, p = idx - px * PCT;
+            const unsigned w = wo0 + (px % TILE_W), h = ho0 + (px / TILE_W);
+            ok[it] = w < (unsigned)Wo && h < (unsigned)Ho;
             if (ok[it]) {
-                const size_t pgi = (img_pix + (size_t)h * Wo + w) * G + g;
-                po[it] = __ldg(reinterpret_cast<const Pair *>(offset) + pgi * PCT + p);
-                pm[it] = __ldg(mask + pgi * PCT + p);
+                const unsigned rel = (h * Wo + w) * (unsigned)(G * PCT) + p;
+                po[it] = __ldg(obase + rel);
+                pm[it] = __ldg(mbase + rel);
             }
         }
 #pragma unroll
@@ -47,13 +51,13 @@ __device__ __forceinline__ void stage_offsets_masks(const T *__restrict__ offset
             }
         }
     } else {
-        for (int idx = tid; idx < NTHREADS * P; idx += NTHREADS) {
-            const int px = idx / P, p = idx - px * P;
-            const int w = wo0 + (px % TILE_W), h = ho0 + (px / TILE_W);
-            if (w < Wo && h < Ho) {
-                const size_t pgi = (img_pix + (size_t)h * Wo + w) * G + g;
-                s_off[idx] = __ldg(reinterpret_cast<const Pair *>(offset) + pgi * P + p);
-                s_msk[idx] = __ldg(mask + pgi * P + p);
+        for (unsigned idx = tid; idx < (unsigned)(NTHREADS * P); idx += NTHREADS) {
+            const unsigned px = idx / P, p = idx - px * P;
+            const unsigned w = wo0 + (px % TILE_W), h = ho0 + (px / TILE_W);
+            if (w < (unsigned)Wo && h < (unsigned)Ho) {
+                const unsigned rel = (h * Wo + w) * (unsigned)(G * P) + p;
+                s_off[idx] = __ldg(obase + rel);
+                s_msk[idx] = __ldg(mbase + rel);
             }
         }
     }
