@@ -79,11 +79,11 @@ __device__ __forceinline__ void red_add4(float *p, float4 v) { atomicAdd(reinter
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
 }
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
 }
 // D(16x8, fp32) += A(16x16) * B(16x8)
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, __nv_bfloat16) {
@@ -100,6 +100,169 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 // byte offset of A[cell][pixel] inside a warp buffer: 64-byte rows, 16-byte chunks swizzled
 __device__ __forceinline__ uint32_t a_elem_off(int cell, int pixel) {
     return (uint32_t)cell * 64u + ((((uint32_t)pixel >> 3) ^ (((uint32_t)cell >> 1) & 3u)) << 4) + (((uint32_t)pixel & 7u) << 1);
+}
+
+// Everything one thread needs to process the sampling points of its pixel.
+template <typename T> struct PointCtx {
+    int H, W, C, row_stride;        // map extents (elements)
+    int oy, ox;                      // window origin in the map
+    int band_cell0;                  // first window cell of this warp's band
+    int j, half, lane;               // lane in quarter-warp, first 16-byte chunk, lane in warp
+    uint32_t win_addr;               // shared address of the window (+ half * 16)
+    unsigned char *abuf;             // this warp's A tile
+    const T *img;                    // value + image/group base
+    float *gv_img;                   // fp32 accumulator + image/group base
+    uint4 gq_a, gq_b;                // upstream gradient of the pixel, chunk `half` / other chunk
+    float sigma;
+};
+
+// One sampling point at (loc_h, loc_w) with mask m: returns the three channel sums
+// (grad_mask, grad_offset_x / sigma, grad_offset_y / sigma) and adds the point's coefficients to
+// the A tile (window path) or straight to the global accumulator (fallback).
+template <typename T>
+__device__ __forceinline__ void process_point(const PointCtx<T> &c, float loc_h, float loc_w, float m,
+                                              float &gm, float &gx, float &gy) {
+    constexpr int E = 8;
+    gm = gx = gy = 0.f;
+    // range test of the reference (dcnv3_im2col_cuda.cuh:262-263); also rejects NaN
+    const bool inside = loc_h > -1.f && loc_w > -1.f && loc_h < (float)c.H && loc_w < (float)c.W;
+    if (!inside) return;
+    const float fh = floorf(loc_h), fw = floorf(loc_w);
+    const float lh = loc_h - fh, lw = loc_w - fw, hh = 1.f - lh, hw = 1.f - lw;
+    const int hwin = (int)fh - c.oy, wwin = (int)fw - c.ox;
+    const int cb = hwin * kWinW + wwin - c.band_cell0;   // top-left cell inside the band
+    if ((unsigned)hwin < (unsigned)(kWinH - 1) && (unsigned)wwin < (unsigned)(kWinW - 1) && cb >= 0 &&
+        cb < (kBandH - 1) * kWinW - 1) {
+        // ---- window path; out-of-map corners read zeros and their cells are dropped at flush time
+        int o[4] = {0, kSliceBytes, kWinW * kSliceBytes, kWinW * kSliceBytes + kSliceBytes};
+        const int rho = ((c.j >> 1) - (wwin + 2 * hwin)) & 3;
+        rotate4(o, rho);
+        const uint32_t tl = c.win_addr + (uint32_t)(hwin * kWinW + wwin) * kSliceBytes;
+        float dr[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const uint32_t a = tl + o[t];
+            const uint4 qa = lds128(a), qb = lds128(a ^ 16u);
+            dr[t] = dot<T>(c.gq_a, qa, 0.f) + dot<T>(c.gq_b, qb, 0.f);
+        }
+        rotate4(dr, (4 - rho) & 3);   // back to corner order TL, TR, BL, BR
+        const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+        gm = w1 * dr[0] + w2 * dr[1] + w3 * dr[2] + w4 * dr[3];
+        gx = m * (hh * (dr[1] - dr[0]) + lh * (dr[3] - dr[2]));
+        gy = m * (hw * (dr[2] - dr[0]) + lw * (dr[3] - dr[1]));
+        // drop the four coefficients into this pixel's column of A (thread-exclusive; the four
+        // corner cells are distinct: read all four, then write all four)
+        T *e0 = reinterpret_cast<T *>(c.abuf + a_elem_off(cb, c.lane));
+        T *e1 = reinterpret_cast<T *>(c.abuf + a_elem_off(cb + 1, c.lane));
+        T *e2 = reinterpret_cast<T *>(c.abuf + a_elem_off(cb + kWinW, c.lane));
+        T *e3 = reinterpret_cast<T *>(c.abuf + a_elem_off(cb + kWinW + 1, c.lane));
+        const float a0 = to_f32(*e0), a1 = to_f32(*e1), a2 = to_f32(*e2), a3 = to_f32(*e3);
+        *e0 = from_f32<T>(a0 + w1 * m);
+        *e1 = from_f32<T>(a1 + w2 * m);
+        *e2 = from_f32<T>(a2 + w3 * m);
+        *e3 = from_f32<T>(a3 + w4 * m);
+    } else {
+        // ---- fallback: clamped global reads, direct reductions
+        const ClampedTap ct = make_clamped_tap(loc_h, loc_w, c.H, c.W);
+        const int r_lo = ct.row_lo * c.row_stride, r_hi = ct.row_hi * c.row_stride;
+        const int c_lo = ct.col_lo * c.C, c_hi = ct.col_hi * c.C;
+        const int at[4] = {r_lo + c_lo, r_lo + c_hi, r_hi + c_lo, r_hi + c_hi};
+        const int ea = c.half * E, eb = (c.half ^ 1) * E;
+        float dk[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const uint4 qa = __ldg(reinterpret_cast<const uint4 *>(c.img + at[t] + ea));
+            const uint4 qb = __ldg(reinterpret_cast<const uint4 *>(c.img + at[t] + eb));
+            dk[t] = dot<T>(c.gq_a, qa, 0.f) + dot<T>(c.gq_b, qb, 0.f);
+        }
+        const float fy_lo = ct.hh * ct.top, fy_hi = ct.lh * ct.bot;
+        const float fx_lo = ct.hw * ct.lef, fx_hi = ct.lw * ct.rig;
+        const float wk[4] = {fy_lo * fx_lo, fy_lo * fx_hi, fy_hi * fx_lo, fy_hi * fx_hi};
+        gm = wk[0] * dk[0] + wk[1] * dk[1] + wk[2] * dk[2] + wk[3] * dk[3];
+        gx = m * (fy_lo * (ct.rig * dk[1] - ct.lef * dk[0]) + fy_hi * (ct.rig * dk[3] - ct.lef * dk[2]));
+        gy = m * (fx_lo * (ct.bot * dk[2] - ct.top * dk[0]) + fx_hi * (ct.bot * dk[3] - ct.top * dk[1]));
+        float ga[E], gb[E];
+        unpack<T>(c.gq_a, ga);
+        unpack<T>(c.gq_b, gb);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float cf = wk[t] * m;
+            if (cf != 0.f) {
+                float *dst = c.gv_img + at[t];
+#pragma unroll
+                for (int e = 0; e < E; e += 4) {
+                    red_add4(dst + ea + e, make_float4(cf * ga[e], cf * ga[e + 1], cf * ga[e + 2], cf * ga[e + 3]));
+                    red_add4(dst + eb + e, make_float4(cf * gb[e], cf * gb[e + 1], cf * gb[e + 2], cf * gb[e + 3]));
+                }
+            }
+        }
+    }
+}
+
+// band = A (272 x 32) * grad_out (32 x 16) for one warp; the fp32 result overwrites A in place,
+// m-tile by m-tile ([cell][16 ch] rows of 64 bytes).
+template <typename T>
+__device__ __forceinline__ void band_mma(unsigned char *abuf, const unsigned char *s_gout, int warp, int lane) {
+    const uint32_t a_base = smem_u32(abuf);
+    uint32_t bf[2][4];   // [k-step][{n0:k0-7, n0:k8-15, n1:k0-7, n1:k8-15}]
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        const int px = warp * 32 + ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        ldmatrix_x4_trans(bf[ks], smem_u32(s_gout) + px * kSliceBytes + (lane >> 4) * 16);
+    }
+    const int r_in = (lane & 7) + ((lane >> 3) & 1) * 8;   // row inside an m-tile this lane addresses
+    const int kc_in = lane >> 4;                            // 16-byte k chunk (0/1) inside a k-step
+#pragma unroll 4
+    for (int mt = 0; mt < kMTiles; ++mt) {
+        float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+        const int row = mt * 16 + r_in;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            uint32_t af[4];
+            const uint32_t chunk = (uint32_t)(ks * 2 + kc_in) ^ (((uint32_t)row >> 1) & 3u);
+            ldmatrix_x4(af, a_base + (uint32_t)row * 64u + (chunk << 4));
+            mma16816(acc0, af, bf[ks][0], bf[ks][1], T());
+            mma16816(acc1, af, bf[ks][2], bf[ks][3], T());
+        }
+        float *r0 = reinterpret_cast<float *>(abuf) + (size_t)(mt * 16 + (lane >> 2)) * kCh + 2 * (lane & 3);
+        *reinterpret_cast<float2 *>(r0) = make_float2(acc0[0], acc0[1]);
+        *reinterpret_cast<float2 *>(r0 + 8) = make_float2(acc1[0], acc1[1]);
+        *reinterpret_cast<float2 *>(r0 + 8 * kCh) = make_float2(acc0[2], acc0[3]);
+        *reinterpret_cast<float2 *>(r0 + 8 * kCh + 8) = make_float2(acc1[2], acc1[3]);
+    }
+}
+
+// Flush: add the four warps' bands to the global fp32 accumulator and (ZERO) leave them cleared.
+// Thread <-> one (window column, 16-byte piece): 72 of the 128 threads walk the 26 window rows
+// with a fully unrolled loop, so which bands cover a row is known at compile time and the address
+// arithmetic is one pointer increment per row (the generic per-cell loop cost 91 instructions per
+// 16 bytes flushed and 41 % of the kernel's run time, profiles/README.md).
+template <bool ZERO>
+__device__ __forceinline__ void flush_bands(float *bands, float *gimg /* accumulator at (n,0,0,ch0) */,
+                                            int oy, int ox, int H, int W, int row_stride, int C, int tid) {
+    if (tid >= kWinW * 4) return;
+    const int wx = tid >> 2, piece = tid & 3;
+    const int x = ox + wx;
+    const bool x_ok = (unsigned)x < (unsigned)W;
+    float *col = bands + wx * kCh + piece * 4;                       // (band 0, row 0) of this column
+    float *dst = gimg + (ptrdiff_t)oy * row_stride + (ptrdiff_t)x * C + piece * 4;
+#pragma unroll
+    for (int wy = 0; wy < kWinH; ++wy) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const int by = wy - w * kRowsPerWarp;                    // compile-time after unrolling
+            if (by >= 0 && by < kBandH) {
+                float4 *src = reinterpret_cast<float4 *>(col + ((size_t)w * kBufCells + by * kWinW) * kCh);
+                const float4 t = *src;
+                if (ZERO) *src = make_float4(0.f, 0.f, 0.f, 0.f);
+                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+            }
+        }
+        if (x_ok && (unsigned)(oy + wy) < (unsigned)H && (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f))
+            red_add4(dst, v);
+        dst += row_stride;
+    }
 }
 
 template <typename T, int KH, int KW>
@@ -177,131 +340,30 @@ bwd_mma(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
 
     // ------------------------------------------------------------------ gather + A build
     if (live) {
+        PointCtx<T> c;
+        c.H = q.H; c.W = q.W; c.C = C; c.row_stride = row_stride; c.oy = oy; c.ox = ox;
+        c.band_cell0 = band_cell0; c.j = j; c.half = half; c.lane = lane; c.win_addr = win_addr;
+        c.abuf = abuf; c.img = img; c.gv_img = gv_acc + img_base; c.gq_a = gq_a; c.gq_b = gq_b;
+        c.sigma = q.sigma;
 #pragma unroll 1
         for (int i = 0; i < kw; ++i) {
 #pragma unroll
             for (int jj = 0; jj < (KH ? KH : 8); ++jj) {
                 if (jj >= kh) break;
                 const int p = i * kh + jj;
-                float gm = 0.f, gx = 0.f, gy = 0.f;
                 const float2 d = unpack2(s_off[tid * P + p], T());
                 const float m = to_f32(s_msk[tid * P + p]);
                 const float loc_w = base_w + ((float)(i * q.dw) + d.x) * q.sigma;
                 const float loc_h = base_h + ((float)(jj * q.dh) + d.y) * q.sigma;
-                // range test of the reference (dcnv3_im2col_cuda.cuh:262-263); also rejects NaN
-                const bool inside = loc_h > -1.f && loc_w > -1.f && loc_h < (float)q.H && loc_w < (float)q.W;
-                const float fh = floorf(loc_h), fw = floorf(loc_w);
-                const float lh = loc_h - fh, lw = loc_w - fw, hh = 1.f - lh, hw = 1.f - lw;
-                const int hwin = (int)fh - oy, wwin = (int)fw - ox;
-                const int cb = hwin * kWinW + wwin - band_cell0;   // top-left cell inside the band
-                if (!inside) {
-                    // contributes nothing (all three gradients are zero)
-                } else if ((unsigned)hwin < (unsigned)(kWinH - 1) && (unsigned)wwin < (unsigned)(kWinW - 1) &&
-                           cb >= 0 && cb < (kBandH - 1) * kWinW - 1) {
-                    // ---- window path; out-of-map corners read zeros and their cells are dropped
-                    //      at flush time, so no per-corner range test is needed
-                    int o[4] = {0, kSliceBytes, kWinW * kSliceBytes, kWinW * kSliceBytes + kSliceBytes};
-                    const int rho = ((j >> 1) - (wwin + 2 * hwin)) & 3;
-                    rotate4(o, rho);
-                    const uint32_t tl = win_addr + (uint32_t)(hwin * kWinW + wwin) * kSliceBytes;
-                    float dr[4];
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const uint32_t a = tl + o[t];
-                        const uint4 qa = lds128(a), qb = lds128(a ^ 16u);
-                        dr[t] = dot<T>(gq_a, qa, 0.f) + dot<T>(gq_b, qb, 0.f);
-                    }
-                    rotate4(dr, (4 - rho) & 3);   // back to corner order TL, TR, BL, BR
-                    const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
-                    gm = w1 * dr[0] + w2 * dr[1] + w3 * dr[2] + w4 * dr[3];
-                    gx = m * (hh * (dr[1] - dr[0]) + lh * (dr[3] - dr[2]));
-                    gy = m * (hw * (dr[2] - dr[0]) + lw * (dr[3] - dr[1]));
-                    // drop the four coefficients into this pixel's column of A (thread-exclusive)
-                    // (the four corner cells are distinct: read all four, then write all four)
-                    T *e0 = reinterpret_cast<T *>(abuf + a_elem_off(cb, lane));
-                    T *e1 = reinterpret_cast<T *>(abuf + a_elem_off(cb + 1, lane));
-                    T *e2 = reinterpret_cast<T *>(abuf + a_elem_off(cb + kWinW, lane));
-                    T *e3 = reinterpret_cast<T *>(abuf + a_elem_off(cb + kWinW + 1, lane));
-                    const float a0 = to_f32(*e0), a1 = to_f32(*e1), a2 = to_f32(*e2), a3 = to_f32(*e3);
-                    *e0 = from_f32<T>(a0 + w1 * m);
-                    *e1 = from_f32<T>(a1 + w2 * m);
-                    *e2 = from_f32<T>(a2 + w3 * m);
-                    *e3 = from_f32<T>(a3 + w4 * m);
-                } else {
-                    // ---- fallback: clamped global reads, direct reductions
-                    const ClampedTap ct = make_clamped_tap(loc_h, loc_w, q.H, q.W);
-                    const int r_lo = ct.row_lo * row_stride, r_hi = ct.row_hi * row_stride;
-                    const int c_lo = ct.col_lo * C, c_hi = ct.col_hi * C;
-                    const int at[4] = {r_lo + c_lo, r_lo + c_hi, r_hi + c_lo, r_hi + c_hi};
-                    const int ea = half * E, eb = (half ^ 1) * E;
-                    float dk[4];
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const uint4 qa = __ldg(reinterpret_cast<const uint4 *>(img + at[t] + ea));
-                        const uint4 qb = __ldg(reinterpret_cast<const uint4 *>(img + at[t] + eb));
-                        dk[t] = dot<T>(gq_a, qa, 0.f) + dot<T>(gq_b, qb, 0.f);
-                    }
-                    const float fy_lo = ct.hh * ct.top, fy_hi = ct.lh * ct.bot;
-                    const float fx_lo = ct.hw * ct.lef, fx_hi = ct.lw * ct.rig;
-                    const float wk[4] = {fy_lo * fx_lo, fy_lo * fx_hi, fy_hi * fx_lo, fy_hi * fx_hi};
-                    gm = wk[0] * dk[0] + wk[1] * dk[1] + wk[2] * dk[2] + wk[3] * dk[3];
-                    gx = m * (fy_lo * (ct.rig * dk[1] - ct.lef * dk[0]) + fy_hi * (ct.rig * dk[3] - ct.lef * dk[2]));
-                    gy = m * (fx_lo * (ct.bot * dk[2] - ct.top * dk[0]) + fx_hi * (ct.bot * dk[3] - ct.top * dk[1]));
-                    float ga[E], gb[E];
-                    unpack<T>(gq_a, ga);
-                    unpack<T>(gq_b, gb);
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const float c = wk[t] * m;
-                        if (c != 0.f) {
-                            float *dst = gv_acc + img_base + at[t];
-#pragma unroll
-                            for (int e = 0; e < E; e += 4) {
-                                red_add4(dst + ea + e, make_float4(c * ga[e], c * ga[e + 1], c * ga[e + 2], c * ga[e + 3]));
-                                red_add4(dst + eb + e, make_float4(c * gb[e], c * gb[e + 1], c * gb[e + 2], c * gb[e + 3]));
-                            }
-                        }
-                    }
-                }
+                float gm, gx, gy;
+                process_point<T>(c, loc_h, loc_w, m, gm, gx, gy);
                 s_off[tid * P + p] = pack2(q.sigma * gx, q.sigma * gy, T());
                 s_msk[tid * P + p] = from_f32<T>(gm);
             }
         }
     }
     __syncwarp();
-
-    // ------------------------------------------------------------------ band = A (272x32) * grad_out (32x16)
-    {
-        const uint32_t a_base = smem_u32(abuf);
-        // B fragments: grad_out of this warp's 32 pixels, [pixel][16 ch] rows of 32 bytes
-        uint32_t bf[2][4];   // [k-step][{n0:k0-7, n0:k8-15, n1:k0-7, n1:k8-15}]
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            const int px = warp * 32 + ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-            ldmatrix_x4_trans(bf[ks], smem_u32(s_gout) + px * kSliceBytes + (lane >> 4) * 16);
-        }
-        const int r_in = (lane & 7) + ((lane >> 3) & 1) * 8;   // row inside an m-tile this lane addresses
-        const int kc_in = lane >> 4;                            // 16-byte k chunk (0/1) inside a k-step
-#pragma unroll 4
-        for (int mt = 0; mt < kMTiles; ++mt) {
-            float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
-            const int row = mt * 16 + r_in;
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                uint32_t af[4];
-                const uint32_t chunk = (uint32_t)(ks * 2 + kc_in) ^ (((uint32_t)row >> 1) & 3u);
-                ldmatrix_x4(af, a_base + (uint32_t)row * 64u + (chunk << 4));
-                mma16816(acc0, af, bf[ks][0], bf[ks][1], T());
-                mma16816(acc1, af, bf[ks][2], bf[ks][3], T());
-            }
-            // overwrite the m-tile's 16 rows with the fp32 result: row = cell, 16 channels x 4 B
-            float *r0 = reinterpret_cast<float *>(abuf) + (size_t)(mt * 16 + (lane >> 2)) * kCh + 2 * (lane & 3);
-            *reinterpret_cast<float2 *>(r0) = make_float2(acc0[0], acc0[1]);
-            *reinterpret_cast<float2 *>(r0 + 8) = make_float2(acc1[0], acc1[1]);
-            *reinterpret_cast<float2 *>(r0 + 8 * kCh) = make_float2(acc0[2], acc0[3]);
-            *reinterpret_cast<float2 *>(r0 + 8 * kCh + 8) = make_float2(acc1[2], acc1[3]);
-        }
-    }
+    band_mma<T>(abuf, s_gout, warp, lane);
     __syncthreads();
 
     // ---- grad_offset / grad_mask: coalesced write-out of the staged values
@@ -317,27 +379,223 @@ bwd_mma(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
             }
         }
     }
-    // ---- flush: sum the warps' bands per window cell and add to the global accumulator;
-    //      lane <-> (cell, 16-byte piece), piece fastest => a cell's pieces are contiguous in global
-    const float *bands = reinterpret_cast<const float *>(s_buf);
-    for (int idx = tid; idx < kCells * 4; idx += kThreads) {
-        const int cell = idx >> 2, piece = idx & 3;
-        const int wy = cell / kWinW, wx = cell % kWinW;
-        const int y = oy + wy, x = ox + wx;
-        if ((unsigned)y < (unsigned)q.H && (unsigned)x < (unsigned)q.W) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    flush_bands<false>(reinterpret_cast<float *>(s_buf), gv_acc + img_base, oy, ox, q.H, q.W, row_stride, C, tid);
+}
+
+// ================================================================================================
+// Persistent form (3x3 kernels): a CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... so
+// that every global-memory latency is taken off the critical path:
+//   * the NEXT tile's offsets / masks / grad_out are loaded into registers while the current tile
+//     is being gathered and parked in the second staging buffer at the end of the iteration;
+//   * the NEXT tile's value window is requested (TMA) as soon as the last warp has finished
+//     gathering from the window, and lands during the tensor-core product and the flush;
+//   * the flush leaves the A tiles / bands zeroed, so there is no separate clearing pass.
+// In the one-tile-per-CTA kernel above these waits were 26 % of the run time at 2 CTAs per SM
+// (profiles/README.md, bwd_mma source view).
+struct PersistParams {
+    int ox_rel, oy_rel, tiles_x, tiles_xy, total_tiles;
+};
+
+struct TileAt {
+    int n, g, wo0, ho0, ox, oy;
+};
+__device__ __forceinline__ TileAt decode_tile(int t, const Geom &q, const PersistParams &pp) {
+    TileAt a;
+    const int txy = t % pp.tiles_xy, r = t / pp.tiles_xy;
+    a.g = r % q.G;
+    a.n = r / q.G;
+    a.wo0 = (txy % pp.tiles_x) * kTileW;
+    a.ho0 = (txy / pp.tiles_x) * kTileH;
+    a.ox = a.wo0 * q.sw + pp.ox_rel;
+    a.oy = a.ho0 * q.sh + pp.oy_rel;
+    return a;
+}
+
+// one tile's staging data, in registers (P = 9)
+template <typename T> struct StageRegs {
+    uint32_t off[9];
+    T msk[9];
+    uint4 go[2];
+};
+template <typename T>
+__device__ __forceinline__ void stage_load(StageRegs<T> &r, const TileAt &a, const T *__restrict__ offset,
+                                           const T *__restrict__ mask, const T *__restrict__ grad_out,
+                                           const Geom &q, int tid) {
+    const size_t img_pix = (size_t)a.n * q.Ho * q.Wo;
+    const size_t base = (img_pix * q.G + a.g) * 9;
+    const uint32_t *obase = reinterpret_cast<const uint32_t *>(offset) + base;
+    const T *mbase = mask + base;
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) {
-                const int by = wy - w * kRowsPerWarp;
-                if (by >= 0 && by < kBandH) {
-                    const float4 t = *reinterpret_cast<const float4 *>(
-                        bands + ((size_t)w * kBufCells + by * kWinW + wx) * kCh + piece * 4);
-                    v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+    for (int it = 0; it < 9; ++it) {
+        const unsigned idx = tid + it * kThreads;
+        const unsigned px = idx / 9, p = idx - px * 9;
+        const unsigned w = a.wo0 + (px % kTileW), h = a.ho0 + (px / kTileW);
+        r.off[it] = 0u;
+        r.msk[it] = from_f32<T>(0.f);
+        if (w < (unsigned)q.Wo && h < (unsigned)q.Ho) {
+            const unsigned rel = (h * q.Wo + w) * (unsigned)(q.G * 9) + p;
+            r.off[it] = __ldg(obase + rel);
+            r.msk[it] = __ldg(mbase + rel);
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int idx = tid + it * kThreads, px = idx >> 1, c = idx & 1;
+        const int w = a.wo0 + (px % kTileW), h = a.ho0 + (px / kTileW);
+        r.go[it] = make_uint4(0u, 0u, 0u, 0u);   // pixels outside the map contribute nothing
+        if (w < q.Wo && h < q.Ho)
+            r.go[it] = __ldg(reinterpret_cast<const uint4 *>(
+                grad_out + (img_pix + (size_t)h * q.Wo + w) * (q.G * q.gc) + a.g * q.gc + c * 8));
+    }
+}
+template <typename T>
+__device__ __forceinline__ void stage_store(const StageRegs<T> &r, uint32_t *s_off, T *s_msk,
+                                            unsigned char *s_gout, int tid) {
+#pragma unroll
+    for (int it = 0; it < 9; ++it) {
+        s_off[tid + it * kThreads] = r.off[it];
+        s_msk[tid + it * kThreads] = r.msk[it];
+    }
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int idx = tid + it * kThreads;
+        *reinterpret_cast<uint4 *>(s_gout + (idx >> 1) * kSliceBytes + (idx & 1) * 16) = r.go[it];
+    }
+}
+
+struct PLayout {   // bytes
+    static constexpr size_t win = 0;
+    static constexpr size_t buf = win + (size_t)kCells * kSliceBytes;
+    static constexpr size_t stage = buf + (size_t)kWarps * kBufCells * 64;
+    static constexpr size_t stage_bytes = (size_t)kThreads * kSliceBytes + (size_t)kThreads * 9 * 6;   // gout + off + msk
+    static constexpr size_t total = stage + 2 * stage_bytes;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+bwd_mma_persistent(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
+                   const T *__restrict__ offset, const T *__restrict__ mask,
+                   const T *__restrict__ grad_out, float *__restrict__ gv_acc,
+                   T *__restrict__ grad_offset, T *__restrict__ grad_mask, const Geom q,
+                   const PersistParams pp) {
+    constexpr int P = 9;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    unsigned char *win = smem + PLayout::win;
+    unsigned char *s_buf = smem + PLayout::buf;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = q.G * q.gc, row_stride = q.W * C;
+    const int j = tid & 7, half = j & 1;
+    unsigned char *abuf = s_buf + (size_t)warp * kBufCells * 64;
+    const int band_cell0 = warp * kRowsPerWarp * kWinW;
+    auto stage_gout = [&](int b) { return smem + PLayout::stage + (size_t)b * PLayout::stage_bytes; };
+    auto stage_off = [&](int b) { return reinterpret_cast<uint32_t *>(stage_gout(b) + kThreads * kSliceBytes); };
+    auto stage_msk = [&](int b) { return reinterpret_cast<T *>(stage_off(b) + kThreads * P); };
+
+    int t = blockIdx.x;
+    if (t >= pp.total_tiles) return;
+    TileAt cur = decode_tile(t, q, pp);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+    }
+    {   // prologue: first tile's staging data, zero the A tiles once
+        StageRegs<T> r;
+        stage_load<T>(r, cur, offset, mask, grad_out, q, tid);
+        uint4 *z = reinterpret_cast<uint4 *>(s_buf);
+        for (int i = tid; i < kWarps * kBufCells * 4; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        stage_store<T>(r, stage_off(0), stage_msk(0), stage_gout(0), tid);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar, kCells * kSliceBytes);
+        tma_load_4d(win, &tmap, &bar, cur.g * q.gc, cur.ox, cur.oy, cur.n);
+    }
+
+    for (int it = 0;; ++it) {
+        const int b = it & 1;
+        const int t_next = t + gridDim.x;
+        const bool has_next = t_next < pp.total_tiles;
+        TileAt nxt = cur;
+        StageRegs<T> nr;
+        if (has_next) {
+            nxt = decode_tile(t_next, q, pp);
+            stage_load<T>(nr, nxt, offset, mask, grad_out, q, tid);   // in flight during the gather
+        }
+        uint32_t *s_off = stage_off(b);
+        T *s_msk = stage_msk(b);
+        unsigned char *s_gout = stage_gout(b);
+        const int wo = cur.wo0 + (tid % kTileW), ho = cur.ho0 + (tid / kTileW);
+        const bool live = wo < q.Wo && ho < q.Ho;
+        const size_t img_base = (size_t)cur.n * q.H * row_stride + cur.g * q.gc;
+
+        mbar_wait(&bar, it & 1);   // value window of the current tile has landed
+
+        // ---------------------------------------------------------------- gather + A build
+        if (live) {
+            PointCtx<T> c;
+            c.H = q.H; c.W = q.W; c.C = C; c.row_stride = row_stride; c.oy = cur.oy; c.ox = cur.ox;
+            c.band_cell0 = band_cell0; c.j = j; c.half = half; c.lane = lane;
+            c.win_addr = smem_u32(win) + half * 16;
+            c.abuf = abuf; c.img = value + img_base; c.gv_img = gv_acc + img_base;
+            c.gq_a = *reinterpret_cast<const uint4 *>(s_gout + tid * kSliceBytes + half * 16);
+            c.gq_b = *reinterpret_cast<const uint4 *>(s_gout + tid * kSliceBytes + (half ^ 1) * 16);
+            c.sigma = q.sigma;
+            const float base_w = axis_base(wo, 3, q.sw, q.pw, q.dw, q.sigma);
+            const float base_h = axis_base(ho, 3, q.sh, q.ph, q.dh, q.sigma);
+#pragma unroll 1
+            for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                for (int jj = 0; jj < 3; ++jj) {
+                    const int p = i * 3 + jj;
+                    const float2 d = unpack2(s_off[tid * P + p], T());
+                    const float m = to_f32(s_msk[tid * P + p]);
+                    const float loc_w = base_w + ((float)(i * q.dw) + d.x) * q.sigma;
+                    const float loc_h = base_h + ((float)(jj * q.dh) + d.y) * q.sigma;
+                    float gm, gx, gy;
+                    process_point<T>(c, loc_h, loc_w, m, gm, gx, gy);
+                    s_off[tid * P + p] = pack2(q.sigma * gx, q.sigma * gy, T());
+                    s_msk[tid * P + p] = from_f32<T>(gm);
                 }
             }
-            if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f)
-                red_add4(gv_acc + img_base + (size_t)y * row_stride + (size_t)x * C + piece * 4, v);
         }
+        __syncthreads();   // every warp is done with the window (and with its own A columns)
+        if (has_next && tid == 0) {
+            // order the generic-proxy reads of the window before the async-proxy overwrite
+            fence_proxy_async();
+            mbar_expect_tx(&bar, kCells * kSliceBytes);
+            tma_load_4d(win, &tmap, &bar, nxt.g * q.gc, nxt.ox, nxt.oy, nxt.n);
+        }
+        // ---------------------------------------------------------------- band = A x grad_out
+        band_mma<T>(abuf, s_gout, warp, lane);
+        __syncthreads();
+
+        // ---- grad_offset / grad_mask: coalesced write-out of the staged results
+        {
+            const size_t img_pix = (size_t)cur.n * q.Ho * q.Wo;
+            const size_t base = (img_pix * q.G + cur.g) * P;
+            uint32_t *ob = reinterpret_cast<uint32_t *>(grad_offset) + base;
+            T *mb = grad_mask + base;
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                const unsigned idx = tid + k * kThreads;
+                const unsigned px = idx / P, p = idx - px * P;
+                const unsigned w = cur.wo0 + (px % kTileW), h = cur.ho0 + (px / kTileW);
+                if (w < (unsigned)q.Wo && h < (unsigned)q.Ho) {
+                    const unsigned rel = (h * q.Wo + w) * (unsigned)(q.G * P) + p;
+                    ob[rel] = s_off[idx];
+                    mb[rel] = s_msk[idx];
+                }
+            }
+        }
+        // ---- flush (leaves the bands zeroed: they are the next tile's A tiles; band rows below
+        //      the window and the two pad cells per band never receive a coefficient)
+        flush_bands<true>(reinterpret_cast<float *>(s_buf), gv_acc + img_base, cur.oy, cur.ox, q.H, q.W, row_stride, C, tid);
+        if (!has_next) break;
+        stage_store<T>(nr, stage_off(b ^ 1), stage_msk(b ^ 1), stage_gout(b ^ 1), tid);
+        __syncthreads();   // next staging buffer visible, bands zeroed
+        cur = nxt;
+        t = t_next;
     }
 }
 
@@ -370,6 +628,24 @@ static bool launch_typed(const void *value, const void *offset, const void *mask
             *m = static_cast<const T *>(mask), *go = static_cast<const T *>(grad_out);
     T *goff = static_cast<T *>(grad_offset), *gmsk = static_cast<T *>(grad_mask);
     const bool k33 = q.kh == 3 && q.kw == 3;
+    const char *pe = std::getenv("DCNV3_BWD_PERSIST");   // development knob: 0 = one tile per CTA
+    if (k33 && !(pe && pe[0] == '0') && (long long)tp.tiles_x * tiles_y * q.G * q.N < (1LL << 31)) {
+        static int num_sms = 0;
+        if (num_sms == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        }
+        PersistParams pp;
+        pp.ox_rel = tp.ox_rel; pp.oy_rel = tp.oy_rel; pp.tiles_x = tp.tiles_x;
+        pp.tiles_xy = tp.tiles_x * tiles_y;
+        pp.total_tiles = pp.tiles_xy * q.G * q.N;
+        const int ctas = std::min(pp.total_tiles, 2 * num_sms);   // 2 resident CTAs per SM (107 KB each)
+        cudaFuncSetAttribute(bwd_mma_persistent<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PLayout::total);
+        bwd_mma_persistent<T><<<ctas, kThreads, PLayout::total, stream>>>(tmap, v, o, m, go, gv_acc, goff, gmsk, q, pp);
+        *err = cudaGetLastError();
+        return true;
+    }
     if (k33) cudaFuncSetAttribute(bwd_mma<T, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     else cudaFuncSetAttribute(bwd_mma<T, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     for (int n0 = 0; n0 < q.N; n0 += 65535) {
