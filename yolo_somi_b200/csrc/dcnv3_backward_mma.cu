@@ -212,23 +212,34 @@ __device__ __forceinline__ void band_mma(unsigned char *abuf, const unsigned cha
     }
     const int r_in = (lane & 7) + ((lane >> 3) & 1) * 8;   // row inside an m-tile this lane addresses
     const int kc_in = lane >> 4;                            // 16-byte k chunk (0/1) inside a k-step
-#pragma unroll 4
-    for (int mt = 0; mt < kMTiles; ++mt) {
-        float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+    // A fragments are fetched one m-tile ahead of the HMMAs that consume them
+    auto load_a = [&](int mt, uint32_t (&af)[2][4]) {
         const int row = mt * 16 + r_in;
+        const uint32_t sw = ((uint32_t)row >> 1) & 3u;
+        ldmatrix_x4(af[0], a_base + (uint32_t)row * 64u + (((uint32_t)kc_in ^ sw) << 4));
+        ldmatrix_x4(af[1], a_base + (uint32_t)row * 64u + (((uint32_t)(2 + kc_in) ^ sw) << 4));
+    };
+    uint32_t cur[2][4], nxt[2][4];
+    load_a(0, cur);
+#pragma unroll
+    for (int mt = 0; mt < kMTiles; ++mt) {
+        if (mt + 1 < kMTiles) load_a(mt + 1, nxt);
+        float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
-            uint32_t af[4];
-            const uint32_t chunk = (uint32_t)(ks * 2 + kc_in) ^ (((uint32_t)row >> 1) & 3u);
-            ldmatrix_x4(af, a_base + (uint32_t)row * 64u + (chunk << 4));
-            mma16816(acc0, af, bf[ks][0], bf[ks][1], T());
-            mma16816(acc1, af, bf[ks][2], bf[ks][3], T());
+            mma16816(acc0, cur[ks], bf[ks][0], bf[ks][1], T());
+            mma16816(acc1, cur[ks], bf[ks][2], bf[ks][3], T());
         }
+        // the m-tile's 16 rows are dead now (their fragments are in registers): overwrite them
         float *r0 = reinterpret_cast<float *>(abuf) + (size_t)(mt * 16 + (lane >> 2)) * kCh + 2 * (lane & 3);
         *reinterpret_cast<float2 *>(r0) = make_float2(acc0[0], acc0[1]);
         *reinterpret_cast<float2 *>(r0 + 8) = make_float2(acc1[0], acc1[1]);
         *reinterpret_cast<float2 *>(r0 + 8 * kCh) = make_float2(acc0[2], acc0[3]);
         *reinterpret_cast<float2 *>(r0 + 8 * kCh + 8) = make_float2(acc1[2], acc1[3]);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) cur[ks][e] = nxt[ks][e];
     }
 }
 
