@@ -257,6 +257,8 @@ __device__ __forceinline__ void flush_bands(float *bands, float *gimg /* accumul
     const bool x_ok = (unsigned)x < (unsigned)W;
     float *col = bands + wx * kCh + piece * 4;                       // (band 0, row 0) of this column
     float *dst = gimg + (ptrdiff_t)oy * row_stride + (ptrdiff_t)x * C + piece * 4;
+    // pass 1: loads, sums and reductions only -- no store in between, so the 60 LDS.128 of a
+    // column are independent and pipeline (interleaving the clearing stores serialised them)
 #pragma unroll
     for (int wy = 0; wy < kWinH; ++wy) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -264,15 +266,22 @@ __device__ __forceinline__ void flush_bands(float *bands, float *gimg /* accumul
         for (int w = 0; w < kWarps; ++w) {
             const int by = wy - w * kRowsPerWarp;                    // compile-time after unrolling
             if (by >= 0 && by < kBandH) {
-                float4 *src = reinterpret_cast<float4 *>(col + ((size_t)w * kBufCells + by * kWinW) * kCh);
-                const float4 t = *src;
-                if (ZERO) *src = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 t = *reinterpret_cast<const float4 *>(col + ((size_t)w * kBufCells + by * kWinW) * kCh);
                 v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
             }
         }
         if (x_ok && (unsigned)(oy + wy) < (unsigned)H && (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f))
             red_add4(dst, v);
         dst += row_stride;
+    }
+    // pass 2: clear what was read
+    if (ZERO) {
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w)
+#pragma unroll
+            for (int by = 0; by < kBandH; ++by)
+                if (by + w * kRowsPerWarp < kWinH)
+                    *reinterpret_cast<float4 *>(col + ((size_t)w * kBufCells + by * kWinW) * kCh) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
