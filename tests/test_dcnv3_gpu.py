@@ -117,11 +117,14 @@ _TILE_CASES = [
     cases.Case("tile_k5", N=1, H=20, W=27, G=2, gc=16, kh=5, kw=5, ph=2, pw=2, seed=204),
     cases.Case("tile_dil2", N=1, H=19, W=23, G=2, gc=16, ph=2, pw=2, dh=2, dw=2, seed=205),
     cases.Case("tile_gc32_two_slices", N=1, H=18, W=20, G=2, gc=32, seed=206),
+    # the register-accumulator strip backward: no padding (Ho = H-2), sigma != 1, odd group count
+    cases.Case("tile_pad0_sigma075", N=2, H=30, W=41, G=3, gc=16, ph=0, pw=0, sigma=0.75, seed=207),
+    cases.Case("tile_pad2_sigma12", N=1, H=35, W=33, G=2, gc=16, ph=2, pw=2, sigma=1.2, seed=208),
 ]
 
 
 @pytest.mark.parametrize("fwd", ["default", "mma"])
-@pytest.mark.parametrize("bwd", ["default", "tile", "scatter", "mma2"])
+@pytest.mark.parametrize("bwd", ["default", "mma", "tile", "scatter", "mma2"])
 @pytest.mark.parametrize("spread", [1.0, 4.0], ids=["near", "far"])
 @pytest.mark.parametrize("case", _TILE_CASES, ids=lambda c: c.name)
 def test_tiled_kernels_vs_oracle(case, spread, bwd, fwd, monkeypatch):

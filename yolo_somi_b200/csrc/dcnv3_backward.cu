@@ -460,7 +460,8 @@ static cudaError_t backward_typed(const void *value, const void *offset, const v
         float *acc = reinterpret_cast<float *>(static_cast<char *>(workspace) + kWorkspaceHeader);
         if ((err = cudaMemsetAsync(acc, 0, plane * sizeof(float), stream)) != cudaSuccess) return err;
         const int dtype_tag = std::is_same<T, __half>::value ? 1 : 2;
-        if (!(vec_ok && (try_launch_backward_mma2(value, offset, mask, grad_out, acc, grad_offset, grad_mask, q, dtype_tag, stream, &err) ||
+        if (!(vec_ok && (try_launch_backward_strip(value, offset, mask, grad_out, acc, grad_offset, grad_mask, q, dtype_tag, stream, &err) ||
+                         try_launch_backward_mma2(value, offset, mask, grad_out, acc, grad_offset, grad_mask, q, dtype_tag, stream, &err) ||
                          try_launch_backward_mma(value, offset, mask, grad_out, acc, grad_offset, grad_mask, q, dtype_tag, stream, &err) ||
                          try_launch_backward_tile(value, offset, mask, grad_out, acc, grad_offset, grad_mask, q, dtype_tag, stream, &err))))
             err = launch_scatter<T>(v, o, m, go, AccumF32{acc}, nullptr, goff, gmsk, q, vec_ok, stream);

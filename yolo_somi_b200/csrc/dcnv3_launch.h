@@ -31,6 +31,12 @@ bool try_launch_backward_mma(const void *value, const void *offset, const void *
                              const void *grad_out, float *gv_acc, void *grad_offset, void *grad_mask,
                              const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err);
 
+// tensor-core backward with register-resident accumulators (dcnv3_backward_strip.cu): 16-bit I/O,
+// group_channels == 16, 3x3 / stride 1 / dilation 1
+bool try_launch_backward_strip(const void *value, const void *offset, const void *mask,
+                               const void *grad_out, float *gv_acc, void *grad_offset, void *grad_mask,
+                               const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err);
+
 bool try_launch_backward_mma2(const void *value, const void *offset, const void *mask,
                               const void *grad_out, float *gv_acc, void *grad_offset, void *grad_mask,
                               const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err);
