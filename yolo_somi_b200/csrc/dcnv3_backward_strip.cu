@@ -139,26 +139,30 @@ __device__ __forceinline__ uint32_t a_elem_off(int cell, int pixel) {
     return (uint32_t)cell * 64u + ((((uint32_t)pixel >> 3) ^ (((uint32_t)cell >> 1) & 3u)) << 4) + (((uint32_t)pixel & 7u) << 1);
 }
 
-template <typename T> struct Ctx {
+// ------------------------------------------------------------------------------------------------
+// Rare paths, kept out of line so that the hot loop stays small (instruction cache) and is not
+// register-allocated for them.  Everything they need that changes once per tile lives in a
+// per-thread context in local memory; per-step values come as arguments.
+template <typename T> struct SlowCtx {
     int H, W, C, row_stride;
     int oy, ox;                      // window origin in the map
-    int band_row0, band_col0;        // band origin of this warp / step in window coordinates
-    int j, half, lane;
+    int lane, j, half;
     uint32_t win_addr;               // shared address of the window (+ half * 16)
     unsigned char *abuf;             // this warp's A tile
     unsigned char *spill;            // this warp's spill list
+    const unsigned char *s_gout;     // this warp's staged grad_out [32][32 B]
     const T *img;                    // value + (n, 0, 0, ch0)
     float *gv_img;                   // fp32 accumulator + (n, 0, 0, ch0)
-    uint4 gq_a, gq_b;                // upstream gradient of the pixel: chunk `half` / the other chunk
 };
 
-// coefficient x grad_out of one lane's pixel straight to the global accumulator (rare paths)
+// coefficient x grad_out of one lane's pixel straight to the global accumulator
 template <typename T>
-__device__ __forceinline__ void direct_scatter(const Ctx<T> &c, const int (&at)[4], const float (&cf)[4]) {
+__device__ __forceinline__ void direct_scatter(const SlowCtx<T> &c, const uint4 &gq_a, const uint4 &gq_b,
+                                               const int (&at)[4], const float (&cf)[4]) {
     constexpr int E = 8;
     float ga[E], gb[E];
-    unpack<T>(c.gq_a, ga);
-    unpack<T>(c.gq_b, gb);
+    unpack<T>(gq_a, ga);
+    unpack<T>(gq_b, gb);
     const int ea = c.half * E, eb = (c.half ^ 1) * E;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
@@ -173,15 +177,18 @@ __device__ __forceinline__ void direct_scatter(const Ctx<T> &c, const int (&at)[
     }
 }
 
-// One sampling point: channel sums (grad_mask, grad_offset / sigma) and the point's four
-// coefficients into the A tile / the spill list / the global accumulator.
+// One sampling point, any location: channel sums (grad_mask, grad_offset / sigma) and the point's
+// four coefficients into the A tile / the spill list / the global accumulator.
 template <typename T>
-__device__ __forceinline__ void process_point(const Ctx<T> &c, float loc_h, float loc_w, float m,
-                                              float &gm, float &gx, float &gy) {
-    gm = gx = gy = 0.f;
+__device__ __noinline__ void slow_point(const SlowCtx<T> *cp, int band_row0, int band_col0, float loc_h,
+                                        float loc_w, float m, float *res /* gm, gx, gy */) {
+    const SlowCtx<T> &c = *cp;
+    res[0] = res[1] = res[2] = 0.f;
     // range test of the reference (dcnv3_im2col_cuda.cuh:262-263); also rejects NaN
     const bool inside = loc_h > -1.f && loc_w > -1.f && loc_h < (float)c.H && loc_w < (float)c.W;
     if (!inside) return;
+    const uint4 gq_a = *reinterpret_cast<const uint4 *>(c.s_gout + c.lane * kSliceBytes + c.half * 16);
+    const uint4 gq_b = *reinterpret_cast<const uint4 *>(c.s_gout + c.lane * kSliceBytes + (c.half ^ 1) * 16);
     const float fh = floorf(loc_h), fw = floorf(loc_w);
     const float lh = loc_h - fh, lw = loc_w - fw, hh = 1.f - lh, hw = 1.f - lw;
     const int h0 = (int)fh, w0 = (int)fw;
@@ -197,17 +204,15 @@ __device__ __forceinline__ void process_point(const Ctx<T> &c, float loc_h, floa
         for (int t = 0; t < 4; ++t) {
             const uint32_t a = tl + o[t];
             const uint4 qa = lds128(a), qb = lds128(a ^ 16u);
-            dr[t] = dot<T>(c.gq_a, qa, 0.f) + dot<T>(c.gq_b, qb, 0.f);
+            dr[t] = dot<T>(gq_a, qa, 0.f) + dot<T>(gq_b, qb, 0.f);
         }
         rotate4(dr, (4 - rho) & 3);   // back to corner order TL, TR, BL, BR
         const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
-        gm = w1 * dr[0] + w2 * dr[1] + w3 * dr[2] + w4 * dr[3];
-        gx = m * (hh * (dr[1] - dr[0]) + lh * (dr[3] - dr[2]));
-        gy = m * (hw * (dr[2] - dr[0]) + lw * (dr[3] - dr[1]));
-        const int br = hwin - c.band_row0, bc = wwin - c.band_col0;
+        res[0] = w1 * dr[0] + w2 * dr[1] + w3 * dr[2] + w4 * dr[3];
+        res[1] = m * (hh * (dr[1] - dr[0]) + lh * (dr[3] - dr[2]));
+        res[2] = m * (hw * (dr[2] - dr[0]) + lw * (dr[3] - dr[1]));
+        const int br = hwin - band_row0, bc = wwin - band_col0;
         if ((unsigned)br < (unsigned)(kBandH - 1) && (unsigned)bc < (unsigned)(kBandW - 1)) {
-            // this pixel's column of A (thread-exclusive; the four corner cells are distinct:
-            // read all four, then write all four)
             const int cb = br * kBandW + bc;
             T *e0 = reinterpret_cast<T *>(c.abuf + a_elem_off(cb, c.lane));
             T *e1 = reinterpret_cast<T *>(c.abuf + a_elem_off(cb + 1, c.lane));
@@ -233,11 +238,11 @@ __device__ __forceinline__ void process_point(const Ctx<T> &c, float loc_h, floa
                                    (h0 + 1) * c.row_stride + w0 * c.C, (h0 + 1) * c.row_stride + (w0 + 1) * c.C};
                 const float cg[4] = {top && lef ? cf[0] : 0.f, top && rig ? cf[1] : 0.f,
                                      bot && lef ? cf[2] : 0.f, bot && rig ? cf[3] : 0.f};
-                direct_scatter<T>(c, at, cg);
+                direct_scatter<T>(c, gq_a, gq_b, at, cg);
             }
         }
     } else {
-        // ---- fallback: clamped global reads, direct reductions
+        // ---- outside the window: clamped global reads, direct reductions
         constexpr int E = 8;
         const ClampedTap ct = make_clamped_tap(loc_h, loc_w, c.H, c.W);
         const int r_lo = ct.row_lo * c.row_stride, r_hi = ct.row_hi * c.row_stride;
@@ -249,40 +254,231 @@ __device__ __forceinline__ void process_point(const Ctx<T> &c, float loc_h, floa
         for (int t = 0; t < 4; ++t) {
             const uint4 qa = __ldg(reinterpret_cast<const uint4 *>(c.img + at[t] + ea));
             const uint4 qb = __ldg(reinterpret_cast<const uint4 *>(c.img + at[t] + eb));
-            dk[t] = dot<T>(c.gq_a, qa, 0.f) + dot<T>(c.gq_b, qb, 0.f);
+            dk[t] = dot<T>(gq_a, qa, 0.f) + dot<T>(gq_b, qb, 0.f);
         }
         const float fy_lo = ct.hh * ct.top, fy_hi = ct.lh * ct.bot;
         const float fx_lo = ct.hw * ct.lef, fx_hi = ct.lw * ct.rig;
         const float wk[4] = {fy_lo * fx_lo, fy_lo * fx_hi, fy_hi * fx_lo, fy_hi * fx_hi};
-        gm = wk[0] * dk[0] + wk[1] * dk[1] + wk[2] * dk[2] + wk[3] * dk[3];
-        gx = m * (fy_lo * (ct.rig * dk[1] - ct.lef * dk[0]) + fy_hi * (ct.rig * dk[3] - ct.lef * dk[2]));
-        gy = m * (fx_lo * (ct.bot * dk[2] - ct.top * dk[0]) + fx_hi * (ct.bot * dk[3] - ct.top * dk[1]));
+        res[0] = wk[0] * dk[0] + wk[1] * dk[1] + wk[2] * dk[2] + wk[3] * dk[3];
+        res[1] = m * (fy_lo * (ct.rig * dk[1] - ct.lef * dk[0]) + fy_hi * (ct.rig * dk[3] - ct.lef * dk[2]));
+        res[2] = m * (fx_lo * (ct.bot * dk[2] - ct.top * dk[0]) + fx_hi * (ct.bot * dk[3] - ct.top * dk[1]));
         const float cf[4] = {wk[0] * m, wk[1] * m, wk[2] * m, wk[3] * m};
-        direct_scatter<T>(c, at, cf);
+        direct_scatter<T>(c, gq_a, gq_b, at, cf);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Hot path.  Per-step values of one lane; coordinates are BAND-relative (the band origin is folded
+// into the anchors), so one float range test decides "window and band hit" and the zero fill of
+// the TMA window stands in for the reference's range test (all four corners of a point that
+// fails it lie outside the map and read zeros).
+template <typename T> struct StepCtx {
+    uint32_t win_b;        // shared address of the band's first window cell (+ half * 16)
+    uint32_t a_lane;       // shared address of the A tile + (lane & 7) * 2
+    uint32_t chunk;        // lane >> 3: this pixel's 16-byte chunk of an A row
+    int jq;                // ((lane & 7) >> 1) - (band_col0 + 2 * band_row0): rotation phase
+    float bw, bh;          // band-relative anchors of the pixel
+    float sigma;
+    uint32_t s_off_lane;   // shared address of this lane's 9 (dx, dy) pairs / results
+    uint32_t s_msk_lane;   // shared address of this lane's 9 masks / results
+    uint4 gq_a, gq_b;      // upstream gradient of the pixel: chunk `half` / the other chunk
+};
+
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
+
+// NP points p0 .. p0+NP-1 of this lane's pixel at once (independent instruction streams for the
+// scheduler).  Returns false, having done nothing, if any of them leaves the band.
+template <typename T, int NP>
+__device__ __forceinline__ bool points_fast(const StepCtx<T> &c, int p0) {
+    float ub[NP], vb[NP], m[NP];
+    bool ok = true;
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        const int p = p0 + q, i = (p * 11) >> 5, jj = p - 3 * i;
+        const float2 d = unpack2(lds32(c.s_off_lane + p * 4), T());
+        m[q] = f32_of((uint16_t)lds16(c.s_msk_lane + p * 2), T());
+        ub[q] = c.bw + ((float)i + d.x) * c.sigma;
+        vb[q] = c.bh + ((float)jj + d.y) * c.sigma;
+        // 0 <= x < limit on the float's bit pattern: negative values and NaN compare as large unsigned
+        ok = ok && __float_as_uint(ub[q]) < __float_as_uint((float)(kBandW - 1)) &&
+             __float_as_uint(vb[q]) < __float_as_uint((float)(kBandH - 1));
+    }
+    if (!ok) return false;
+
+    float lh[NP], lw[NP];
+    int cb[NP], rho[NP];
+    uint4 qa[NP][4], qb[NP][4];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        const float fw = floorf(ub[q]), fh = floorf(vb[q]);
+        lw[q] = ub[q] - fw;
+        lh[q] = vb[q] - fh;
+        const int bc = (int)fw, br = (int)fh;
+        cb[q] = br * kBandW + bc;
+        rho[q] = (c.jq - (bc + 2 * br)) & 3;
+        int o[4] = {0, kSliceBytes, kWinW * kSliceBytes, kWinW * kSliceBytes + kSliceBytes};
+        rotate4(o, rho[q]);
+        const uint32_t tl = c.win_b + (uint32_t)(br * kWinW + bc) * kSliceBytes;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            qa[q][t] = lds128(tl + o[t]);
+            qb[q][t] = lds128((tl + o[t]) ^ 16u);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        float dr[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) dr[t] = dot<T>(c.gq_a, qa[q][t], 0.f) + dot<T>(c.gq_b, qb[q][t], 0.f);
+        rotate4(dr, (4 - rho[q]) & 3);   // back to corner order TL, TR, BL, BR
+        const float hh = 1.f - lh[q], hw = 1.f - lw[q];
+        const float gm = hh * (hw * dr[0] + lw[q] * dr[1]) + lh[q] * (hw * dr[2] + lw[q] * dr[3]);
+        const float gx = m[q] * (hh * (dr[1] - dr[0]) + lh[q] * (dr[3] - dr[2]));
+        const float gy = m[q] * (hw * (dr[2] - dr[0]) + lw[q] * (dr[3] - dr[1]));
+        const int p = p0 + q;
+        sts32(c.s_off_lane + p * 4, pack2(c.sigma * gx, c.sigma * gy, T()));
+        sts16(c.s_msk_lane + p * 2, bits16(gm, T()));
+    }
+    // A build: this pixel's column (thread-exclusive).  The four corner cells of a point are
+    // distinct (read all four, then write all four); points go one after the other because two
+    // points of a pixel may share a cell.  Rows cb and cb+16 have the same swizzle.
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        const uint32_t c0 = (uint32_t)cb[q], c1 = c0 + 1u;
+        const uint32_t e0 = c.a_lane + c0 * 64u + ((c.chunk ^ ((c0 >> 1) & 3u)) << 4);
+        const uint32_t e1 = c.a_lane + c1 * 64u + ((c.chunk ^ ((c1 >> 1) & 3u)) << 4);
+        const float hm = (1.f - lh[q]) * m[q], lm = lh[q] * m[q], hw = 1.f - lw[q];
+        const float a0 = f32_of((uint16_t)lds16(e0), T()), a1 = f32_of((uint16_t)lds16(e1), T());
+        const float a2 = f32_of((uint16_t)lds16(e0 + kBandW * 64), T()), a3 = f32_of((uint16_t)lds16(e1 + kBandW * 64), T());
+        sts16(e0, bits16(a0 + hm * hw, T()));
+        sts16(e1, bits16(a1 + hm * lw[q], T()));
+        sts16(e0 + kBandW * 64, bits16(a2 + lm * hw, T()));
+        sts16(e1 + kBandW * 64, bits16(a3 + lm * lw[q], T()));
+    }
+    return true;
 }
 
 // Reductions of NR finished band rows, straight from the accumulator fragments:
 // lane (gid, tig) holds cells gid / gid+8 of every row and channels 2tig,2tig+1 (+8).
+// p = accumulator element (row my0, column mx0 + gid, channel 2 tig); ok0 / ok1: column in the map.
 template <int NR>
-__device__ __forceinline__ void flush_rows(const float (&acc)[kMTiles][2][4], float *gv_img, int my0, int mx0,
-                                           int H, int W, int row_stride, int C, int lane) {
-    const int gid = lane >> 2, tig = lane & 3;
+__device__ __forceinline__ void flush_rows(const float (&acc)[kMTiles][2][4], float *p, int my0, int H,
+                                           int row_stride, int C, bool ok0, bool ok1) {
+    float *p1 = p + 8 * C;
 #pragma unroll
     for (int b = 0; b < NR; ++b) {
-        const int my = my0 + b;
-        if ((unsigned)my < (unsigned)H) {
+        const bool okr = (unsigned)(my0 + b) < (unsigned)H;
+        if (okr && ok0) {
+            red_add2(p, acc[b][0][0], acc[b][0][1]);
+            red_add2(p + 8, acc[b][1][0], acc[b][1][1]);
+        }
+        if (okr && ok1) {
+            red_add2(p1, acc[b][0][2], acc[b][0][3]);
+            red_add2(p1 + 8, acc[b][1][2], acc[b][1][3]);
+        }
+        p += row_stride;
+        p1 += row_stride;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Staging I/O of one warp, out of line (one copy of the code, called once per step): write the
+// finished step's grad_offset / grad_mask out of the staging buffer, then request the next step's
+// offsets / masks / grad_out with cp.async (no registers held while they are in flight).
+// Lane <-> (pixel column lane>>2, quarter lane&3): a lane moves words quarter, quarter+4 (and 8)
+// of its pixel's 9-word run in each of the patch's 4 rows, so every address is one per-lane base
+// plus a per-row stride plus an immediate, and a warp access covers 8 runs of 16 contiguous bytes.
+template <typename T> struct IoCtx {   // kernel-constant, one copy per CTA in shared memory
+    const T *offset, *mask, *grad_out;
+    T *grad_offset, *grad_mask;
+    const unsigned char *mask_end;
+    int Wo, Ho, G, C;
+};
+
+template <typename T>
+__device__ __noinline__ void stage_io(const IoCtx<T> *io_s, uint32_t sa /* staging buffer */, size_t pix_w, int g_w,
+                                      int wb_w, int hb_w, int do_w, size_t pix_p, int g_p, int wb_p, int hb_p,
+                                      int do_p) {
+    const IoCtx<T> io = *io_s;     // registers from here on (the asm statements below clobber memory)
+    const int lane = threadIdx.x & 31, col = lane >> 2, qt = lane & 3;
+    const int Wo = io.Wo, Ho = io.Ho, G9 = io.G * kP;
+    const int rowstep = Wo * G9;   // elements between vertically adjacent pixels of one group
+    if (do_w) {
+        const size_t e0 = (pix_w * io.G + g_w) * kP + (size_t)col * G9;   // first element of this lane's run, row 0
+        uint32_t *ob = reinterpret_cast<uint32_t *>(io.grad_offset) + e0 + qt;
+        uint16_t *mb = reinterpret_cast<uint16_t *>(io.grad_mask) + e0 + qt;
+        unsigned par = (unsigned)e0 & 1u;                                   // misalignment of the staged mask run
+        uint32_t so = sa + kStageOff + (col * kP + qt) * 4;
+        uint32_t sm = sa + kStageMsk + col * (kMskWords * 4) + qt * 2;
+        const bool okc = wb_w + col < Wo;
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                const int mx = mx0 + gid + 8 * hf;
-                if ((unsigned)mx < (unsigned)W) {
-                    float *p = gv_img + (ptrdiff_t)my * row_stride + (ptrdiff_t)mx * C + 2 * tig;
-                    red_add2(p, acc[b][0][2 * hf], acc[b][0][2 * hf + 1]);
-                    red_add2(p + 8, acc[b][1][2 * hf], acc[b][1][2 * hf + 1]);
+        for (int row = 0; row < kPatchH; ++row) {
+            if (okc && hb_w + row < Ho) {
+                ob[0] = lds32(so);
+                ob[4] = lds32(so + 16);
+                const uint32_t smr = sm + par * 2;
+                mb[0] = (uint16_t)lds16(smr);
+                mb[4] = (uint16_t)lds16(smr + 8);
+                if (qt == 0) {
+                    ob[8] = lds32(so + 32);
+                    mb[8] = (uint16_t)lds16(smr + 16);
                 }
             }
+            ob += rowstep;
+            mb += rowstep;
+            par = (par + (unsigned)rowstep) & 1u;
+            so += kStripW * kP * 4;
+            sm += kStripW * kMskWords * 4;
         }
     }
+    __syncwarp();   // every lane is done reading the staging buffer (gather results, B fragments)
+    if (do_p) {
+        const size_t e0 = (pix_p * io.G + g_p) * kP + (size_t)col * G9;
+        const uint32_t *os = reinterpret_cast<const uint32_t *>(io.offset) + e0 + qt;
+        const unsigned char *ms = reinterpret_cast<const unsigned char *>(io.mask) + e0 * 2;
+        uint32_t so = sa + kStageOff + (col * kP + qt) * 4;
+        uint32_t sm = sa + kStageMsk + col * (kMskWords * 4) + qt * 4;
+        const bool okc = wb_p + col < Wo;
+#pragma unroll
+        for (int row = 0; row < kPatchH; ++row) {
+            if (okc && hb_p + row < Ho) {
+                cp_async4(so, os, 4);
+                cp_async4(so + 16, os + 4, 4);
+                // the 18-byte mask run is staged from its enclosing 4-byte words (5 of them)
+                const unsigned char *al = ms - ((uintptr_t)ms & 2u) + qt * 4;
+                cp_async4(sm, al, al + 4 <= io.mask_end ? 4 : 2);
+                if (qt == 0) {
+                    cp_async4(so + 32, os + 8, 4);
+                    cp_async4(sm + 16, al + 16, al + 20 <= io.mask_end ? 4 : 2);
+                }
+            }
+            os += rowstep;
+            ms += (size_t)rowstep * 2;
+            so += kStripW * kP * 4;
+            sm += kStripW * kMskWords * 4;
+        }
+        // grad_out: lane <-> (pixel lane>>1 of 16, 16-byte chunk lane&1), two rounds; zero fill for
+        // pixels outside the map (their A columns are zero, the product must not see NaN bits)
+#pragma unroll
+        for (int r2 = 0; r2 < 2; ++r2) {
+            const int px = r2 * 16 + (lane >> 1), row = px >> 3, c8 = px & 7, ck = lane & 1;
+            const bool ok = wb_p + c8 < Wo && hb_p + row < Ho;
+            const T *gs = io.grad_out + (pix_p + (size_t)(row * Wo + c8)) * io.C + g_p * kCh + ck * 8;
+            cp_async16(sa + kStageGout + px * kSliceBytes + ck * 16, ok ? gs : io.grad_out, ok ? 16 : 0);
+        }
+    }
+    cp_async_commit();
 }
 
 template <typename T>
@@ -298,54 +494,28 @@ bwd_strip(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
     unsigned char *abuf = smem + kWinBytes + warp * kABytes;
     unsigned char *stage = smem + kWinBytes + kWarps * kABytes + warp * kStageBytes;
     unsigned char *spill = smem + kWinBytes + kWarps * (kABytes + kStageBytes) + warp * kSpillBytes;
-    uint32_t *s_off = reinterpret_cast<uint32_t *>(stage + kStageOff);
-    uint16_t *s_msk = reinterpret_cast<uint16_t *>(stage + kStageMsk);
-    unsigned char *s_gout = stage + kStageGout;
     const uint32_t stage_addr = smem_u32(stage);
     const uint32_t a_base = smem_u32(abuf);
 
     const int C = q.G * q.gc, row_stride = q.W * C;
-    const int j = lane & 7, half = j & 1;
+    const int half = lane & 1;
     const int px_x = lane & 7, px_y = lane >> 3;      // this lane's pixel inside the 8x4 patch
 
     int t = blockIdx.x;
     if (t >= pp.total_tiles) return;
     TileAt cur = decode_tile(t, q, pp);
 
-    // cp.async staging of one step's offsets / masks / grad_out for this warp (no registers held)
-    auto prefetch = [&](const TileAt &a, int s) {
-        const size_t img_pix = (size_t)a.n * q.Ho * q.Wo;
-        const int wb = a.wo0 + warp * kStripW, hb = a.ho0 + s * kPatchH;
-        const uint32_t *obase = reinterpret_cast<const uint32_t *>(offset);
-        const unsigned char *mbase = reinterpret_cast<const unsigned char *>(mask);
-#pragma unroll
-        for (int it = 0; it < kP; ++it) {
-            const int idx = lane + it * 32, px = idx / kP, p = idx - px * kP;
-            const int w = wb + (px & 7), h = hb + (px >> 3);
-            const bool ok = w < q.Wo && h < q.Ho;
-            const size_t e0 = ok ? ((img_pix + (size_t)h * q.Wo + w) * q.G + a.g) * kP + p : 0;
-            cp_async4(stage_addr + kStageOff + idx * 4, obase + e0, ok ? 4 : 0);
-        }
-#pragma unroll
-        for (int it = 0; it < 5; ++it) {
-            const int idx = lane + it * 32, px = idx / 5, wd = idx - px * 5;
-            const int w = wb + (px & 7), h = hb + (px >> 3);
-            const bool ok = w < q.Wo && h < q.Ho;
-            const unsigned long long byte0 = ok ? (((img_pix + (size_t)h * q.Wo + w) * q.G + a.g) * kP * 2ull & ~3ull) + wd * 4 : 0ull;
-            const long long rem = (long long)(pp.mask_bytes - byte0);
-            const int nb = ok ? (int)(rem < 4 ? (rem < 0 ? 0 : rem) : 4) : 0;
-            cp_async4(stage_addr + kStageMsk + (px * kMskWords + wd) * 4, mbase + (nb ? byte0 : 0ull), nb);
-        }
-#pragma unroll
-        for (int it = 0; it < 2; ++it) {
-            const int idx = lane + it * 32, px = idx >> 1, ck = idx & 1;
-            const int w = wb + (px & 7), h = hb + (px >> 3);
-            const bool ok = w < q.Wo && h < q.Ho;
-            const size_t e0 = ok ? (img_pix + (size_t)h * q.Wo + w) * C + a.g * q.gc + ck * 8 : 0;
-            cp_async16(stage_addr + kStageGout + px * kSliceBytes + ck * 16, grad_out + e0, ok ? 16 : 0);
-        }
-        cp_async_commit();
+    // pixel index of the first pixel of a step's patch
+    auto patch_pix = [&](const TileAt &a, int s) -> size_t {
+        return ((size_t)a.n * q.Ho + (a.ho0 + s * kPatchH)) * q.Wo + (a.wo0 + warp * kStripW);
     };
+    __shared__ __align__(16) IoCtx<T> io;
+    if (tid == 0) {
+        io.offset = offset; io.mask = mask; io.grad_out = grad_out; io.grad_offset = grad_offset; io.grad_mask = grad_mask;
+        io.mask_end = reinterpret_cast<const unsigned char *>(mask) + pp.mask_bytes;
+        io.Wo = q.Wo; io.Ho = q.Ho; io.G = q.G; io.C = C;
+    }
+    __syncthreads();
 
     if (tid == 0) {
         mbar_init(&bar, 1);
@@ -354,13 +524,19 @@ bwd_strip(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
     {   // prologue: zero this warp's A tile and spill counter, request the first staging data
         for (int i = lane; i < kABytes / 16; i += 32) sts128_zero(a_base + i * 16);
         if (lane == 0) *reinterpret_cast<unsigned *>(spill) = 0u;
-        prefetch(cur, 0);
+        stage_io<T>(&io, stage_addr, 0, 0, 0, 0, 0, patch_pix(cur, 0), cur.g, cur.wo0 + warp * kStripW, cur.ho0, 1);
     }
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(&bar, kWinBytes);
         tma_load_4d(win, &tmap, &bar, cur.g * q.gc, cur.ox, cur.oy, cur.n);
     }
+
+    SlowCtx<T> sc;
+    sc.H = q.H; sc.W = q.W; sc.C = C; sc.row_stride = row_stride;
+    sc.lane = lane; sc.j = lane & 7; sc.half = half;
+    sc.win_addr = smem_u32(win) + half * 16;
+    sc.abuf = abuf; sc.spill = spill; sc.s_gout = stage + kStageGout;
 
     float acc[kMTiles][2][4];
 
@@ -369,9 +545,10 @@ bwd_strip(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
         const bool has_next = t_next < pp.total_tiles;
         TileAt nxt = cur;
         if (has_next) nxt = decode_tile(t_next, q, pp);
-        const size_t img_base = (size_t)cur.n * q.H * row_stride + cur.g * q.gc;
-        const size_t img_pix = (size_t)cur.n * q.Ho * q.Wo;
-        float *gv_img = gv_acc + img_base;
+        {
+            const size_t img_base = (size_t)cur.n * q.H * row_stride + cur.g * q.gc;
+            sc.oy = cur.oy; sc.ox = cur.ox; sc.img = value + img_base; sc.gv_img = gv_acc + img_base;
+        }
 
 #pragma unroll
         for (int b = 0; b < kMTiles; ++b)
@@ -384,43 +561,47 @@ bwd_strip(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
 
 #pragma unroll 1
         for (int s = 0; s < kSteps; ++s) {
-            const int wo = cur.wo0 + warp * kStripW + px_x, ho = cur.ho0 + s * kPatchH + px_y;
+            const int wb = cur.wo0 + warp * kStripW, hb = cur.ho0 + s * kPatchH;
+            const int wo = wb + px_x, ho = hb + px_y;
             const bool live = wo < q.Wo && ho < q.Ho;
+            const int band_row0 = pp.byw + s * kPatchH, band_col0 = pp.bxw + warp * kStripW;
+            const size_t pix = patch_pix(cur, s);
             cp_async_wait_all();
             __syncwarp();
 
             // ------------------------------------------------------------ gather + A build
             if (live) {
-                Ctx<T> c;
-                c.H = q.H; c.W = q.W; c.C = C; c.row_stride = row_stride; c.oy = cur.oy; c.ox = cur.ox;
-                c.band_row0 = pp.byw + s * kPatchH; c.band_col0 = pp.bxw + warp * kStripW;
-                c.j = j; c.half = half; c.lane = lane;
-                c.win_addr = smem_u32(win) + half * 16;
-                c.abuf = abuf; c.spill = spill;
-                c.img = value + img_base; c.gv_img = gv_img;
-                c.gq_a = *reinterpret_cast<const uint4 *>(s_gout + lane * kSliceBytes + half * 16);
-                c.gq_b = *reinterpret_cast<const uint4 *>(s_gout + lane * kSliceBytes + (half ^ 1) * 16);
+                StepCtx<T> c;
+                c.win_b = smem_u32(win) + (uint32_t)(band_row0 * kWinW + band_col0) * kSliceBytes + half * 16;
+                c.a_lane = a_base + (lane & 7) * 2;
+                c.chunk = (uint32_t)lane >> 3;
+                c.jq = ((lane & 7) >> 1) - (band_col0 + 2 * band_row0);
                 const float base_w = axis_base(wo, 3, 1, q.pw, 1, q.sigma);
                 const float base_h = axis_base(ho, 3, 1, q.ph, 1, q.sigma);
-                // mask run of this pixel starts at element e0 of the tensor; staged from the
-                // enclosing 4-byte words, so it sits at a 0- or 1-element shift
-                const unsigned sh = (unsigned)((((img_pix + (size_t)ho * q.Wo + wo) * q.G + cur.g) * kP) & 1);
-                uint16_t *mrow = s_msk + lane * (kMskWords * 2) + sh;
+                c.bw = base_w - (float)(cur.ox + band_col0);
+                c.bh = base_h - (float)(cur.oy + band_row0);
+                c.sigma = q.sigma;
+                // the mask run of this pixel was staged from its enclosing 4-byte words: 0/1 element shift
+                const unsigned sh = (unsigned)(((pix + (size_t)(px_y * q.Wo + px_x)) * q.G + cur.g) * kP) & 1u;
+                c.s_off_lane = stage_addr + kStageOff + lane * (kP * 4);
+                c.s_msk_lane = stage_addr + kStageMsk + lane * (kMskWords * 4) + sh * 2;
+                c.gq_a = lds128(stage_addr + kStageGout + lane * kSliceBytes + half * 16);
+                c.gq_b = lds128(stage_addr + kStageGout + lane * kSliceBytes + (half ^ 1) * 16);
+                auto slow = [&](int p) {
+                    const int i = (p * 11) >> 5, jj = p - 3 * i;
+                    const float2 d = unpack2(lds32(c.s_off_lane + p * 4), T());
+                    const float m = f32_of((uint16_t)lds16(c.s_msk_lane + p * 2), T());
+                    float res[3];
+                    slow_point<T>(&sc, band_row0, band_col0, base_h + ((float)jj + d.y) * q.sigma,
+                                  base_w + ((float)i + d.x) * q.sigma, m, res);
+                    sts32(c.s_off_lane + p * 4, pack2(q.sigma * res[1], q.sigma * res[2], T()));
+                    sts16(c.s_msk_lane + p * 2, bits16(res[0], T()));
+                };
 #pragma unroll 1
-                for (int i = 0; i < 3; ++i) {
-#pragma unroll
-                    for (int jj = 0; jj < 3; ++jj) {
-                        const int p = i * 3 + jj;
-                        const float2 d = unpack2(s_off[lane * kP + p], T());
-                        const float m = f32_of(mrow[p], T());
-                        const float loc_w = base_w + ((float)i + d.x) * q.sigma;
-                        const float loc_h = base_h + ((float)jj + d.y) * q.sigma;
-                        float gm, gx, gy;
-                        process_point<T>(c, loc_h, loc_w, m, gm, gx, gy);
-                        s_off[lane * kP + p] = pack2(q.sigma * gx, q.sigma * gy, T());
-                        mrow[p] = bits16(gm, T());
-                    }
+                for (int p = 0; p < kP - 1; p += 2) {
+                    if (!points_fast<T, 2>(c, p)) { slow(p); slow(p + 1); }
                 }
+                if (!points_fast<T, 1>(c, kP - 1)) slow(kP - 1);
             }
             __syncwarp();
 
@@ -434,9 +615,8 @@ bwd_strip(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
                         const int hh = se[e].h0 + (corner >> 1), ww = se[e].w0 + (corner & 1);
                         if ((unsigned)hh < (unsigned)q.H && (unsigned)ww < (unsigned)q.W) {
                             const float cf = se[e].c[corner];
-                            const uint32_t g2 = *reinterpret_cast<const uint32_t *>(s_gout + se[e].lane * kSliceBytes + chp * 2);
-                            const float2 gf = unpack2(g2, T());
-                            if (cf != 0.f) red_add2(gv_img + (ptrdiff_t)hh * row_stride + (ptrdiff_t)ww * C + chp, cf * gf.x, cf * gf.y);
+                            const float2 gf = unpack2(lds32(stage_addr + kStageGout + se[e].lane * kSliceBytes + chp * 2), T());
+                            if (cf != 0.f) red_add2(sc.gv_img + (ptrdiff_t)hh * row_stride + (ptrdiff_t)ww * C + chp, cf * gf.x, cf * gf.y);
                         }
                     }
                     __syncwarp();
@@ -444,33 +624,22 @@ bwd_strip(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
                 }
             }
 
-            // ---- grad_offset / grad_mask of this step: coalesced write-out of the staged results
-            {
-                const int wb = cur.wo0 + warp * kStripW, hb = cur.ho0 + s * kPatchH;
-                uint32_t *ob = reinterpret_cast<uint32_t *>(grad_offset);
-                uint16_t *mb = reinterpret_cast<uint16_t *>(grad_mask);
-#pragma unroll
-                for (int k = 0; k < kP; ++k) {
-                    const int idx = lane + k * 32, px = idx / kP, p = idx - px * kP;
-                    const int w = wb + (px & 7), h = hb + (px >> 3);
-                    if (w < q.Wo && h < q.Ho) {
-                        const size_t e0 = ((img_pix + (size_t)h * q.Wo + w) * q.G + cur.g) * kP;
-                        ob[e0 + p] = s_off[idx];
-                        mb[e0 + p] = s_msk[px * (kMskWords * 2) + (unsigned)(e0 & 1) + p];
-                    }
-                }
-            }
-
-            // ---- B fragments (grad_out of the 32 pixels), then the staging buffer is free
+            // ---- B fragments (grad_out of the 32 pixels)
             uint32_t bf[2][4];   // [k-step][{n0:k0-7, n0:k8-15, n1:k0-7, n1:k8-15}]
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
                 const int px = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-                ldmatrix_x4_trans(bf[ks], smem_u32(s_gout) + px * kSliceBytes + (lane >> 4) * 16);
+                ldmatrix_x4_trans(bf[ks], stage_addr + kStageGout + px * kSliceBytes + (lane >> 4) * 16);
             }
-            __syncwarp();
-            if (s + 1 < kSteps) prefetch(cur, s + 1);
-            else if (has_next) prefetch(nxt, 0);
+
+            // ---- write this step's grad_offset / grad_mask out, request the next step's inputs
+            {
+                const bool in_tile = s + 1 < kSteps;
+                const TileAt &na = in_tile ? cur : nxt;
+                const int ns = in_tile ? s + 1 : 0;
+                stage_io<T>(&io, stage_addr, pix, cur.g, wb, hb, 1, patch_pix(na, ns), na.g, na.wo0 + warp * kStripW,
+                            na.ho0 + ns * kPatchH, in_tile || has_next);
+            }
 
             if (s + 1 == kSteps) {
                 __syncthreads();   // both warps are done with the window
@@ -484,40 +653,46 @@ bwd_strip(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
             // ------------------------------------------------------------ acc += A x grad_out
             {
                 const int r_in = (lane & 7) + ((lane >> 3) & 1) * 8;
-                const int kc_in = lane >> 4;
+                const uint32_t kc_in = (uint32_t)lane >> 4;
+                const uint32_t sw = ((uint32_t)r_in >> 1) & 3u;            // (row >> 1) & 3, row = 16 b + r_in
+                const uint32_t ra0 = a_base + (uint32_t)r_in * 64u + ((kc_in ^ sw) << 4);
+                const uint32_t ra1 = a_base + (uint32_t)r_in * 64u + (((2u + kc_in) ^ sw) << 4);
+                const uint32_t za = a_base + lane * 16;
 #pragma unroll
                 for (int b = 0; b < kMTiles; ++b) {
-                    const int row = b * 16 + r_in;
-                    const uint32_t sw = ((uint32_t)row >> 1) & 3u;
                     uint32_t a0[4], a1[4];
-                    ldmatrix_x4(a0, a_base + (uint32_t)row * 64u + (((uint32_t)kc_in ^ sw) << 4));
-                    ldmatrix_x4(a1, a_base + (uint32_t)row * 64u + (((uint32_t)(2 + kc_in) ^ sw) << 4));
+                    ldmatrix_x4(a0, ra0 + b * 1024);
+                    ldmatrix_x4(a1, ra1 + b * 1024);
                     mma16816(acc[b][0], a0, bf[0][0], bf[0][1], T());
                     mma16816(acc[b][1], a0, bf[0][2], bf[0][3], T());
                     mma16816(acc[b][0], a1, bf[1][0], bf[1][1], T());
                     mma16816(acc[b][1], a1, bf[1][2], bf[1][3], T());
                     // the m-tile is in registers: clear it for the next step
-                    sts128_zero(a_base + b * 1024 + lane * 16);
-                    sts128_zero(a_base + b * 1024 + 512 + lane * 16);
+                    sts128_zero(za + b * 1024);
+                    sts128_zero(za + b * 1024 + 512);
                 }
             }
 
             // ------------------------------------------------------------ finished rows leave
-            const int my0 = cur.oy + pp.byw + s * kPatchH;
-            const int mx0 = cur.ox + pp.bxw + warp * kStripW;
-            if (s + 1 < kSteps) {
-                flush_rows<kPatchH>(acc, gv_img, my0, mx0, q.H, q.W, row_stride, C, lane);
+            {
+                const int gid = lane >> 2, tig = lane & 3;
+                const int my0 = cur.oy + band_row0, mx = cur.ox + band_col0 + gid;
+                float *p0 = sc.gv_img + (ptrdiff_t)my0 * row_stride + (ptrdiff_t)mx * C + 2 * tig;
+                const bool ok0 = (unsigned)mx < (unsigned)q.W, ok1 = (unsigned)(mx + 8) < (unsigned)q.W;
+                if (s + 1 < kSteps) {
+                    flush_rows<kPatchH>(acc, p0, my0, q.H, row_stride, C, ok0, ok1);
 #pragma unroll
-                for (int b = 0; b < kMTiles; ++b)
+                    for (int b = 0; b < kMTiles; ++b)
 #pragma unroll
-                    for (int n = 0; n < 2; ++n)
+                        for (int n = 0; n < 2; ++n)
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            if (b + kPatchH < kMTiles) acc[b][n][e] = acc[b + kPatchH < kMTiles ? b + kPatchH : 0][n][e];
-                            else acc[b][n][e] = 0.f;
-                        }
-            } else {
-                flush_rows<kMTiles>(acc, gv_img, my0, mx0, q.H, q.W, row_stride, C, lane);
+                            for (int e = 0; e < 4; ++e) {
+                                if (b + kPatchH < kMTiles) acc[b][n][e] = acc[b + kPatchH < kMTiles ? b + kPatchH : 0][n][e];
+                                else acc[b][n][e] = 0.f;
+                            }
+                } else {
+                    flush_rows<kMTiles>(acc, p0, my0, q.H, row_stride, C, ok0, ok1);
+                }
             }
         }
         if (!has_next) break;
