@@ -98,6 +98,39 @@ DCNV3_API int dcnv3_backward_sm100(const void *value, const void *offset, const 
                          float offset_scale, int dtype, unsigned flags,
                          void *stream /* cudaStream_t */);
 
+/* ------------------------------------------------------------------------------------------------
+ * Host-buffer pipeline: forward + backward of the core with every tensor in HOST memory.
+ *
+ * In the reference the host<->device traffic of a step is torch's: `imgs.to(device,
+ * non_blocking=True)` (train.py:249) before the model, `.cpu()` / `.item()` reads after it
+ * (train.py:279-282), with the op called in between (functions/dcnv3_func.py:39-43,53-58), all on
+ * one stream, one after the other.  This entry point is what a host-side caller of the DCNv3
+ * core binds instead: the batch is cut into chunks of images (images are independent in forward
+ * and backward, dcnv3_im2col_cuda.cuh:238,247,315-317) and three streams overlap the H2D copy of
+ * chunk c+1, the kernels of chunk c and the D2H copy of chunk c-1 (PCIe is full duplex), across
+ * calls as well: _run() only enqueues, _sync() waits.
+ *
+ *   - host buffers should be page-locked (cudaHostAlloc / torch pin_memory); pageable memory works
+ *     but serialises the copies;
+ *   - the pipeline owns its device buffers (two slots of `chunk_images` images incl. the backward
+ *     scratch), its streams and events; one pipeline per host thread and shape;
+ *   - outputs are complete after _sync() returns 0.
+ */
+typedef struct dcnv3_host_pipeline dcnv3_host_pipeline;
+
+DCNV3_API int dcnv3_host_pipeline_create(dcnv3_host_pipeline **out, int chunk_images,
+                        int H, int W, int G, int gc, int kernel_h, int kernel_w,
+                        int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w,
+                        float offset_scale, int dtype, unsigned flags);
+
+/* forward + backward of N images: h_out, h_grad_value, h_grad_offset, h_grad_mask are written */
+DCNV3_API int dcnv3_host_pipeline_run(dcnv3_host_pipeline *p, const void *h_value, const void *h_offset,
+                        const void *h_mask, const void *h_grad_out, void *h_out, void *h_grad_value,
+                        void *h_grad_offset, void *h_grad_mask, int N);
+
+DCNV3_API int dcnv3_host_pipeline_sync(dcnv3_host_pipeline *p);
+DCNV3_API void dcnv3_host_pipeline_destroy(dcnv3_host_pipeline *p);
+
 #ifdef __cplusplus
 }
 #endif

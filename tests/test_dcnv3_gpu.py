@@ -398,3 +398,51 @@ def test_layer_bf16_autocast_runs_and_is_close():
         y = mod(x)
     assert y.dtype == torch.bfloat16
     assert float((y.float() - ref).abs().max()) <= 0.08 * float(ref.abs().max())
+
+
+# ----------------------------------------------------------------------------- host-buffer pipeline
+@pytest.mark.parametrize("dt", ["bf16", "f32"])
+def test_host_pipeline_matches_device_path(dt):
+    """dcnv3_host_pipeline_* (C ABI, host buffers, chunked over the batch, three streams): same
+    kernels as the device-resident calls, so out / grad_offset / grad_mask are bit-identical and
+    grad_value agrees to its accumulation-order noise; N = 7 with chunks of 3 covers a ragged tail
+    and slot reuse, two runs back to back cover the cross-call pipelining."""
+    import DCNv3
+    from yolo_somi_b200.host_pipeline import DCNv3HostPipeline
+    dtype = TDT[dt]
+    c = cases.Case("pipe", N=7, H=33, W=40, G=4, gc=16, seed=301)
+    v, o, m, g = (torch.as_tensor(a).to(dtype) for a in cases.make_inputs(c))
+    pipe = DCNv3HostPipeline(c.H, c.W, c.G, c.gc, dtype=dtype, chunk_images=3)
+    host_in = [t.contiguous().pin_memory() for t in (v, o, m, g)]
+    sv, so, sm, sy = pipe.shapes(c.N)
+    outs = [[torch.full(shp, 7.0, dtype=dtype).pin_memory() for shp in (sy, sv, so, sm)] for _ in range(2)]
+    pipe.run(*host_in, *outs[0])
+    pipe.run(*host_in, *outs[1])
+    pipe.sync()
+    dv, do, dm, dg = (t.cuda() for t in (v, o, m, g))
+    want_out = DCNv3.dcnv3_forward(dv, do, dm, *c.geom, 256)
+    want = [want_out] + DCNv3.dcnv3_backward(dv, do, dm, *c.geom, dg, 256)
+    torch.cuda.synchronize()
+    for got in outs:
+        assert torch.equal(got[0], want[0].cpu())
+        assert torch.equal(got[2], want[2].cpu()) and torch.equal(got[3], want[3].cpu())
+        a, w = got[1].double().numpy(), want[1].double().cpu().numpy()
+        rms = float(np.sqrt(np.mean(w ** 2)))
+        assert max_abs(a, w) <= (1e-5 if dt == "f32" else 2e-2) * rms
+    pipe.close()
+
+
+def test_host_pipeline_rejects_bad_arguments():
+    from yolo_somi_b200.host_pipeline import DCNv3HostPipeline
+    from yolo_somi_b200._native import DCNv3NativeError
+    with pytest.raises(DCNv3NativeError):
+        DCNv3HostPipeline(0, 8, 2, 16)
+    pipe = DCNv3HostPipeline(8, 8, 2, 16, dtype=torch.float32, chunk_images=2)
+    sv, so, sm, sy = pipe.shapes(2)
+    good = [torch.zeros(s) for s in (sv, so, sm, sy, sy, sv, so, sm)]
+    bad = list(good); bad[1] = torch.zeros(so[:-1] + (so[-1] + 1,))
+    with pytest.raises(RuntimeError):
+        pipe.run(*bad)
+    pipe.run(*good); pipe.sync()      # pageable host memory is accepted
+    assert float(good[4].abs().sum()) == 0.0
+    pipe.close()

@@ -17,7 +17,9 @@ F32, F16, BF16 = 0, 1, 2
 BWD_DETERMINISTIC = 1
 
 EXPORTS = ("dcnv3_sm100_abi_version", "dcnv3_sm100_strerror", "dcnv3_forward_sm100",
-           "dcnv3_backward_workspace_bytes", "dcnv3_backward_sm100")
+           "dcnv3_backward_workspace_bytes", "dcnv3_backward_sm100",
+           "dcnv3_host_pipeline_create", "dcnv3_host_pipeline_run", "dcnv3_host_pipeline_sync",
+           "dcnv3_host_pipeline_destroy")
 
 _lib = None
 
@@ -49,6 +51,14 @@ def load() -> ctypes.CDLL:
     lib.dcnv3_backward_workspace_bytes.argtypes = [c_int] * 6 + [c_u]
     lib.dcnv3_backward_sm100.restype = c_int
     lib.dcnv3_backward_sm100.argtypes = [c_vp] * 8 + [c_sz] + geom + [c_f, c_int, c_u, c_vp]
+    lib.dcnv3_host_pipeline_create.restype = c_int
+    lib.dcnv3_host_pipeline_create.argtypes = [ctypes.POINTER(c_vp)] + [c_int] * 13 + [c_f, c_int, c_u]
+    lib.dcnv3_host_pipeline_run.restype = c_int
+    lib.dcnv3_host_pipeline_run.argtypes = [c_vp] * 9 + [c_int]
+    lib.dcnv3_host_pipeline_sync.restype = c_int
+    lib.dcnv3_host_pipeline_sync.argtypes = [c_vp]
+    lib.dcnv3_host_pipeline_destroy.restype = None
+    lib.dcnv3_host_pipeline_destroy.argtypes = [c_vp]
     got = lib.dcnv3_sm100_abi_version()
     if got != ABI_VERSION:
         raise DCNv3NativeError(f"{LIB_PATH}: ABI version {got}, expected {ABI_VERSION}; rebuild")
