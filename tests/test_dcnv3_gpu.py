@@ -120,10 +120,13 @@ _TILE_CASES = [
     # the register-accumulator strip backward: no padding (Ho = H-2), sigma != 1, odd group count
     cases.Case("tile_pad0_sigma075", N=2, H=30, W=41, G=3, gc=16, ph=0, pw=0, sigma=0.75, seed=207),
     cases.Case("tile_pad2_sigma12", N=1, H=35, W=33, G=2, gc=16, ph=2, pw=2, sigma=1.2, seed=208),
+    # the group-slice forward needs a multiple of 8 groups: partial tiles, two group blocks
+    cases.Case("gs_g16_partial", N=2, H=27, W=21, G=16, gc=16, seed=209),
+    cases.Case("gs_g8_pad0", N=1, H=19, W=34, G=8, gc=16, ph=0, pw=0, sigma=0.8, seed=210),
 ]
 
 
-@pytest.mark.parametrize("fwd", ["default", "mma"])
+@pytest.mark.parametrize("fwd", ["default", "tile", "mma"])
 @pytest.mark.parametrize("bwd", ["default", "mma", "tile", "scatter", "mma2"])
 @pytest.mark.parametrize("spread", [1.0, 4.0], ids=["near", "far"])
 @pytest.mark.parametrize("case", _TILE_CASES, ids=lambda c: c.name)

@@ -205,6 +205,8 @@ static cudaError_t launch_typed(const void *value, const void *offset, const voi
 cudaError_t launch_forward(const void *value, const void *offset, const void *mask, void *out,
                            const Geom &q, int dtype, cudaStream_t stream) {
     cudaError_t err = cudaSuccess;
+    if (try_launch_forward_gs(value, offset, mask, out, q, dtype, fast_weights_requested(), stream, &err))
+        return err;
     if (try_launch_forward_tile(value, offset, mask, out, q, dtype, fast_weights_requested(), stream, &err))
         return err;
     if (try_launch_forward_mma(value, offset, mask, out, q, dtype, stream, &err)) return err;

@@ -16,6 +16,9 @@ cudaError_t launch_forward(const void *value, const void *offset, const void *ma
 bool try_launch_forward_tile(const void *value, const void *offset, const void *mask, void *out,
                              const Geom &q, int dtype, bool fast, cudaStream_t stream, cudaError_t *err);
 bool fast_weights_requested();
+// group-slice forward (dcnv3_forward_gs.cu): 16-bit I/O, group_channels == 16, G % 8 == 0, 3x3 / stride 1
+bool try_launch_forward_gs(const void *value, const void *offset, const void *mask, void *out,
+                           const Geom &q, int dtype, bool fast, cudaStream_t stream, cudaError_t *err);
 // tensor-core forward for 16-bit I/O, group_channels == 16 (dcnv3_forward_mma.cu)
 bool try_launch_forward_mma(const void *value, const void *offset, const void *mask, void *out,
                             const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err);
