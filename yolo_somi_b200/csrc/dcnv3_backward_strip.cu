@@ -46,22 +46,23 @@ constexpr int kWarps = 2;
 constexpr int kTileW = kStripW * kWarps, kTileH = kPatchH * kSteps;   // 16 x 16 output pixels
 constexpr int kThreads = kWarps * 32;
 constexpr int kWinW = 26, kWinH = 26;            // value window (2 mod 4: conflict-free corners)
-constexpr int kBandW = 16, kBandH = 14;          // cells one step of one warp can reach
+constexpr int kBandW = 16, kBandH = 12;          // cells one step of one warp scatters into (taps +- 3 px)
 constexpr int kMTiles = kBandH;                  // one m-tile (16 cells) per band row
 constexpr int kCh = 16, kSliceBytes = 32;
 constexpr int kP = 9;
-constexpr int kSpillCap = 8;
+constexpr int kSpillCap = 32;
 static_assert(kWinW % 4 == 2, "window width must be 2 mod 4");
 
 constexpr int kWinBytes = kWinW * kWinH * kSliceBytes;          // 21632
-constexpr int kABytes = kBandH * kBandW * 64;                   // 14336 per warp
+constexpr int kABytes = kBandH * kBandW * 64;                   // 12288 per warp
 constexpr int kMskWords = 7;                                    // per pixel: 5 words used, odd stride
 constexpr int kStageOff = 0;                                    // [32][9] u32
 constexpr int kStageMsk = kStageOff + 32 * kP * 4;              // [32][7] u32
 constexpr int kStageGout = kStageMsk + 32 * kMskWords * 4;      // [32][32 B]
 constexpr int kStageBytes = kStageGout + 32 * kSliceBytes;      // 3072 per warp
 constexpr int kSpillBytes = 16 + kSpillCap * 32;                // 272 per warp
-constexpr int kSmemBytes = kWinBytes + kWarps * (kABytes + kStageBytes + kSpillBytes);
+constexpr int kIoTblBytes = (kP + 5) * 32 * 4;                  // staging I/O index table, per CTA
+constexpr int kSmemBytes = kWinBytes + kWarps * (kABytes + kStageBytes + kSpillBytes) + kIoTblBytes;
 
 struct Params {
     int ox_rel, oy_rel;      // window origin relative to the tile origin
@@ -177,6 +178,28 @@ __device__ __forceinline__ void direct_scatter(const SlowCtx<T> &c, const uint4 
     }
 }
 
+// A point inside the window whose corner block leaves the band: its four coefficients go to the
+// warp's spill list (or, if that is full, straight to the global accumulator).
+template <typename T>
+__device__ __noinline__ void spill_push(const SlowCtx<T> *cp, int h0, int w0, float c0, float c1, float c2, float c3) {
+    const SlowCtx<T> &c = *cp;
+    unsigned *cnt = reinterpret_cast<unsigned *>(c.spill);
+    const unsigned pos = atomicAdd(cnt, 1u);
+    if (pos < (unsigned)kSpillCap) {
+        SpillEntry *e = reinterpret_cast<SpillEntry *>(c.spill + 16) + pos;
+        e->h0 = h0; e->w0 = w0; e->lane = c.lane; e->pad = 0;
+        e->c[0] = c0; e->c[1] = c1; e->c[2] = c2; e->c[3] = c3;
+    } else {
+        const uint4 gq_a = *reinterpret_cast<const uint4 *>(c.s_gout + c.lane * kSliceBytes + c.half * 16);
+        const uint4 gq_b = *reinterpret_cast<const uint4 *>(c.s_gout + c.lane * kSliceBytes + (c.half ^ 1) * 16);
+        const bool top = h0 >= 0, bot = h0 + 1 < c.H, lef = w0 >= 0, rig = w0 + 1 < c.W;
+        const int at[4] = {h0 * c.row_stride + w0 * c.C, h0 * c.row_stride + (w0 + 1) * c.C,
+                           (h0 + 1) * c.row_stride + w0 * c.C, (h0 + 1) * c.row_stride + (w0 + 1) * c.C};
+        const float cg[4] = {top && lef ? c0 : 0.f, top && rig ? c1 : 0.f, bot && lef ? c2 : 0.f, bot && rig ? c3 : 0.f};
+        direct_scatter<T>(c, gq_a, gq_b, at, cg);
+    }
+}
+
 // One sampling point, any location: channel sums (grad_mask, grad_offset / sigma) and the point's
 // four coefficients into the A tile / the spill list / the global accumulator.
 template <typename T>
@@ -224,22 +247,7 @@ __device__ __noinline__ void slow_point(const SlowCtx<T> *cp, int band_row0, int
             *e2 = from_f32<T>(a2 + w3 * m);
             *e3 = from_f32<T>(a3 + w4 * m);
         } else {
-            // beyond the band: hand the coefficients to the warp (spill list), or reduce directly
-            unsigned *cnt = reinterpret_cast<unsigned *>(c.spill);
-            const unsigned pos = atomicAdd(cnt, 1u);
-            const float cf[4] = {w1 * m, w2 * m, w3 * m, w4 * m};
-            if (pos < (unsigned)kSpillCap) {
-                SpillEntry *e = reinterpret_cast<SpillEntry *>(c.spill + 16) + pos;
-                e->h0 = h0; e->w0 = w0; e->lane = c.lane; e->pad = 0;
-                e->c[0] = cf[0]; e->c[1] = cf[1]; e->c[2] = cf[2]; e->c[3] = cf[3];
-            } else {
-                const bool top = h0 >= 0, bot = h0 + 1 < c.H, lef = w0 >= 0, rig = w0 + 1 < c.W;
-                const int at[4] = {h0 * c.row_stride + w0 * c.C, h0 * c.row_stride + (w0 + 1) * c.C,
-                                   (h0 + 1) * c.row_stride + w0 * c.C, (h0 + 1) * c.row_stride + (w0 + 1) * c.C};
-                const float cg[4] = {top && lef ? cf[0] : 0.f, top && rig ? cf[1] : 0.f,
-                                     bot && lef ? cf[2] : 0.f, bot && rig ? cf[3] : 0.f};
-                direct_scatter<T>(c, gq_a, gq_b, at, cg);
-            }
+            spill_push<T>(cp, h0, w0, w1 * m, w2 * m, w3 * m, w4 * m);
         }
     } else {
         // ---- outside the window: clamped global reads, direct reductions
@@ -268,20 +276,24 @@ __device__ __noinline__ void slow_point(const SlowCtx<T> *cp, int band_row0, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// Hot path.  Per-step values of one lane; coordinates are BAND-relative (the band origin is folded
-// into the anchors), so one float range test decides "window and band hit" and the zero fill of
-// the TMA window stands in for the reference's range test (all four corners of a point that
-// fails it lie outside the map and read zeros).
+// Hot path.  Per-step values of one lane; coordinates are WINDOW-relative (the window origin is
+// folded into the anchors), so one range test on the floats' bit patterns decides "window hit" and
+// the zero fill of the TMA window stands in for the reference's range test (all four corners of a
+// point that fails it lie outside the map and read zeros).
 template <typename T> struct StepCtx {
-    uint32_t win_b;        // shared address of the band's first window cell (+ half * 16)
+    uint32_t win_addr;     // shared address of the window (+ half * 16)
     uint32_t a_lane;       // shared address of the A tile + (lane & 7) * 2
     uint32_t chunk;        // lane >> 3: this pixel's 16-byte chunk of an A row
-    int jq;                // ((lane & 7) >> 1) - (band_col0 + 2 * band_row0): rotation phase
-    float bw, bh;          // band-relative anchors of the pixel
+    int jq;                // (lane & 7) >> 1: rotation phase
+    int band_row0, band_col0;   // band origin in window coordinates
+    int oy, ox;            // window origin in the map
+    float bw, bh;          // window-relative anchors of the pixel
     float sigma;
     uint32_t s_off_lane;   // shared address of this lane's 9 (dx, dy) pairs / results
     uint32_t s_msk_lane;   // shared address of this lane's 9 masks / results
     uint4 gq_a, gq_b;      // upstream gradient of the pixel: chunk `half` / the other chunk
+    uint32_t spill;        // shared address of this warp's spill list
+    int lane;
 };
 
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
@@ -297,39 +309,62 @@ __device__ __forceinline__ uint32_t lds16(uint32_t a) {
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
 
-// NP points p0 .. p0+NP-1 of this lane's pixel at once (independent instruction streams for the
-// scheduler).  Returns false, having done nothing, if any of them leaves the band.
+// The NP points (tap column i, tap rows 0..NP-1) of this lane's pixel at once: independent
+// instruction streams for the scheduler.  Returns false, having done nothing, if any of them
+// leaves the window.
 template <typename T, int NP>
-__device__ __forceinline__ bool points_fast(const StepCtx<T> &c, int p0) {
-    float ub[NP], vb[NP], m[NP];
+__device__ __forceinline__ bool points_fast(const StepCtx<T> &c, int i) {
+    float uw[NP], vw[NP], m[NP];
     bool ok = true;
+    const float fi = (float)i;
+    const int p0 = i * 3;
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
-        const int p = p0 + q, i = (p * 11) >> 5, jj = p - 3 * i;
-        const float2 d = unpack2(lds32(c.s_off_lane + p * 4), T());
-        m[q] = f32_of((uint16_t)lds16(c.s_msk_lane + p * 2), T());
-        ub[q] = c.bw + ((float)i + d.x) * c.sigma;
-        vb[q] = c.bh + ((float)jj + d.y) * c.sigma;
+        const float2 d = unpack2(lds32(c.s_off_lane + (p0 + q) * 4), T());
+        m[q] = f32_of((uint16_t)lds16(c.s_msk_lane + (p0 + q) * 2), T());
+        uw[q] = c.bw + (fi + d.x) * c.sigma;
+        vw[q] = c.bh + ((float)q + d.y) * c.sigma;
         // 0 <= x < limit on the float's bit pattern: negative values and NaN compare as large unsigned
-        ok = ok && __float_as_uint(ub[q]) < __float_as_uint((float)(kBandW - 1)) &&
-             __float_as_uint(vb[q]) < __float_as_uint((float)(kBandH - 1));
+        ok = ok && __float_as_uint(uw[q]) < __float_as_uint((float)(kWinW - 1)) &&
+             __float_as_uint(vw[q]) < __float_as_uint((float)(kWinH - 1));
     }
     if (!ok) return false;
+    // points that leave the band need a slot in the spill list: reserve them all now, while nothing
+    // has been written yet; if the list is full the whole group takes the general path instead
+    uint32_t pos0 = 0;
+    int nslot = 0;
+    {
+        int nmiss = 0;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const int br = (int)floorf(vw[q]) - c.band_row0, bc = (int)floorf(uw[q]) - c.band_col0;
+            nmiss += !((unsigned)br < (unsigned)(kBandH - 1) && (unsigned)bc < (unsigned)(kBandW - 1));
+        }
+        if (nmiss) {
+            asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(pos0) : "r"(c.spill), "r"((uint32_t)nmiss) : "memory");
+            if (pos0 + (uint32_t)nmiss > (uint32_t)kSpillCap) {
+                // reserved slots that exist stay empty (zero coefficients are skipped)
+                for (uint32_t k = pos0; k < pos0 + (uint32_t)nmiss && k < (uint32_t)kSpillCap; ++k)
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%1,%1,%1};" ::"r"(c.spill + 16 + k * 32 + 16), "f"(0.f) : "memory");
+                return false;
+            }
+        }
+    }
 
     float lh[NP], lw[NP];
-    int cb[NP], rho[NP];
+    int wc[NP], wr[NP], rho[NP];
     uint4 qa[NP][4], qb[NP][4];
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
-        const float fw = floorf(ub[q]), fh = floorf(vb[q]);
-        lw[q] = ub[q] - fw;
-        lh[q] = vb[q] - fh;
-        const int bc = (int)fw, br = (int)fh;
-        cb[q] = br * kBandW + bc;
-        rho[q] = (c.jq - (bc + 2 * br)) & 3;
+        const float fw = floorf(uw[q]), fh = floorf(vw[q]);
+        lw[q] = uw[q] - fw;
+        lh[q] = vw[q] - fh;
+        wc[q] = (int)fw;
+        wr[q] = (int)fh;
+        rho[q] = (c.jq - (wc[q] + 2 * wr[q])) & 3;
         int o[4] = {0, kSliceBytes, kWinW * kSliceBytes, kWinW * kSliceBytes + kSliceBytes};
         rotate4(o, rho[q]);
-        const uint32_t tl = c.win_b + (uint32_t)(br * kWinW + bc) * kSliceBytes;
+        const uint32_t tl = c.win_addr + (uint32_t)(wr[q] * kWinW + wc[q]) * kSliceBytes;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             qa[q][t] = lds128(tl + o[t]);
@@ -346,25 +381,33 @@ __device__ __forceinline__ bool points_fast(const StepCtx<T> &c, int p0) {
         const float gm = hh * (hw * dr[0] + lw[q] * dr[1]) + lh[q] * (hw * dr[2] + lw[q] * dr[3]);
         const float gx = m[q] * (hh * (dr[1] - dr[0]) + lh[q] * (dr[3] - dr[2]));
         const float gy = m[q] * (hw * (dr[2] - dr[0]) + lw[q] * (dr[3] - dr[1]));
-        const int p = p0 + q;
-        sts32(c.s_off_lane + p * 4, pack2(c.sigma * gx, c.sigma * gy, T()));
-        sts16(c.s_msk_lane + p * 2, bits16(gm, T()));
+        sts32(c.s_off_lane + (p0 + q) * 4, pack2(c.sigma * gx, c.sigma * gy, T()));
+        sts16(c.s_msk_lane + (p0 + q) * 2, bits16(gm, T()));
     }
     // A build: this pixel's column (thread-exclusive).  The four corner cells of a point are
     // distinct (read all four, then write all four); points go one after the other because two
     // points of a pixel may share a cell.  Rows cb and cb+16 have the same swizzle.
+    // A point whose corner block leaves the band hands its coefficients to the warp's spill list.
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
-        const uint32_t c0 = (uint32_t)cb[q], c1 = c0 + 1u;
-        const uint32_t e0 = c.a_lane + c0 * 64u + ((c.chunk ^ ((c0 >> 1) & 3u)) << 4);
-        const uint32_t e1 = c.a_lane + c1 * 64u + ((c.chunk ^ ((c1 >> 1) & 3u)) << 4);
+        const int br = wr[q] - c.band_row0, bc = wc[q] - c.band_col0;
         const float hm = (1.f - lh[q]) * m[q], lm = lh[q] * m[q], hw = 1.f - lw[q];
-        const float a0 = f32_of((uint16_t)lds16(e0), T()), a1 = f32_of((uint16_t)lds16(e1), T());
-        const float a2 = f32_of((uint16_t)lds16(e0 + kBandW * 64), T()), a3 = f32_of((uint16_t)lds16(e1 + kBandW * 64), T());
-        sts16(e0, bits16(a0 + hm * hw, T()));
-        sts16(e1, bits16(a1 + hm * lw[q], T()));
-        sts16(e0 + kBandW * 64, bits16(a2 + lm * hw, T()));
-        sts16(e1 + kBandW * 64, bits16(a3 + lm * lw[q], T()));
+        if ((unsigned)br < (unsigned)(kBandH - 1) && (unsigned)bc < (unsigned)(kBandW - 1)) {
+            const uint32_t c0 = (uint32_t)(br * kBandW + bc), c1 = c0 + 1u;
+            const uint32_t e0 = c.a_lane + c0 * 64u + ((c.chunk ^ ((c0 >> 1) & 3u)) << 4);
+            const uint32_t e1 = c.a_lane + c1 * 64u + ((c.chunk ^ ((c1 >> 1) & 3u)) << 4);
+            const float a0 = f32_of((uint16_t)lds16(e0), T()), a1 = f32_of((uint16_t)lds16(e1), T());
+            const float a2 = f32_of((uint16_t)lds16(e0 + kBandW * 64), T()), a3 = f32_of((uint16_t)lds16(e1 + kBandW * 64), T());
+            sts16(e0, bits16(a0 + hm * hw, T()));
+            sts16(e1, bits16(a1 + hm * lw[q], T()));
+            sts16(e0 + kBandW * 64, bits16(a2 + lm * hw, T()));
+            sts16(e1 + kBandW * 64, bits16(a3 + lm * lw[q], T()));
+        } else {
+            const uint32_t e = c.spill + 16 + (pos0 + (uint32_t)nslot) * 32;   // slot reserved above
+            ++nslot;
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(e), "r"(wr[q] + c.oy), "r"(wc[q] + c.ox), "r"(c.lane), "r"(0) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(e + 16), "f"(hm * hw), "f"(hm * lw[q]), "f"(lm * hw), "f"(lm * lw[q]) : "memory");
+        }
     }
     return true;
 }
@@ -396,9 +439,6 @@ __device__ __forceinline__ void flush_rows(const float (&acc)[kMTiles][2][4], fl
 // Staging I/O of one warp, out of line (one copy of the code, called once per step): write the
 // finished step's grad_offset / grad_mask out of the staging buffer, then request the next step's
 // offsets / masks / grad_out with cp.async (no registers held while they are in flight).
-// Lane <-> (pixel column lane>>2, quarter lane&3): a lane moves words quarter, quarter+4 (and 8)
-// of its pixel's 9-word run in each of the patch's 4 rows, so every address is one per-lane base
-// plus a per-row stride plus an immediate, and a warp access covers 8 runs of 16 contiguous bytes.
 template <typename T> struct IoCtx {   // kernel-constant, one copy per CTA in shared memory
     const T *offset, *mask, *grad_out;
     T *grad_offset, *grad_mask;
@@ -406,74 +446,92 @@ template <typename T> struct IoCtx {   // kernel-constant, one copy per CTA in s
     int Wo, Ho, G, C;
 };
 
+// Index table (shared memory, built once per CTA): element k = lane + 32 it of a patch's 32 x 9
+// staged values belongs to pixel k / 9, point k % 9 -- consecutive lanes walk a pixel's contiguous
+// 36-byte (offsets) / 18-byte (masks) run, so a warp access touches the minimal number of 32-byte
+// sectors (one LSU wavefront each).  Entry = element offset from the patch's first run | pixel << 27;
+// rows 9..13: the same for the mask runs' 5 enclosing words (k / 5, k % 5 << 24).
+__device__ __forceinline__ void build_io_table(uint32_t *tbl, int Wo, int G9, int tid, int nthreads) {
+    for (int e = tid; e < (kP + 5) * 32; e += nthreads) {
+        const int it = e >> 5, lane = e & 31;
+        uint32_t v;
+        if (it < kP) {
+            const int k = lane + 32 * it, px = k / kP, p = k - px * kP;
+            v = (uint32_t)(((px >> 3) * Wo + (px & 7)) * G9 + p) | ((uint32_t)px << 27);
+        } else {
+            const int k = lane + 32 * (it - kP), px = k / 5, wd = k - px * 5;
+            v = (uint32_t)(((px >> 3) * Wo + (px & 7)) * G9) | ((uint32_t)wd << 24) | ((uint32_t)px << 27);
+        }
+        tbl[e] = v;
+    }
+}
+
 template <typename T>
-__device__ __noinline__ void stage_io(const IoCtx<T> *io_s, uint32_t sa /* staging buffer */, size_t pix_w, int g_w,
-                                      int wb_w, int hb_w, int do_w, size_t pix_p, int g_p, int wb_p, int hb_p,
-                                      int do_p) {
+__device__ __noinline__ void stage_io(const IoCtx<T> *io_s, const uint32_t *tbl, uint32_t sa /* staging buffer */,
+                                      size_t pix_w, int g_w, int wb_w, int hb_w, int do_w, size_t pix_p, int g_p,
+                                      int wb_p, int hb_p, int do_p) {
     const IoCtx<T> io = *io_s;     // registers from here on (the asm statements below clobber memory)
-    const int lane = threadIdx.x & 31, col = lane >> 2, qt = lane & 3;
-    const int Wo = io.Wo, Ho = io.Ho, G9 = io.G * kP;
-    const int rowstep = Wo * G9;   // elements between vertically adjacent pixels of one group
-    if (do_w) {
-        const size_t e0 = (pix_w * io.G + g_w) * kP + (size_t)col * G9;   // first element of this lane's run, row 0
-        uint32_t *ob = reinterpret_cast<uint32_t *>(io.grad_offset) + e0 + qt;
-        uint16_t *mb = reinterpret_cast<uint16_t *>(io.grad_mask) + e0 + qt;
-        unsigned par = (unsigned)e0 & 1u;                                   // misalignment of the staged mask run
-        uint32_t so = sa + kStageOff + (col * kP + qt) * 4;
-        uint32_t sm = sa + kStageMsk + col * (kMskWords * 4) + qt * 2;
-        const bool okc = wb_w + col < Wo;
+    const int lane = threadIdx.x & 31;
+    const int Wo = io.Wo, Ho = io.Ho;
+    uint32_t ent[kP];
 #pragma unroll
-        for (int row = 0; row < kPatchH; ++row) {
-            if (okc && hb_w + row < Ho) {
-                ob[0] = lds32(so);
-                ob[4] = lds32(so + 16);
-                const uint32_t smr = sm + par * 2;
-                mb[0] = (uint16_t)lds16(smr);
-                mb[4] = (uint16_t)lds16(smr + 8);
-                if (qt == 0) {
-                    ob[8] = lds32(so + 32);
-                    mb[8] = (uint16_t)lds16(smr + 16);
-                }
+    for (int it = 0; it < kP; ++it) ent[it] = tbl[it * 32 + lane];
+    if (do_w) {
+        const size_t e0 = (pix_w * io.G + g_w) * kP;             // first element of the patch's first run
+        uint32_t *ob = reinterpret_cast<uint32_t *>(io.grad_offset) + e0;
+        uint16_t *mb = reinterpret_cast<uint16_t *>(io.grad_mask) + e0;
+        const unsigned par0 = (unsigned)e0 & 1u;
+        const bool full = wb_w + kStripW <= Wo && hb_w + kPatchH <= Ho;
+        uint32_t vo[kP], vm[kP];
+        // all reads first (independent), then the stores
+#pragma unroll
+        for (int it = 0; it < kP; ++it) {
+            const int px = (int)(ent[it] >> 27), rel = (int)(ent[it] & 0x7ffffffu);
+            const int p = lane + 32 * it - px * kP;
+            const unsigned shp = (par0 + (unsigned)(rel - p)) & 1u;   // misalignment of the staged mask run
+            vo[it] = lds32(sa + kStageOff + (lane + 32 * it) * 4);
+            vm[it] = lds16(sa + kStageMsk + px * (kMskWords * 4) + (shp + p) * 2);
+        }
+#pragma unroll
+        for (int it = 0; it < kP; ++it) {
+            const int px = (int)(ent[it] >> 27), rel = (int)(ent[it] & 0x7ffffffu);
+            if (full || (wb_w + (px & 7) < Wo && hb_w + (px >> 3) < Ho)) {
+                ob[rel] = vo[it];
+                mb[rel] = (uint16_t)vm[it];
             }
-            ob += rowstep;
-            mb += rowstep;
-            par = (par + (unsigned)rowstep) & 1u;
-            so += kStripW * kP * 4;
-            sm += kStripW * kMskWords * 4;
         }
     }
     __syncwarp();   // every lane is done reading the staging buffer (gather results, B fragments)
     if (do_p) {
-        const size_t e0 = (pix_p * io.G + g_p) * kP + (size_t)col * G9;
-        const uint32_t *os = reinterpret_cast<const uint32_t *>(io.offset) + e0 + qt;
+        const size_t e0 = (pix_p * io.G + g_p) * kP;
+        const uint32_t *os = reinterpret_cast<const uint32_t *>(io.offset) + e0;
         const unsigned char *ms = reinterpret_cast<const unsigned char *>(io.mask) + e0 * 2;
-        uint32_t so = sa + kStageOff + (col * kP + qt) * 4;
-        uint32_t sm = sa + kStageMsk + col * (kMskWords * 4) + qt * 4;
-        const bool okc = wb_p + col < Wo;
+        const unsigned mlow = (unsigned)(uintptr_t)ms & 3u;
+        const bool full = wb_p + kStripW <= Wo && hb_p + kPatchH <= Ho;
 #pragma unroll
-        for (int row = 0; row < kPatchH; ++row) {
-            if (okc && hb_p + row < Ho) {
-                cp_async4(so, os, 4);
-                cp_async4(so + 16, os + 4, 4);
-                // the 18-byte mask run is staged from its enclosing 4-byte words (5 of them)
-                const unsigned char *al = ms - ((uintptr_t)ms & 2u) + qt * 4;
-                cp_async4(sm, al, al + 4 <= io.mask_end ? 4 : 2);
-                if (qt == 0) {
-                    cp_async4(so + 32, os + 8, 4);
-                    cp_async4(sm + 16, al + 16, al + 20 <= io.mask_end ? 4 : 2);
-                }
+        for (int it = 0; it < kP; ++it) {
+            const int px = (int)(ent[it] >> 27), rel = (int)(ent[it] & 0x7ffffffu);
+            if (full || (wb_p + (px & 7) < Wo && hb_p + (px >> 3) < Ho))
+                cp_async4(sa + kStageOff + (lane + 32 * it) * 4, os + rel, 4);
+        }
+        // the 18-byte mask run of a pixel is staged from its 5 enclosing 4-byte words
+#pragma unroll
+        for (int it = 0; it < 5; ++it) {
+            const uint32_t en = tbl[(kP + it) * 32 + lane];
+            const int px = (int)(en >> 27), wd = (int)((en >> 24) & 7u);
+            if (full || (wb_p + (px & 7) < Wo && hb_p + (px >> 3) < Ho)) {
+                const unsigned relb = (en & 0xffffffu) * 2u;                      // byte offset of the run
+                const unsigned low = (mlow + relb) & 3u;                          // its misalignment (0 or 2)
+                const unsigned char *src = ms + ((ptrdiff_t)relb - (ptrdiff_t)low + wd * 4);
+                cp_async4(sa + kStageMsk + (px * kMskWords + wd) * 4, src, src + 4 <= io.mask_end ? 4 : 2);
             }
-            os += rowstep;
-            ms += (size_t)rowstep * 2;
-            so += kStripW * kP * 4;
-            sm += kStripW * kMskWords * 4;
         }
         // grad_out: lane <-> (pixel lane>>1 of 16, 16-byte chunk lane&1), two rounds; zero fill for
         // pixels outside the map (their A columns are zero, the product must not see NaN bits)
 #pragma unroll
         for (int r2 = 0; r2 < 2; ++r2) {
             const int px = r2 * 16 + (lane >> 1), row = px >> 3, c8 = px & 7, ck = lane & 1;
-            const bool ok = wb_p + c8 < Wo && hb_p + row < Ho;
+            const bool ok = full || (wb_p + c8 < Wo && hb_p + row < Ho);
             const T *gs = io.grad_out + (pix_p + (size_t)(row * Wo + c8)) * io.C + g_p * kCh + ck * 8;
             cp_async16(sa + kStageGout + px * kSliceBytes + ck * 16, ok ? gs : io.grad_out, ok ? 16 : 0);
         }
@@ -494,6 +552,7 @@ bwd_strip(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
     unsigned char *abuf = smem + kWinBytes + warp * kABytes;
     unsigned char *stage = smem + kWinBytes + kWarps * kABytes + warp * kStageBytes;
     unsigned char *spill = smem + kWinBytes + kWarps * (kABytes + kStageBytes) + warp * kSpillBytes;
+    uint32_t *io_tbl = reinterpret_cast<uint32_t *>(smem + kWinBytes + kWarps * (kABytes + kStageBytes + kSpillBytes));
     const uint32_t stage_addr = smem_u32(stage);
     const uint32_t a_base = smem_u32(abuf);
 
@@ -515,6 +574,7 @@ bwd_strip(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
         io.mask_end = reinterpret_cast<const unsigned char *>(mask) + pp.mask_bytes;
         io.Wo = q.Wo; io.Ho = q.Ho; io.G = q.G; io.C = C;
     }
+    build_io_table(io_tbl, q.Wo, q.G * kP, tid, kThreads);
     __syncthreads();
 
     if (tid == 0) {
@@ -524,7 +584,7 @@ bwd_strip(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
     {   // prologue: zero this warp's A tile and spill counter, request the first staging data
         for (int i = lane; i < kABytes / 16; i += 32) sts128_zero(a_base + i * 16);
         if (lane == 0) *reinterpret_cast<unsigned *>(spill) = 0u;
-        stage_io<T>(&io, stage_addr, 0, 0, 0, 0, 0, patch_pix(cur, 0), cur.g, cur.wo0 + warp * kStripW, cur.ho0, 1);
+        stage_io<T>(&io, io_tbl, stage_addr, 0, 0, 0, 0, 0, patch_pix(cur, 0), cur.g, cur.wo0 + warp * kStripW, cur.ho0, 1);
     }
     __syncthreads();
     if (tid == 0) {
@@ -572,14 +632,15 @@ bwd_strip(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
             // ------------------------------------------------------------ gather + A build
             if (live) {
                 StepCtx<T> c;
-                c.win_b = smem_u32(win) + (uint32_t)(band_row0 * kWinW + band_col0) * kSliceBytes + half * 16;
+                c.win_addr = smem_u32(win) + half * 16;
                 c.a_lane = a_base + (lane & 7) * 2;
                 c.chunk = (uint32_t)lane >> 3;
-                c.jq = ((lane & 7) >> 1) - (band_col0 + 2 * band_row0);
+                c.jq = (lane & 7) >> 1;
+                c.band_row0 = band_row0; c.band_col0 = band_col0; c.oy = cur.oy; c.ox = cur.ox; c.spill = smem_u32(spill); c.lane = lane;
                 const float base_w = axis_base(wo, 3, 1, q.pw, 1, q.sigma);
                 const float base_h = axis_base(ho, 3, 1, q.ph, 1, q.sigma);
-                c.bw = base_w - (float)(cur.ox + band_col0);
-                c.bh = base_h - (float)(cur.oy + band_row0);
+                c.bw = base_w - (float)cur.ox;
+                c.bh = base_h - (float)cur.oy;
                 c.sigma = q.sigma;
                 // the mask run of this pixel was staged from its enclosing 4-byte words: 0/1 element shift
                 const unsigned sh = (unsigned)(((pix + (size_t)(px_y * q.Wo + px_x)) * q.G + cur.g) * kP) & 1u;
@@ -598,10 +659,9 @@ bwd_strip(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
                     sts16(c.s_msk_lane + p * 2, bits16(res[0], T()));
                 };
 #pragma unroll 1
-                for (int p = 0; p < kP - 1; p += 2) {
-                    if (!points_fast<T, 2>(c, p)) { slow(p); slow(p + 1); }
+                for (int i = 0; i < 3; ++i) {
+                    if (!points_fast<T, 3>(c, i)) { slow(3 * i); slow(3 * i + 1); slow(3 * i + 2); }
                 }
-                if (!points_fast<T, 1>(c, kP - 1)) slow(kP - 1);
             }
             __syncwarp();
 
@@ -615,8 +675,10 @@ bwd_strip(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
                         const int hh = se[e].h0 + (corner >> 1), ww = se[e].w0 + (corner & 1);
                         if ((unsigned)hh < (unsigned)q.H && (unsigned)ww < (unsigned)q.W) {
                             const float cf = se[e].c[corner];
-                            const float2 gf = unpack2(lds32(stage_addr + kStageGout + se[e].lane * kSliceBytes + chp * 2), T());
-                            if (cf != 0.f) red_add2(sc.gv_img + (ptrdiff_t)hh * row_stride + (ptrdiff_t)ww * C + chp, cf * gf.x, cf * gf.y);
+                            if (cf != 0.f) {   // (also skips reserved-but-unused slots: zero coefficients)
+                                const float2 gf = unpack2(lds32(stage_addr + kStageGout + (se[e].lane & 31) * kSliceBytes + chp * 2), T());
+                                red_add2(sc.gv_img + (ptrdiff_t)hh * row_stride + (ptrdiff_t)ww * C + chp, cf * gf.x, cf * gf.y);
+                            }
                         }
                     }
                     __syncwarp();
@@ -637,7 +699,7 @@ bwd_strip(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ value,
                 const bool in_tile = s + 1 < kSteps;
                 const TileAt &na = in_tile ? cur : nxt;
                 const int ns = in_tile ? s + 1 : 0;
-                stage_io<T>(&io, stage_addr, pix, cur.g, wb, hb, 1, patch_pix(na, ns), na.g, na.wo0 + warp * kStripW,
+                stage_io<T>(&io, io_tbl, stage_addr, pix, cur.g, wb, hb, 1, patch_pix(na, ns), na.g, na.wo0 + warp * kStripW,
                             na.ho0 + ns * kPatchH, in_tile || has_next);
             }
 
@@ -731,6 +793,7 @@ static bool launch_typed(const void *value, const void *offset, const void *mask
     pp.tiles_xy = pp.tiles_x * tiles_y;
     pp.total_tiles = (int)total;
     pp.mask_bytes = (unsigned long long)q.N * q.Ho * q.Wo * q.G * kP * 2ull;
+    if ((long long)(3 * q.Wo + 8) * q.G * kP + kP >= (1LL << 24)) return false;   // staging index table packing
     CUtensorMap tmap;
     if (!make_nhwc_tensor_map(&tmap, value, dtype, q.N, q.H, q.W, C, kCh, kWinW, kWinH)) return false;
     static int num_sms = 0;
