@@ -300,7 +300,10 @@ def test_deterministic_backward_is_bit_reproducible(dt, monkeypatch):
     tol = 1e-5 if dt == "f32" else 1e-2
     for name, a, b in zip(WHAT, runs[0], base):
         # 16-bit default backward = tensor-core path: grad_value carries bf16-rounded coefficients
-        lim = 1e-3 if (name == "gv" and dt != "f32") else 0.0
+        # grad_offset is discontinuous where a sampling location crosses an integer: the default
+        # 16-bit kernels compute window-relative coordinates (one fp32 ulp from the direct kernel's),
+        # so a handful of points may sit on the other side (same allowance as the oracle tests)
+        lim = 1e-3 if (name == "gv" and dt != "f32") else (2e-3 if (name == "go" and dt != "f32") else 0.0)
         assert allclose_frac(a, b, rtol=tol, atol=tol * 0.1 * (np.abs(b).max() + 1e-30)) <= lim, name
 
 
