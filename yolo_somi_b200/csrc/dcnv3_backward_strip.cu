@@ -476,6 +476,8 @@ __device__ __noinline__ void stage_io(const IoCtx<T> *io_s, const uint32_t *tbl,
     uint32_t ent[kP];
 #pragma unroll
     for (int it = 0; it < kP; ++it) ent[it] = tbl[it * 32 + lane];
+    // Patches that lie fully inside the output map (the common case) take warp-uniform branches with
+    // unconditional accesses; a per-element guard costs a divergence barrier around every access.
     if (do_w) {
         const size_t e0 = (pix_w * io.G + g_w) * kP;             // first element of the patch's first run
         uint32_t *ob = reinterpret_cast<uint32_t *>(io.grad_offset) + e0;
@@ -492,12 +494,21 @@ __device__ __noinline__ void stage_io(const IoCtx<T> *io_s, const uint32_t *tbl,
             vo[it] = lds32(sa + kStageOff + (lane + 32 * it) * 4);
             vm[it] = lds16(sa + kStageMsk + px * (kMskWords * 4) + (shp + p) * 2);
         }
+        if (full) {
 #pragma unroll
-        for (int it = 0; it < kP; ++it) {
-            const int px = (int)(ent[it] >> 27), rel = (int)(ent[it] & 0x7ffffffu);
-            if (full || (wb_w + (px & 7) < Wo && hb_w + (px >> 3) < Ho)) {
+            for (int it = 0; it < kP; ++it) {
+                const int rel = (int)(ent[it] & 0x7ffffffu);
                 ob[rel] = vo[it];
                 mb[rel] = (uint16_t)vm[it];
+            }
+        } else {
+#pragma unroll 1
+            for (int it = 0; it < kP; ++it) {
+                const int px = (int)(ent[it] >> 27), rel = (int)(ent[it] & 0x7ffffffu);
+                if (wb_w + (px & 7) < Wo && hb_w + (px >> 3) < Ho) {
+                    ob[rel] = vo[it];
+                    mb[rel] = (uint16_t)vm[it];
+                }
             }
         }
     }
@@ -508,32 +519,56 @@ __device__ __noinline__ void stage_io(const IoCtx<T> *io_s, const uint32_t *tbl,
         const unsigned char *ms = reinterpret_cast<const unsigned char *>(io.mask) + e0 * 2;
         const unsigned mlow = (unsigned)(uintptr_t)ms & 3u;
         const bool full = wb_p + kStripW <= Wo && hb_p + kPatchH <= Ho;
+        const T *g_first = io.grad_out + pix_p * io.C + g_p * kCh;
+        if (full) {
 #pragma unroll
-        for (int it = 0; it < kP; ++it) {
-            const int px = (int)(ent[it] >> 27), rel = (int)(ent[it] & 0x7ffffffu);
-            if (full || (wb_p + (px & 7) < Wo && hb_p + (px >> 3) < Ho))
-                cp_async4(sa + kStageOff + (lane + 32 * it) * 4, os + rel, 4);
-        }
-        // the 18-byte mask run of a pixel is staged from its 5 enclosing 4-byte words
+            for (int it = 0; it < kP; ++it)
+                cp_async4(sa + kStageOff + (lane + 32 * it) * 4, os + (ent[it] & 0x7ffffffu), 4);
+            // the 18-byte mask run of a pixel is staged from its 5 enclosing 4-byte words; only the
+            // tensor's very last word can be half outside (warp-uniform test for the whole patch)
+            const bool tail = ms + ((size_t)((kPatchH - 1) * Wo + kStripW) * (io.G * kP)) * 2 + 4 > io.mask_end;
 #pragma unroll
-        for (int it = 0; it < 5; ++it) {
-            const uint32_t en = tbl[(kP + it) * 32 + lane];
-            const int px = (int)(en >> 27), wd = (int)((en >> 24) & 7u);
-            if (full || (wb_p + (px & 7) < Wo && hb_p + (px >> 3) < Ho)) {
+            for (int it = 0; it < 5; ++it) {
+                const uint32_t en = tbl[(kP + it) * 32 + lane];
+                const int px = (int)(en >> 27), wd = (int)((en >> 24) & 7u);
                 const unsigned relb = (en & 0xffffffu) * 2u;                      // byte offset of the run
                 const unsigned low = (mlow + relb) & 3u;                          // its misalignment (0 or 2)
                 const unsigned char *src = ms + ((ptrdiff_t)relb - (ptrdiff_t)low + wd * 4);
-                cp_async4(sa + kStageMsk + (px * kMskWords + wd) * 4, src, src + 4 <= io.mask_end ? 4 : 2);
+                if (!tail) cp_async4(sa + kStageMsk + (px * kMskWords + wd) * 4, src, 4);
+                else cp_async4(sa + kStageMsk + (px * kMskWords + wd) * 4, src, src + 4 <= io.mask_end ? 4 : 2);
             }
-        }
-        // grad_out: lane <-> (pixel lane>>1 of 16, 16-byte chunk lane&1), two rounds; zero fill for
-        // pixels outside the map (their A columns are zero, the product must not see NaN bits)
 #pragma unroll
-        for (int r2 = 0; r2 < 2; ++r2) {
-            const int px = r2 * 16 + (lane >> 1), row = px >> 3, c8 = px & 7, ck = lane & 1;
-            const bool ok = full || (wb_p + c8 < Wo && hb_p + row < Ho);
-            const T *gs = io.grad_out + (pix_p + (size_t)(row * Wo + c8)) * io.C + g_p * kCh + ck * 8;
-            cp_async16(sa + kStageGout + px * kSliceBytes + ck * 16, ok ? gs : io.grad_out, ok ? 16 : 0);
+            for (int r2 = 0; r2 < 2; ++r2) {
+                const int px = r2 * 16 + (lane >> 1), row = px >> 3, c8 = px & 7, ck = lane & 1;
+                cp_async16(sa + kStageGout + px * kSliceBytes + ck * 16, g_first + (size_t)(row * Wo + c8) * io.C + ck * 8, 16);
+            }
+        } else {
+            // ragged patch: copies of pixels outside the map are skipped by a zero source size
+            // (offsets / masks of such pixels are never read; their grad_out must read as zero:
+            // the A columns are zero, but the product must not see NaN bits)
+#pragma unroll 1
+            for (int it = 0; it < kP; ++it) {
+                const int px = (int)(ent[it] >> 27);
+                const bool ok = wb_p + (px & 7) < Wo && hb_p + (px >> 3) < Ho;
+                cp_async4(sa + kStageOff + (lane + 32 * it) * 4, os + (ok ? (ent[it] & 0x7ffffffu) : 0u), ok ? 4 : 0);
+            }
+#pragma unroll 1
+            for (int it = 0; it < 5; ++it) {
+                const uint32_t en = tbl[(kP + it) * 32 + lane];
+                const int px = (int)(en >> 27), wd = (int)((en >> 24) & 7u);
+                const bool ok = wb_p + (px & 7) < Wo && hb_p + (px >> 3) < Ho;
+                const unsigned relb = (en & 0xffffffu) * 2u;
+                const unsigned low = (mlow + relb) & 3u;
+                const unsigned char *src = ok ? ms + ((ptrdiff_t)relb - (ptrdiff_t)low + wd * 4) : reinterpret_cast<const unsigned char *>(io.mask);
+                cp_async4(sa + kStageMsk + (px * kMskWords + wd) * 4, src, ok ? (src + 4 <= io.mask_end ? 4 : 2) : 0);
+            }
+#pragma unroll
+            for (int r2 = 0; r2 < 2; ++r2) {
+                const int px = r2 * 16 + (lane >> 1), row = px >> 3, c8 = px & 7, ck = lane & 1;
+                const bool ok = wb_p + c8 < Wo && hb_p + row < Ho;
+                cp_async16(sa + kStageGout + px * kSliceBytes + ck * 16,
+                           ok ? g_first + (size_t)(row * Wo + c8) * io.C + ck * 8 : io.grad_out, ok ? 16 : 0);
+            }
         }
     }
     cp_async_commit();
