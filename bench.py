@@ -330,7 +330,19 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
-        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL may print its version banner on stdout while the communicator is created; stdout
+        # carries exactly one JSON line, so park fd 1 on stderr until the first collective is done
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     try:
         run_ours(args, rank, world, local_rank)
     finally:
