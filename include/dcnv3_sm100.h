@@ -131,6 +131,24 @@ DCNV3_API int dcnv3_host_pipeline_run(dcnv3_host_pipeline *p, const void *h_valu
 DCNV3_API int dcnv3_host_pipeline_sync(dcnv3_host_pipeline *p);
 DCNV3_API void dcnv3_host_pipeline_destroy(dcnv3_host_pipeline *p);
 
+/* ------------------------------------------------------------------------------------------------
+ * The step in front of the sampler: the layer's `offset` and `mask` linears plus the softmax over
+ * the K*K points of each group (models/ops_dcnv3/modules/dcnv3.py:330-334: two nn.Linear, reshape,
+ * F.softmax, .type(dtype)) as one tcgen05 GEMM with bias, softmax and cast in its epilogue.
+ *
+ *   x        [M, C]            16-bit activations (M = N*H*W rows), dense
+ *   w_cat    [padded_cols, C]  rows 0..2GP-1 = offset.weight, 2GP..3GP-1 = mask.weight, rest zero
+ *   bias_cat [padded_cols]     fp32, same order
+ *   offset   [M, 2GP], mask [M, GP] (soft-maxed over P within each group), dtype of x
+ *
+ * Eligible shapes: P == 9, G % 8 == 0, 3GP <= 512, C % 64 == 0, fp16 / bf16; DCNV3_E_SHAPE
+ * otherwise (the caller keeps the two linears + softmax for those).
+ */
+DCNV3_API int dcnv3_offset_mask_proj_padded_cols(int G, int P);
+DCNV3_API int dcnv3_offset_mask_proj_sm100(const void *x, const void *w_cat, const float *bias_cat,
+                        void *offset, void *mask, long long M, int C, int G, int P, int dtype,
+                        void *stream /* cudaStream_t */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -452,3 +452,77 @@ def test_host_pipeline_rejects_bad_arguments():
     pipe.run(*good); pipe.sync()      # pageable host memory is accepted
     assert float(good[4].abs().sum()) == 0.0
     pipe.close()
+
+
+# ----------------------------------------------------------------------------- fused offset/mask projection
+def _proj_reference(x, w_off, b_off, w_msk, b_msk, G, dtype):
+    """modules/dcnv3.py:330-334 in fp64 on the inputs as the 16-bit kernel sees them."""
+    xd, wo, wm = (t.to(dtype).double() for t in (x, w_off, w_msk))
+    off = xd @ wo.t() + b_off.double()
+    logit = (xd @ wm.t() + b_msk.double()).reshape(x.shape[0], G, -1)
+    return off, torch.softmax(logit, -1).reshape(x.shape[0], -1)
+
+
+@pytest.mark.parametrize("dt", ["bf16", "f16"])
+@pytest.mark.parametrize("M,C,G", [(2 * 37 * 45, 256, 16), (128, 64, 8), (1000, 128, 8), (5, 256, 16)])
+def test_fused_offset_mask_projection_matches_linears_plus_softmax(M, C, G, dt):
+    """tcgen05 GEMM + bias + softmax epilogue (csrc/dcnv3_proj.cu) against the layer's two linears
+    and softmax; 1e-2 relative (north_star), floor 1e-2 x RMS.  M not a multiple of 128 covers the
+    ragged last tile, M < 128 a single partial tile, C = 64 a single K chunk."""
+    from yolo_somi_b200.ops_dcnv3.functions import offset_mask_proj as omp
+    dtype = TDT[dt]
+    g = torch.Generator(device="cpu").manual_seed(M + C + G)
+    x = torch.randn(M, C, generator=g).cuda()
+    w_off = (torch.randn(2 * G * 9, C, generator=g) / C ** 0.5).cuda()
+    w_msk = (torch.randn(G * 9, C, generator=g) * 2 / C ** 0.5).cuda()
+    b_off = torch.randn(2 * G * 9, generator=g).cuda()
+    b_msk = torch.randn(G * 9, generator=g).cuda()
+    assert omp.eligible(x, G, 9, dtype)
+    off, msk = omp.OffsetMaskProj.apply(x, w_off, b_off, w_msk, b_msk, G, dtype)
+    torch.cuda.synchronize()
+    assert off.dtype == dtype and msk.dtype == dtype and off.shape == (M, 2 * G * 9) and msk.shape == (M, G * 9)
+    want_off, want_msk = _proj_reference(x, w_off, b_off, w_msk, b_msk, G, dtype)
+    for name, a, w in (("offset", off, want_off), ("mask", msk, want_msk)):
+        a, w = a.double().cpu().numpy(), w.cpu().numpy()
+        rms = float(np.sqrt(np.mean(w ** 2)))
+        assert allclose_frac(a, w, rtol=1e-2, atol=1e-2 * rms) == 0.0, (name, max_abs(a, w), rms)
+    s = msk.double().reshape(M, G, 9).sum(-1)
+    assert float((s - 1).abs().max()) < 2e-2
+
+
+def test_fused_projection_gradients_match_autograd_of_the_linears():
+    from yolo_somi_b200.ops_dcnv3.functions import offset_mask_proj as omp
+    M, C, G, dtype = 777, 128, 8, torch.bfloat16
+    g = torch.Generator(device="cpu").manual_seed(5)
+    leaves = [torch.randn(M, C, generator=g), torch.randn(2 * G * 9, C, generator=g) / C ** 0.5, torch.randn(2 * G * 9, generator=g),
+              torch.randn(G * 9, C, generator=g) / C ** 0.5, torch.randn(G * 9, generator=g)]
+    go, gm = torch.randn(M, 2 * G * 9, generator=g).cuda(), torch.randn(M, G * 9, generator=g).cuda()
+    def run(fused):
+        x, wo, bo, wm, bm = (t.clone().cuda().requires_grad_(True) for t in leaves)
+        if fused:
+            off, msk = omp.OffsetMaskProj.apply(x, wo, bo, wm, bm, G, dtype)
+        else:   # fp32 reference of the same function
+            off = x @ wo.t() + bo
+            msk = torch.softmax((x @ wm.t() + bm).reshape(M, G, 9), -1).reshape(M, -1)
+        (off.float() * go).sum().backward(retain_graph=True)
+        (msk.float() * gm).sum().backward()
+        return [t.grad.double().cpu().numpy() for t in (x, wo, bo, wm, bm)]
+    got, want = run(True), run(False)
+    for name, a, w in zip(("x", "w_off", "b_off", "w_msk", "b_msk"), got, want):
+        rms = float(np.sqrt(np.mean(w ** 2))) + 1e-30
+        assert allclose_frac(a, w, rtol=3e-2, atol=3e-2 * rms) <= 1e-3, (name, max_abs(a, w), rms)
+
+
+def test_layer_uses_fused_projection_and_matches_unfused(monkeypatch):
+    from yolo_somi_b200.ops_dcnv3.modules import DCNv3
+    torch.manual_seed(3)
+    layer = DCNv3(channels=128, group=8).cuda().to(torch.bfloat16)
+    with torch.no_grad():   # the reference initialises offset / mask to zero: give them some signal
+        layer.offset.weight.normal_(0, 0.05); layer.mask.weight.normal_(0, 0.2); layer.mask.bias.normal_(0, 0.5)
+    x = torch.randn(2, 20, 24, 128, device="cuda", dtype=torch.bfloat16)
+    y_fused = layer(x)
+    monkeypatch.setenv("DCNV3_FUSED_PROJ", "0")
+    y_ref = layer(x)
+    a, w = y_fused.detach().double().cpu().numpy(), y_ref.detach().double().cpu().numpy()
+    rms = float(np.sqrt(np.mean(w ** 2)))
+    assert allclose_frac(a, w, rtol=2e-2, atol=2e-2 * rms) <= 2e-3, (max_abs(a, w), rms)

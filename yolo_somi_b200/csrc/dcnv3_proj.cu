@@ -1,0 +1,316 @@
+// dcnv3_proj.cu -- the step in front of the sampler: the layer's `offset` and
+// `mask` linears and the softmax over the K*K points of each group
+// (reference: models/ops_dcnv3/modules/dcnv3.py:330-334 -- two nn.Linear calls, reshape, F.softmax,
+// .type(dtype): four kernels and three round trips of the 432-wide activations through HBM)
+// as ONE tcgen05 GEMM with the bias, the softmax and the cast in its epilogue:
+//
+//      [offset | mask_logits] = x1[M, C] * Wcat[C, 3GP] + bcat ;  mask = softmax_P(mask_logits)
+//
+// x1 is read once, offset (2GP columns) and the soft-maxed mask (GP columns) are written once, in
+// the op's dtype, in exactly the layouts the sampler reads.
+//
+// Structure (sm_100a, one persistent CTA of 192 threads per SM):
+//   * the 3GP output columns are split in two halves of <= 256 (a tcgen05.mma has N <= 256); a CTA
+//     serves one half and keeps that half of Wcat RESIDENT in shared memory for its whole life
+//     (K-major, 128-byte swizzle, loaded once by TMA);
+//   * warp 0 (one lane): TMA producer -- x1 tiles of 128 rows x 64 channels into a 6-deep ring;
+//   * warp 1 (one lane): issues tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = half width,
+//     K = 16 per instruction), accumulating in TMEM; two accumulator stages of 256 columns, so the
+//     MMAs of tile i+1 overlap the epilogue of tile i; completion is signalled with tcgen05.commit
+//     onto mbarriers (ring slot free / accumulator full);
+//   * warps 2-5: epilogue, thread <-> output row: tcgen05.ld of the row's accumulator columns,
+//     + bias, offsets cast and stored, mask logits soft-maxed over each group's 9 points in fp32
+//     (the logits are never rounded to 16 bits, unlike the reference's), cast and stored.
+// Eligibility: 16-bit I/O, C % 64 == 0, P == 9, G % 8 == 0, 3GP <= 512; anything else is the
+// caller's job (the Python layer keeps the two linears + softmax for those shapes).
+#include "dcnv3_sm100.h"
+
+#include "dcnv3_launch.h"
+#include "dcnv3_tma.cuh"
+
+#include <algorithm>
+#include <type_traits>
+
+namespace dcnv3 {
+namespace proj {
+
+constexpr int BM = 128, BK = 64;
+constexpr int kStages = 6;
+constexpr int kThreads = 192;
+constexpr int kP = 9;
+constexpr int kAStageBytes = BM * BK * 2;          // 16 KB
+constexpr int kAccCols = 256;                       // TMEM columns per accumulator stage
+
+struct Params {
+    long long M;
+    int m_tiles, kchunks;      // ceil(M / 128), C / 64
+    int n_off, n_msk;          // 2GP, GP
+    int nh[2];                 // columns of the two halves (multiples of 16, <= 256)
+    int G;
+};
+
+// ------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], both K-major
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major operand tile with 128-byte swizzle: rows of 64 16-bit elements (128 B), 8-row groups of
+// 1024 B.  cute/arch/mma_sm100_desc.hpp: start address >> 4 at [0,14), leading byte offset at
+// [16,30) (unused for swizzled K-major), stride byte offset >> 4 at [32,46) = 1024 B between 8-row
+// groups, version 1 at [46,48), layout type SWIZZLE_128B = 2 at [61,64).
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (same header): c_format F32 = 1 at [4,6), a/b_format at [7,10)/[10,13)
+// (F16 = 0, BF16 = 1), K-major A and B (bits 15, 16 = 0), N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+#define TMEM_LD_16(taddr, r)                                                                                   \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),    \
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) \
+                 : "r"(taddr))
+#define TMEM_LD_4(taddr, r)                                                                  \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"                \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr))
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <typename T> __device__ __forceinline__ uint32_t pack_pair(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack_pair<__nv_bfloat16>(float a, float b) { return pack2(a, b, __nv_bfloat16()); }
+template <> __device__ __forceinline__ uint32_t pack_pair<__half>(float a, float b) { return pack2(a, b, __half()); }
+
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+offset_mask_proj(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w0,
+                 const __grid_constant__ CUtensorMap tmap_w1, const float *__restrict__ bias, T *__restrict__ offset,
+                 T *__restrict__ mask, const Params pp) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], b_bar, acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float s_bias[256];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int half = blockIdx.y;
+    const int NH = pp.nh[half], col0 = half ? pp.nh[0] : 0;
+    const int b_chunk_bytes = NH * 128;
+    // 128-byte-swizzled operand tiles need 1024-byte alignment: align the dynamic region by hand
+    unsigned char *base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
+    unsigned char *b_smem = base;                                                   // [kchunks][NH rows][128 B]
+    unsigned char *a_smem = base + ((pp.kchunks * b_chunk_bytes + 1023) & ~1023);   // [kStages][128 rows][128 B]
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&b_bar, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        fence_barrier_init();
+    }
+    for (int c = tid; c < 256; c += kThreads) s_bias[c] = c < NH ? bias[col0 + c] : 0.f;
+    if (warp == 2) {   // one warp allocates the tensor memory: two accumulator stages
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(2 * kAccCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            const CUtensorMap *tw = half ? &tmap_w1 : &tmap_w0;
+            mbar_expect_tx(&b_bar, (unsigned)(pp.kchunks * b_chunk_bytes));
+            for (int kc = 0; kc < pp.kchunks; ++kc) tma_load_2d(b_smem + kc * b_chunk_bytes, tw, &b_bar, kc * BK, col0);
+            int s = 0, ph = 0;
+            for (int t = blockIdx.x; t < pp.m_tiles; t += gridDim.x) {
+                for (int kc = 0; kc < pp.kchunks; ++kc) {
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_expect_tx(&full_bar[s], kAStageBytes);
+                    tma_load_2d(a_smem + s * kAStageBytes, &tmap_x, &full_bar[s], kc * BK, t * BM);
+                    if (++s == kStages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value ? 1 : 0, BM, NH);
+            mbar_wait(&b_bar, 0);
+            int s = 0, ph = 0, it = 0;
+            for (int t = blockIdx.x; t < pp.m_tiles; t += gridDim.x, ++it) {
+                const int as = it & 1, aph = (it >> 1) & 1;
+                mbar_wait(&acc_empty[as], aph ^ 1);        // the epilogue has drained this accumulator stage
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * kAccCols;
+                for (int kc = 0; kc < pp.kchunks; ++kc) {
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(a_smem + s * kAStageBytes), b_addr = smem_u32(b_smem + kc * b_chunk_bytes);
+#pragma unroll
+                    for (int j = 0; j < BK / 16; ++j)
+                        tc_mma(d_tmem, umma_desc_k_sw128(a_addr + j * 32), umma_desc_k_sw128(b_addr + j * 32), idesc, (kc | j) != 0);
+                    tc_commit(&empty_bar[s]);              // ring slot free once these MMAs have read it
+                    if (++s == kStages) { s = 0; ph ^= 1; }
+                }
+                tc_commit(&acc_full[as]);                  // accumulator complete
+            }
+        }
+    } else {
+        // ===================================================================== epilogue (warps 2..5)
+        const int q = warp & 3;                            // TMEM lane quarter this warp may access
+        const int n_off_here = half ? pp.n_off - col0 : NH;   // local columns [0, n_off_here) are offsets
+        int it = 0;
+        for (int t = blockIdx.x; t < pp.m_tiles; t += gridDim.x, ++it) {
+            const int as = it & 1, aph = (it >> 1) & 1;
+            mbar_wait(&acc_full[as], aph);
+            tc_fence_after();
+            const long long row = (long long)t * BM + q * 32 + lane;
+            const bool row_ok = row < pp.M;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * kAccCols;
+            // ---- offsets: 16 columns at a time
+            T *orow = offset + row * pp.n_off + col0;
+            for (int c = 0; c < n_off_here; c += 16) {
+                uint32_t r[16];
+                TMEM_LD_16(taddr + c, r);
+                tmem_ld_wait();
+                if (row_ok) {
+                    uint32_t o[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        o[e] = pack_pair<T>(__uint_as_float(r[2 * e]) + s_bias[c + 2 * e], __uint_as_float(r[2 * e + 1]) + s_bias[c + 2 * e + 1]);
+                    *reinterpret_cast<uint4 *>(orow + c) = make_uint4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<uint4 *>(orow + c + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+                }
+            }
+            // ---- masks: 4 groups (36 columns) at a time, softmax over each group's 9 points
+            if (half) {
+                T *mrow = mask + row * pp.n_msk;
+                for (int w = 0; w < pp.n_msk; w += 4 * kP) {
+                    uint32_t r[36];
+                    uint32_t *r0 = r, *r1 = r + 16, *r2 = r + 32;
+                    TMEM_LD_16(taddr + n_off_here + w, r0);
+                    TMEM_LD_16(taddr + n_off_here + w + 16, r1);
+                    TMEM_LD_4(taddr + n_off_here + w + 32, r2);
+                    tmem_ld_wait();
+                    float v[36];
+#pragma unroll
+                    for (int e = 0; e < 36; ++e) v[e] = __uint_as_float(r[e]) + s_bias[n_off_here + w + e];
+#pragma unroll
+                    for (int g4 = 0; g4 < 4; ++g4) {
+                        float mx = v[g4 * 9];
+#pragma unroll
+                        for (int e = 1; e < 9; ++e) mx = fmaxf(mx, v[g4 * 9 + e]);
+                        float sum = 0.f;
+#pragma unroll
+                        for (int e = 0; e < 9; ++e) { v[g4 * 9 + e] = __expf(v[g4 * 9 + e] - mx); sum += v[g4 * 9 + e]; }
+                        const float inv = 1.f / sum;
+#pragma unroll
+                        for (int e = 0; e < 9; ++e) v[g4 * 9 + e] *= inv;
+                    }
+                    if (row_ok) {
+#pragma unroll
+                        for (int e = 0; e < 36; e += 4)
+                            *reinterpret_cast<uint2 *>(mrow + w + e) = make_uint2(pack_pair<T>(v[e], v[e + 1]), pack_pair<T>(v[e + 2], v[e + 3]));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * kAccCols) : "memory");
+}
+
+// row-major [rows, cols] 16-bit tensor, box {64 columns, box_rows}, 128-byte swizzle
+static bool make_k_major_map(CUtensorMap *map, const void *base, int dtype, unsigned long long rows, int cols, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const CUtensorMapDataType dt = dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    return fn(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int padded_cols(int G) { return (3 * G * kP + 15) & ~15; }
+
+template <typename T>
+static int launch(const void *x, const void *w_cat, const float *bias_cat, void *offset, void *mask, long long M, int C,
+                  int G, int dtype, cudaStream_t stream) {
+    Params pp;
+    pp.M = M;
+    pp.m_tiles = (int)((M + BM - 1) / BM);
+    pp.kchunks = C / BK;
+    pp.n_off = 2 * G * kP;
+    pp.n_msk = G * kP;
+    pp.G = G;
+    const int n_pad = padded_cols(G);
+    // first half: offset columns only, a multiple of 16, about half of the total
+    pp.nh[0] = std::min(((n_pad / 2 + 15) & ~15), pp.n_off & ~15);
+    pp.nh[1] = n_pad - pp.nh[0];
+    if (pp.nh[0] <= 0 || pp.nh[0] > 256 || pp.nh[1] <= 0 || pp.nh[1] > 256) return DCNV3_E_SHAPE;
+    if ((pp.n_off - pp.nh[0]) % 16 != 0) return DCNV3_E_SHAPE;
+    const size_t smem = (((size_t)pp.kchunks * std::max(pp.nh[0], pp.nh[1]) * 128 + 1023) & ~(size_t)1023) + (size_t)kStages * kAStageBytes + 1024;
+    if (smem > 225 * 1024) return DCNV3_E_SHAPE;
+    CUtensorMap tx, tw0, tw1;
+    if (!make_k_major_map(&tx, x, dtype, (unsigned long long)M, C, BM)) return DCNV3_E_SHAPE;
+    if (!make_k_major_map(&tw0, w_cat, dtype, (unsigned long long)n_pad, C, pp.nh[0])) return DCNV3_E_SHAPE;
+    if (!make_k_major_map(&tw1, w_cat, dtype, (unsigned long long)n_pad, C, pp.nh[1])) return DCNV3_E_SHAPE;
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int per_half = std::max(1, std::min(pp.m_tiles, num_sms / 2));
+    cudaFuncSetAttribute(offset_mask_proj<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    offset_mask_proj<T><<<dim3(per_half, 2), kThreads, smem, stream>>>(tx, tw0, tw1, bias_cat, static_cast<T *>(offset),
+                                                                        static_cast<T *>(mask), pp);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace proj
+}  // namespace dcnv3
+
+extern "C" {
+
+int dcnv3_offset_mask_proj_padded_cols(int G, int P) { return P == dcnv3::proj::kP ? dcnv3::proj::padded_cols(G) : 0; }
+
+int dcnv3_offset_mask_proj_sm100(const void *x, const void *w_cat, const float *bias_cat, void *offset, void *mask,
+                                 long long M, int C, int G, int P, int dtype, void *stream) {
+    if (dtype != DCNV3_F16 && dtype != DCNV3_BF16) return DCNV3_E_DTYPE;
+    if (M < 0 || C <= 0 || G <= 0 || P != dcnv3::proj::kP || C % dcnv3::proj::BK != 0 || G % 8 != 0 ||
+        3 * G * P > 512)
+        return DCNV3_E_SHAPE;
+    if (M == 0) return DCNV3_OK;
+    if (!x || !w_cat || !bias_cat || !offset || !mask) return DCNV3_E_NULL;
+    if (((uintptr_t)x | (uintptr_t)w_cat | (uintptr_t)offset) % 16 || (uintptr_t)mask % 8 || (uintptr_t)bias_cat % 4)
+        return DCNV3_E_ALIGN;
+    if (dtype == DCNV3_F16)
+        return dcnv3::proj::launch<__half>(x, w_cat, bias_cat, offset, mask, M, C, G, dtype, (cudaStream_t)stream);
+    return dcnv3::proj::launch<__nv_bfloat16>(x, w_cat, bias_cat, offset, mask, M, C, G, dtype, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,97 @@
+"""Fused `offset` / `mask` projection of the DCNv3 layer: one tcgen05 GEMM with bias, softmax over
+the K*K points of each group and the cast in its epilogue (libdcnv3_sm100.so,
+``dcnv3_offset_mask_proj_sm100``), replacing
+
+    offset = self.offset(x1)
+    mask = F.softmax(self.mask(x1).reshape(N, H, W, G, -1), -1).reshape(N, H, W, -1).type(dtype)
+
+of the reference layer (models/ops_dcnv3/modules/dcnv3.py:330-334).  The backward is plain PyTorch
+(softmax Jacobian, then the two weight-gradient / one input-gradient matmuls on cuBLAS).
+"""
+from __future__ import annotations
+
+import os
+import weakref
+
+import torch
+
+from ... import _native
+
+_DT = {torch.float16: _native.F16, torch.bfloat16: _native.BF16}
+
+
+def eligible(x1: torch.Tensor, group: int, points: int, dtype: torch.dtype) -> bool:
+    """Shapes the fused kernel takes (everything else keeps the two linears + softmax)."""
+    if os.environ.get("DCNV3_FUSED_PROJ", "1") in ("0", ""):
+        return False
+    c = x1.shape[-1]
+    return (x1.is_cuda and dtype in _DT and points == 9 and group % 8 == 0 and 3 * group * points <= 512
+            and c % 64 == 0)
+
+
+_PACKED = {}   # id(offset weight) -> (weak refs to the four tensors, their versions, dtype, w_cat, b_cat)
+
+
+def _pack(lib, w_off, b_off, w_msk, b_msk, group, points, dtype):
+    """Concatenated, zero-padded weights / biases in the kernel's layout; repacked only when one of
+    the four tensors is another object or has been modified in place (optimizer step)."""
+    tensors = (w_off, b_off, w_msk, b_msk)
+    ver = tuple(t._version for t in tensors)
+    hit = _PACKED.get(id(w_off))
+    if hit is not None and hit[1] == ver and hit[2] == dtype and all(r() is t for r, t in zip(hit[0], tensors)):
+        return hit[3], hit[4]
+    n = 3 * group * points
+    npad = lib.dcnv3_offset_mask_proj_padded_cols(group, points)
+    w_cat = torch.zeros(npad, w_off.shape[1], dtype=dtype, device=w_off.device)
+    w_cat[:n] = torch.cat([w_off.detach(), w_msk.detach()], 0).to(dtype)
+    b_cat = torch.zeros(npad, dtype=torch.float32, device=w_off.device)
+    b_cat[:n] = torch.cat([b_off.detach(), b_msk.detach()], 0).float()
+    if len(_PACKED) > 64:
+        _PACKED.clear()
+    _PACKED[id(w_off)] = (tuple(weakref.ref(t) for t in tensors), ver, dtype, w_cat, b_cat)
+    return w_cat, b_cat
+
+
+class OffsetMaskProj(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x1, w_off, b_off, w_msk, b_msk, group, dtype):
+        lib = _native.load()
+        points = w_msk.shape[0] // group
+        c = x1.shape[-1]
+        lead = x1.shape[:-1]
+        x2 = x1.reshape(-1, c).to(dtype).contiguous()
+        m = x2.shape[0]
+        w_cat, b_cat = _pack(lib, w_off, b_off, w_msk, b_msk, group, points, dtype)
+        offset = torch.empty(m, 2 * group * points, dtype=dtype, device=x1.device)
+        mask = torch.empty(m, group * points, dtype=dtype, device=x1.device)
+        with torch.cuda.device(x1.device):
+            rc = lib.dcnv3_offset_mask_proj_sm100(x2.data_ptr(), w_cat.data_ptr(), b_cat.data_ptr(),
+                                                  offset.data_ptr(), mask.data_ptr(), m, c, group, points,
+                                                  _DT[dtype], torch.cuda.current_stream().cuda_stream)
+        _native.check(rc, "dcnv3_offset_mask_proj_sm100")
+        ctx.save_for_backward(x2, w_off, w_msk, mask)
+        ctx.group, ctx.points, ctx.lead, ctx.in_dtype = group, points, lead, x1.dtype
+        return offset.reshape(*lead, -1), mask.reshape(*lead, -1)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_off, g_msk):
+        x2, w_off, w_msk, mask = ctx.saved_tensors
+        g, p = ctx.group, ctx.points
+        m = x2.shape[0]
+        g_off = g_off.reshape(m, -1)
+        pm = mask.float().reshape(m, g, p)
+        gm = g_msk.reshape(m, g, p).float()
+        g_logit = (pm * (gm - (gm * pm).sum(-1, keepdim=True))).reshape(m, g * p).to(x2.dtype)   # softmax Jacobian
+        gx = g_off @ w_off.to(x2.dtype) + g_logit @ w_msk.to(x2.dtype)
+        gw_off = (g_off.t() @ x2).to(w_off.dtype)
+        gw_msk = (g_logit.t() @ x2).to(w_msk.dtype)
+        gb_off = g_off.float().sum(0)
+        gb_msk = g_logit.float().sum(0)
+        return gx.reshape(*ctx.lead, -1).to(ctx.in_dtype), gw_off, gb_off.to(w_off.dtype), gw_msk, gb_msk.to(w_msk.dtype), None, None
+
+
+def offset_mask_proj(x1, offset_linear, mask_linear, group, dtype):
+    """offset [..., 2GP], mask [..., GP] (soft-maxed over P) in ``dtype`` from x1 [..., C]."""
+    return OffsetMaskProj.apply(x1, offset_linear.weight, offset_linear.bias, mask_linear.weight,
+                                mask_linear.bias, group, dtype)

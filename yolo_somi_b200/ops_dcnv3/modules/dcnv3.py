@@ -22,6 +22,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from ..functions import DCNv3Function
+from ..functions import offset_mask_proj
 
 
 class to_channels_first(nn.Module):
@@ -125,9 +126,13 @@ class DCNv3(nn.Module):
         n, h, w, _ = input.shape
         x = self.input_proj(input)
         x1 = self.dw_conv(input.permute(0, 3, 1, 2))
-        offset = self.offset(x1)
-        mask = F.softmax(self.mask(x1).reshape(n, h, w, self.group, -1), -1)
-        mask = mask.reshape(n, h, w, -1).type(x.dtype)
+        if offset_mask_proj.eligible(x1, self.group, self.kernel_size * self.kernel_size, x.dtype):
+            # one tcgen05 GEMM with bias, softmax and cast in its epilogue (csrc/dcnv3_proj.cu)
+            offset, mask = offset_mask_proj.offset_mask_proj(x1, self.offset, self.mask, self.group, x.dtype)
+        else:
+            offset = self.offset(x1)
+            mask = F.softmax(self.mask(x1).reshape(n, h, w, self.group, -1), -1)
+            mask = mask.reshape(n, h, w, -1).type(x.dtype)
         k, s, p, d = self.kernel_size, self.stride, self.pad, self.dilation
         y = DCNv3Function.apply(x, offset, mask, k, k, s, s, p, p, d, d, self.group,
                                 self.group_channels, self.offset_scale, 256)
