@@ -1,41 +1,65 @@
 """Fused offset/mask projection (tcgen05) vs the layer's two linears + softmax on cuBLAS/eager,
-BASELINE configs[1] shape: M = 16*80*80 rows, C = 256, G = 16.  Prints one JSON object."""
+BASELINE configs[1] shape: M = 16*80*80 rows, C = 256, G = 16.  Prints one JSON object.
+Kernel times are taken from CUDA-graph replays (no host launch latency between kernels); inputs
+rotate over 4 buffers so that a call never finds its activations in L2."""
 import json, sys
 import torch
 import torch.nn.functional as F
 sys.path.insert(0, '.')
+from yolo_somi_b200 import _native
 from yolo_somi_b200.ops_dcnv3.functions import offset_mask_proj as omp
 
 M, C, G, dt = 16 * 80 * 80, 256, 16, torch.bfloat16
 torch.manual_seed(0)
-xs = [torch.randn(M, C, device='cuda', dtype=dt) for _ in range(4)]      # rotate: > L2 between uses
+xs = [torch.randn(M, C, device='cuda', dtype=dt) for _ in range(4)]
 w_off = (torch.randn(2 * G * 9, C, device='cuda') / 16).to(dt); b_off = torch.randn(2 * G * 9, device='cuda').to(dt)
 w_msk = (torch.randn(G * 9, C, device='cuda') / 8).to(dt); b_msk = torch.randn(G * 9, device='cuda').to(dt)
+lib = _native.load()
+w_cat, b_cat = omp._pack(lib, w_off, b_off, w_msk, b_msk, G, 9, dt)
+off = torch.empty(M, 2 * G * 9, device='cuda', dtype=dt); msk = torch.empty(M, G * 9, device='cuda', dtype=dt)
 
-def fused(x):
+def fused_raw(x):
+    rc = lib.dcnv3_offset_mask_proj_sm100(x.data_ptr(), w_cat.data_ptr(), b_cat.data_ptr(), off.data_ptr(), msk.data_ptr(),
+                                          M, C, G, 9, _native.BF16, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, rc
+
+def fused_api(x):
     with torch.no_grad():
         return omp.OffsetMaskProj.apply(x, w_off, b_off, w_msk, b_msk, G, dt)
 
 def eager(x):   # modules/dcnv3.py:330-334
     with torch.no_grad():
-        off = F.linear(x, w_off, b_off)
-        msk = F.softmax(F.linear(x, w_msk, b_msk).reshape(M, G, -1).float(), -1).reshape(M, -1).to(dt)
-        return off, msk
+        o = F.linear(x, w_off, b_off)
+        m = F.softmax(F.linear(x, w_msk, b_msk).reshape(M, G, -1).float(), -1).reshape(M, -1).to(dt)
+        return o, m
 
-def timeit(fn, n=30):
+def graph_time(fn, reps=8, replays=10):
+    for i in range(3): fn(xs[i % 4])
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g):
+            for i in range(reps): fn(xs[i % 4])
+    g.replay(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(replays): g.replay()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / (reps * replays)
+
+def call_time(fn, n=30):
     for i in range(5): fn(xs[i % 4])
     torch.cuda.synchronize()
-    e = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
-    e[0].record()
-    for i in range(n):
-        fn(xs[i % 4]); e[i + 1].record()
-    torch.cuda.synchronize()
-    ts = sorted(e[i].elapsed_time(e[i + 1]) for i in range(n))
-    return ts[n // 2] * 1e3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n): fn(xs[i % 4])
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / n
 
-t_f, t_e = timeit(fused), timeit(eager)
+t_k, t_e = graph_time(fused_raw), graph_time(eager)
 by = 2 * (M * C + M * 3 * G * 9) + 2 * 3 * G * 9 * C
 fl = 2.0 * M * C * 3 * G * 9
-print(json.dumps({"shape": {"M": M, "C": C, "G": G, "dtype": "bf16"}, "fused_us": t_f, "eager_us": t_e,
-                  "algorithmic_bytes": by, "fused_gbs": by / t_f / 1e3, "fused_tflops": fl / t_f / 1e6,
-                  "note": "fused time includes the per-call weight packing (torch.cat + cast) of the Python wrapper"}))
+print(json.dumps({"shape": {"M": M, "C": C, "G": G, "dtype": "bf16"}, "fused_kernel_us": t_k, "eager_kernels_us": t_e,
+                  "fused_api_call_us": call_time(fused_api), "eager_api_call_us": call_time(eager),
+                  "algorithmic_bytes": by, "fused_gbs": by / t_k / 1e3, "fused_tflops": fl / t_k / 1e6}))

@@ -29,17 +29,25 @@
 #include "dcnv3_tma.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 namespace dcnv3 {
 namespace proj {
 
 constexpr int BM = 128, BK = 64;
-constexpr int kStages = 6;
-constexpr int kThreads = 192;
+constexpr int kStages = 3;
+constexpr int kEpiWarps = 8;                        // two per TMEM lane quarter, each takes half of the columns
+constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kP = 9;
 constexpr int kAStageBytes = BM * BK * 2;          // 16 KB
 constexpr int kAccCols = 256;                       // TMEM columns per accumulator stage
+constexpr int kOffBlk = 32;                         // offset columns per TMA store box (64-byte rows, SWIZZLE_64B)
+constexpr int kOffStageBytes = 32 * kOffBlk * 2;    // 2 KB: one staged 32 x 32 offset block
+constexpr int kMskStageBytes = 32 * 144;            // [32 rows][<= 72 mask columns]: half a mask row per warp
+// Output staging, one region per CTA: first-half CTAs (offsets only) use it as 8 warps x 3 block
+// buffers; second-half CTAs as 4 warps x 2 block buffers (offset tail) + 8 mask tiles.
+constexpr int kOutStageBytes = 4 * 2 * kOffStageBytes + 8 * kMskStageBytes;   // 53248 >= 8 * 3 * 2048
 
 struct Params {
     long long M;
@@ -47,6 +55,8 @@ struct Params {
     int n_off, n_msk;          // 2GP, GP
     int nh[2];                 // columns of the two halves (multiples of 16, <= 256)
     int G;
+    int mask_parts;            // 2: each epilogue part takes half a mask row; 1: part 1 takes it all
+    int dbg;
 };
 
 // ------------------------------------------------------------------------------------ PTX helpers
@@ -56,6 +66,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(smem_u32(src)) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t a, uint2 v) {
+    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -99,12 +121,12 @@ template <> __device__ __forceinline__ uint32_t pack_pair<__half>(float a, float
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 1)
 offset_mask_proj(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w0,
-                 const __grid_constant__ CUtensorMap tmap_w1, const float *__restrict__ bias, T *__restrict__ offset,
-                 T *__restrict__ mask, const Params pp) {
+                 const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_off,
+                 const __grid_constant__ CUtensorMap tmap_msk, const float *__restrict__ bias, const Params pp) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], b_bar, acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ float s_bias[256];
+    __shared__ __align__(16) float s_bias[256];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int half = blockIdx.y;
@@ -114,11 +136,12 @@ offset_mask_proj(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     unsigned char *base = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
     unsigned char *b_smem = base;                                                   // [kchunks][NH rows][128 B]
     unsigned char *a_smem = base + ((pp.kchunks * b_chunk_bytes + 1023) & ~1023);   // [kStages][128 rows][128 B]
+    unsigned char *out_stage = a_smem + kStages * kAStageBytes;                     // kOutStageBytes, see above
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(&b_bar, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
         fence_barrier_init();
     }
     for (int c = tid; c < 256; c += kThreads) s_bias[c] = c < NH ? bias[col0 + c] : 0.f;
@@ -172,36 +195,67 @@ offset_mask_proj(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             }
         }
     } else {
-        // ===================================================================== epilogue (warps 2..5)
+        // ===================================================================== epilogue (warps 2..9)
+        // thread <-> output row.  Results go to a per-warp staging tile in shared memory and leave
+        // with TMA stores (full sectors, no LSU traffic; rows beyond M are clipped by the tensor map):
+        // a lane storing 16 bytes of its own row directly costs one LSU wavefront per half-used sector
+        // and was 2/3 of the kernel's time.
         const int q = warp & 3;                            // TMEM lane quarter this warp may access
+        const int part = (warp - 2) >> 2;                  // 0 / 1: which share of the columns
         const int n_off_here = half ? pp.n_off - col0 : NH;   // local columns [0, n_off_here) are offsets
+        const int n_blk = (n_off_here + kOffBlk - 1) / kOffBlk;   // a ragged last block is clipped by the tensor map
+        // first-half CTAs: both parts take offset blocks; second-half CTAs: part 0 the offset tail
+        // and the first half of the mask row, part 1 the second half (a softmax group stays in one thread)
+        const int b_begin = half ? 0 : (part ? (n_blk + 1) / 2 : 0);
+        const int b_end = half ? (part ? 0 : n_blk) : (part ? n_blk : (n_blk + 1) / 2);
+        const bool do_mask = half && (pp.mask_parts == 2 || part == 1);
+        const int m_cols = pp.n_msk / pp.mask_parts, m_col0 = pp.mask_parts == 2 ? part * m_cols : 0;   // this warp's mask columns
+        const int nbuf = half ? 2 : 3;                     // staged offset blocks in flight per warp
+        unsigned char *obuf = out_stage + (half ? q * 2 : (warp - 2) * 3) * kOffStageBytes;
+        unsigned char *mbuf = out_stage + 4 * 2 * kOffStageBytes + (pp.mask_parts == 2 ? (part * 4 + q) : 2 * q) * kMskStageBytes;
+        const uint32_t mst = smem_u32(mbuf);
+        int ob = 0;                                        // next offset staging buffer
+        const int m_pitch = m_cols * 2;                    // bytes per staged (half) mask row
         int it = 0;
         for (int t = blockIdx.x; t < pp.m_tiles; t += gridDim.x, ++it) {
             const int as = it & 1, aph = (it >> 1) & 1;
             mbar_wait(&acc_full[as], aph);
             tc_fence_after();
-            const long long row = (long long)t * BM + q * 32 + lane;
-            const bool row_ok = row < pp.M;
+            const int row0 = t * BM + q * 32;              // first row of this warp's 32
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * kAccCols;
-            // ---- offsets: 16 columns at a time
-            T *orow = offset + row * pp.n_off + col0;
-            for (int c = 0; c < n_off_here; c += 16) {
-                uint32_t r[16];
-                TMEM_LD_16(taddr + c, r);
+            // ---- offsets: blocks of 32 columns
+            for (int bi = b_begin; bi < b_end; ++bi) {
+                const int c = bi * kOffBlk;
+                uint32_t r[32];
+                uint32_t *r0 = r, *r1 = r + 16;
+                TMEM_LD_16(taddr + c, r0);
+                TMEM_LD_16(taddr + c + 16, r1);
                 tmem_ld_wait();
-                if (row_ok) {
-                    uint32_t o[8];
+                uint32_t o[16];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        o[e] = pack_pair<T>(__uint_as_float(r[2 * e]) + s_bias[c + 2 * e], __uint_as_float(r[2 * e + 1]) + s_bias[c + 2 * e + 1]);
-                    *reinterpret_cast<uint4 *>(orow + c) = make_uint4(o[0], o[1], o[2], o[3]);
-                    *reinterpret_cast<uint4 *>(orow + c + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+                for (int e = 0; e < 16; ++e)
+                    o[e] = pack_pair<T>(__uint_as_float(r[2 * e]) + s_bias[c + 2 * e], __uint_as_float(r[2 * e + 1]) + s_bias[c + 2 * e + 1]);
+                // the store issued nbuf blocks ago has read this staging buffer
+                if (lane == 0) { if (half) bulk_wait_read<1>(); else bulk_wait_read<2>(); }
+                __syncwarp();
+                // 64-byte rows, 16-byte chunk k of row l at chunk (k ^ ((l >> 1) & 3)): SWIZZLE_64B
+                const uint32_t ost = smem_u32(obuf + ob * kOffStageBytes);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    sts128(ost + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4), make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]));
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    if (!(pp.dbg & 1)) tma_store_2d(&tmap_off, obuf + ob * kOffStageBytes, col0 + c, row0);
+                    bulk_commit();
                 }
+                if (++ob == nbuf) ob = 0;
             }
             // ---- masks: 4 groups (36 columns) at a time, softmax over each group's 9 points
-            if (half) {
-                T *mrow = mask + row * pp.n_msk;
-                for (int w = 0; w < pp.n_msk; w += 4 * kP) {
+            if (do_mask) {
+                if (lane == 0) bulk_wait_read<0>();
+                __syncwarp();
+                for (int w = m_col0; w < m_col0 + m_cols; w += 4 * kP) {
                     uint32_t r[36];
                     uint32_t *r0 = r, *r1 = r + 16, *r2 = r + 32;
                     TMEM_LD_16(taddr + n_off_here + w, r0);
@@ -210,7 +264,11 @@ offset_mask_proj(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     tmem_ld_wait();
                     float v[36];
 #pragma unroll
-                    for (int e = 0; e < 36; ++e) v[e] = __uint_as_float(r[e]) + s_bias[n_off_here + w + e];
+                    for (int e = 0; e < 36; e += 4) {   // (n_off_here + w) is a multiple of 4: 16-byte broadcast loads
+                        const float4 b4 = *reinterpret_cast<const float4 *>(&s_bias[n_off_here + w + e]);
+                        v[e] = __uint_as_float(r[e]) + b4.x; v[e + 1] = __uint_as_float(r[e + 1]) + b4.y;
+                        v[e + 2] = __uint_as_float(r[e + 2]) + b4.z; v[e + 3] = __uint_as_float(r[e + 3]) + b4.w;
+                    }
 #pragma unroll
                     for (int g4 = 0; g4 < 4; ++g4) {
                         float mx = v[g4 * 9];
@@ -219,26 +277,45 @@ offset_mask_proj(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         float sum = 0.f;
 #pragma unroll
                         for (int e = 0; e < 9; ++e) { v[g4 * 9 + e] = __expf(v[g4 * 9 + e] - mx); sum += v[g4 * 9 + e]; }
-                        const float inv = 1.f / sum;
+                        const float inv = __fdividef(1.f, sum);
 #pragma unroll
                         for (int e = 0; e < 9; ++e) v[g4 * 9 + e] *= inv;
                     }
-                    if (row_ok) {
 #pragma unroll
-                        for (int e = 0; e < 36; e += 4)
-                            *reinterpret_cast<uint2 *>(mrow + w + e) = make_uint2(pack_pair<T>(v[e], v[e + 1]), pack_pair<T>(v[e + 2], v[e + 3]));
-                    }
+                    for (int e = 0; e < 36; e += 4)
+                        sts64(mst + lane * m_pitch + (w - m_col0 + e) * 2, make_uint2(pack_pair<T>(v[e], v[e + 1]), pack_pair<T>(v[e + 2], v[e + 3])));
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0 && !(pp.dbg & 1)) {
+                    tma_store_2d(&tmap_msk, mbuf, m_col0, row0);
+                    bulk_commit();
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[as]);
         }
+        if (lane == 0) bulk_wait_read<0>();                // shared memory must outlive the last store's read
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * kAccCols) : "memory");
+}
+
+// row-major [rows, cols] 16-bit output tensor, box {box_cols, 32 rows}
+static bool make_out_map(CUtensorMap *map, void *base, int dtype, unsigned long long rows, int cols, int box_cols,
+                         CUtensorMapSwizzle swz) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const CUtensorMapDataType dt = dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, 32u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    return fn(map, dt, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // row-major [rows, cols] 16-bit tensor, box {64 columns, box_rows}, 128-byte swizzle
@@ -266,15 +343,20 @@ static int launch(const void *x, const void *w_cat, const float *bias_cat, void 
     pp.n_off = 2 * G * kP;
     pp.n_msk = G * kP;
     pp.G = G;
+    { const char *d = getenv("DCNV3_PROJ_DBG"); pp.dbg = d ? atoi(d) : 0; }
     const int n_pad = padded_cols(G);
     // first half: offset columns only, a multiple of 16, about half of the total
-    pp.nh[0] = std::min(((n_pad / 2 + 15) & ~15), pp.n_off & ~15);
+    // (a multiple of the 32-column store block, so that only the offset tensor's own edge is ragged)
+    pp.nh[0] = std::min(((n_pad / 2 + 31) & ~31), pp.n_off & ~31);
     pp.nh[1] = n_pad - pp.nh[0];
     if (pp.nh[0] <= 0 || pp.nh[0] > 256 || pp.nh[1] <= 0 || pp.nh[1] > 256) return DCNV3_E_SHAPE;
-    if ((pp.n_off - pp.nh[0]) % 16 != 0) return DCNV3_E_SHAPE;
-    const size_t smem = (((size_t)pp.kchunks * std::max(pp.nh[0], pp.nh[1]) * 128 + 1023) & ~(size_t)1023) + (size_t)kStages * kAStageBytes + 1024;
+    if ((pp.n_off - pp.nh[0]) % 16 != 0 || pp.n_msk > 144) return DCNV3_E_SHAPE;
+    const size_t smem = (((size_t)pp.kchunks * std::max(pp.nh[0], pp.nh[1]) * 128 + 1023) & ~(size_t)1023) + (size_t)kStages * kAStageBytes + (size_t)kOutStageBytes + 1024;
     if (smem > 225 * 1024) return DCNV3_E_SHAPE;
-    CUtensorMap tx, tw0, tw1;
+    CUtensorMap tx, tw0, tw1, to, tm;
+    if (!make_out_map(&to, offset, dtype, (unsigned long long)M, pp.n_off, kOffBlk, CU_TENSOR_MAP_SWIZZLE_64B)) return DCNV3_E_SHAPE;
+    pp.mask_parts = (pp.n_msk % 16 == 0 && (pp.n_msk / 2) % (4 * kP) == 0) ? 2 : 1;   // a TMA box row is a multiple of 16 bytes
+    if (!make_out_map(&tm, mask, dtype, (unsigned long long)M, pp.n_msk, pp.n_msk / pp.mask_parts, CU_TENSOR_MAP_SWIZZLE_NONE)) return DCNV3_E_SHAPE;
     if (!make_k_major_map(&tx, x, dtype, (unsigned long long)M, C, BM)) return DCNV3_E_SHAPE;
     if (!make_k_major_map(&tw0, w_cat, dtype, (unsigned long long)n_pad, C, pp.nh[0])) return DCNV3_E_SHAPE;
     if (!make_k_major_map(&tw1, w_cat, dtype, (unsigned long long)n_pad, C, pp.nh[1])) return DCNV3_E_SHAPE;
@@ -286,8 +368,7 @@ static int launch(const void *x, const void *w_cat, const float *bias_cat, void 
     }
     const int per_half = std::max(1, std::min(pp.m_tiles, num_sms / 2));
     cudaFuncSetAttribute(offset_mask_proj<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    offset_mask_proj<T><<<dim3(per_half, 2), kThreads, smem, stream>>>(tx, tw0, tw1, bias_cat, static_cast<T *>(offset),
-                                                                        static_cast<T *>(mask), pp);
+    offset_mask_proj<T><<<dim3(per_half, 2), kThreads, smem, stream>>>(tx, tw0, tw1, to, tm, bias_cat, pp);
     return (int)cudaGetLastError();
 }
 
@@ -306,7 +387,7 @@ int dcnv3_offset_mask_proj_sm100(const void *x, const void *w_cat, const float *
         return DCNV3_E_SHAPE;
     if (M == 0) return DCNV3_OK;
     if (!x || !w_cat || !bias_cat || !offset || !mask) return DCNV3_E_NULL;
-    if (((uintptr_t)x | (uintptr_t)w_cat | (uintptr_t)offset) % 16 || (uintptr_t)mask % 8 || (uintptr_t)bias_cat % 4)
+    if (((uintptr_t)x | (uintptr_t)w_cat | (uintptr_t)offset | (uintptr_t)mask) % 16 || (uintptr_t)bias_cat % 4)
         return DCNV3_E_ALIGN;
     if (dtype == DCNV3_F16)
         return dcnv3::proj::launch<__half>(x, w_cat, bias_cat, offset, mask, M, C, G, dtype, (cudaStream_t)stream);
