@@ -184,6 +184,60 @@ def run_reference_arm(args, rank, world):
     }))
 
 
+# ------------------------------------------------------------------------------- next row (8f.1)
+def proj_row(dev, dtype):
+    """Fused offset/mask projection vs eager at the bench shape; CUDA-graph replays so that the
+    numbers are kernel time, inputs rotating over 4 buffers (> L2)."""
+    import torch.nn.functional as F
+    from yolo_somi_b200.ops_dcnv3.functions import offset_mask_proj as omp
+    M, C, G = CFG["N"] * CFG["H"] * CFG["W"], CFG["C"], CFG["G"]
+    if not omp.eligible(torch.empty(1, C, device=dev), G, CFG["K"] ** 2, dtype):
+        return None
+    g = torch.Generator(device="cpu").manual_seed(7)
+    xs = [torch.randn(M, C, generator=g).to(dtype).to(dev) for _ in range(4)]
+    w_off = (torch.randn(2 * G * 9, C, generator=g) / 16).to(dtype).to(dev)
+    w_msk = (torch.randn(G * 9, C, generator=g) / 8).to(dtype).to(dev)
+    b_off, b_msk = torch.randn(2 * G * 9, generator=g).to(dtype).to(dev), torch.randn(G * 9, generator=g).to(dtype).to(dev)
+
+    def fused(x):
+        with torch.no_grad():
+            return omp.OffsetMaskProj.apply(x, w_off, b_off, w_msk, b_msk, G, dtype)
+
+    def eager(x):   # models/ops_dcnv3/modules/dcnv3.py:330-334
+        with torch.no_grad():
+            o = F.linear(x, w_off, b_off)
+            m = F.softmax(F.linear(x, w_msk, b_msk).reshape(M, G, -1).float(), -1).reshape(M, -1).to(dtype)
+            return o, m
+
+    def graph_us(fn, reps=8, replays=6):
+        for i in range(3):
+            fn(xs[i % 4])
+        torch.cuda.synchronize()
+        gr, st = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            with torch.cuda.graph(gr):
+                for i in range(reps):
+                    fn(xs[i % 4])
+        gr.replay(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(replays):
+            gr.replay()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / (reps * replays)
+
+    of, mf = fused(xs[0]); oe, me = eager(xs[0])
+    err = max(float((of.float() - oe.float()).abs().max()), float((mf.float() - me.float()).abs().max()))
+    t_f, t_e = graph_us(fused), graph_us(eager)
+    by = 2 * (M * C + M * 3 * G * 9) + 2 * 3 * G * 9 * C
+    peak, _ = peaks()
+    return {"fused_us": t_f, "eager_us": t_e, "speedup": t_e / t_f, "algorithmic_bytes": by,
+            "achieved_gbs": by / t_f / 1e3, "hbm_frac": by / t_f / 1e3 / peak,
+            "tflops": 2.0 * M * C * 3 * G * 9 / t_f / 1e6, "max_abs_diff_vs_eager": err,
+            "what": "offset + mask linears + softmax over the 9 points (modules/dcnv3.py:330-334) as one "
+                    "tcgen05 GEMM with TMEM accumulators and a bias/softmax/cast epilogue"}
+
+
 # ------------------------------------------------------------------------------- our arm
 def run_ours(args, rank, world, local_rank):
     import DCNv3  # the drop-in shim (repo root) over libdcnv3_sm100.so; raises if the .so is absent
@@ -268,6 +322,10 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py: host pipeline output differs from the device-resident forward")
     pipe.close()
 
+    # ---- SURVEY 8(f) rank 1, measured beside the sampler: the fused offset/mask projection
+    # (tcgen05 GEMM + bias + softmax epilogue) against the layer's two linears + softmax, same shape
+    proj = proj_row(dev, dtype) if rank == 0 else None
+
     if rank != 0:
         return
     pts = points_per_step()
@@ -301,6 +359,8 @@ def run_ours(args, rank, world, local_rank):
                    "step_gbs": (ab["fwd"] + ab["bwd"]) / (ms / args.steps * 1e-3) / 1e9,
                    "step_frac": (ab["fwd"] + ab["bwd"]) / (ms / args.steps * 1e-3) / 1e9 / peak},
     }
+    if proj is not None:
+        line["next_rows"] = {"offset_mask_proj": proj}
     if world == 1 and not args.no_cpu:
         t, threads = cpu_reference_run(2, 3)
         line["cpu_baseline"] = {

@@ -55,6 +55,7 @@ struct Params {
     int n_off, n_msk;          // 2GP, GP
     int nh[2];                 // columns of the two halves (multiples of 16, <= 256)
     int G;
+    int ctas[2];               // persistent CTAs serving each half
     int mask_parts;            // 2: each epilogue part takes half a mask row; 1: part 1 takes it all
     int dbg;
 };
@@ -130,6 +131,8 @@ offset_mask_proj(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int half = blockIdx.y;
+    const int n_ctas = pp.ctas[half];          // CTAs of this half stride over the row tiles
+    if ((int)blockIdx.x >= n_ctas) return;
     const int NH = pp.nh[half], col0 = half ? pp.nh[0] : 0;
     const int b_chunk_bytes = NH * 128;
     // 128-byte-swizzled operand tiles need 1024-byte alignment: align the dynamic region by hand
@@ -161,7 +164,7 @@ offset_mask_proj(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             mbar_expect_tx(&b_bar, (unsigned)(pp.kchunks * b_chunk_bytes));
             for (int kc = 0; kc < pp.kchunks; ++kc) tma_load_2d(b_smem + kc * b_chunk_bytes, tw, &b_bar, kc * BK, col0);
             int s = 0, ph = 0;
-            for (int t = blockIdx.x; t < pp.m_tiles; t += gridDim.x) {
+            for (int t = blockIdx.x; t < pp.m_tiles; t += n_ctas) {
                 for (int kc = 0; kc < pp.kchunks; ++kc) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     mbar_expect_tx(&full_bar[s], kAStageBytes);
@@ -176,7 +179,7 @@ offset_mask_proj(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             const uint32_t idesc = umma_idesc(sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value ? 1 : 0, BM, NH);
             mbar_wait(&b_bar, 0);
             int s = 0, ph = 0, it = 0;
-            for (int t = blockIdx.x; t < pp.m_tiles; t += gridDim.x, ++it) {
+            for (int t = blockIdx.x; t < pp.m_tiles; t += n_ctas, ++it) {
                 const int as = it & 1, aph = (it >> 1) & 1;
                 mbar_wait(&acc_empty[as], aph ^ 1);        // the epilogue has drained this accumulator stage
                 tc_fence_after();
@@ -217,7 +220,7 @@ offset_mask_proj(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         int ob = 0;                                        // next offset staging buffer
         const int m_pitch = m_cols * 2;                    // bytes per staged (half) mask row
         int it = 0;
-        for (int t = blockIdx.x; t < pp.m_tiles; t += gridDim.x, ++it) {
+        for (int t = blockIdx.x; t < pp.m_tiles; t += n_ctas, ++it) {
             const int as = it & 1, aph = (it >> 1) & 1;
             mbar_wait(&acc_full[as], aph);
             tc_fence_after();
@@ -366,9 +369,14 @@ static int launch(const void *x, const void *w_cat, const float *bias_cat, void 
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    const int per_half = std::max(1, std::min(pp.m_tiles, num_sms / 2));
+    // the second half (offset tail + masks with their softmax) has the heavier epilogue: it gets
+    // more of the SMs (one CTA per SM; measured optimum at cfg2, see profiles/)
+    int share0 = 42;
+    if (const char *e = getenv("DCNV3_PROJ_SPLIT")) share0 = std::max(10, std::min(90, atoi(e)));
+    pp.ctas[0] = std::max(1, std::min(pp.m_tiles, num_sms * share0 / 100));
+    pp.ctas[1] = std::max(1, std::min(pp.m_tiles, num_sms - pp.ctas[0]));
     cudaFuncSetAttribute(offset_mask_proj<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    offset_mask_proj<T><<<dim3(per_half, 2), kThreads, smem, stream>>>(tx, tw0, tw1, to, tm, bias_cat, pp);
+    offset_mask_proj<T><<<dim3(std::max(pp.ctas[0], pp.ctas[1]), 2), kThreads, smem, stream>>>(tx, tw0, tw1, to, tm, bias_cat, pp);
     return (int)cudaGetLastError();
 }
 
