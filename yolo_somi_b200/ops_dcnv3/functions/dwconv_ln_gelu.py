@@ -1,0 +1,89 @@
+"""Fused producer of the DCNv3 layer's x1: depthwise conv + LayerNorm + GELU, channels-last, one
+kernel (libdcnv3_sm100.so, ``dcnv3_dwconv_ln_gelu_sm100``) instead of the reference's
+permute -> Conv2d(groups=C) -> permute -> LayerNorm -> GELU (models/ops_dcnv3/modules/dcnv3.py:
+276-289,328-329).  The backward recomputes the unfused form under autograd (PyTorch kernels).
+"""
+from __future__ import annotations
+
+import os
+import weakref
+
+import torch
+import torch.nn.functional as F
+
+from ... import _native
+
+_DT = {torch.float16: _native.F16, torch.bfloat16: _native.BF16}
+
+
+def eligible(x, conv, norm, act, dtype) -> bool:
+    if os.environ.get("DCNV3_FUSED_DWCONV", "1") in ("0", ""):
+        return False
+    k = conv.kernel_size
+    return (x.is_cuda and dtype in _DT and x.dim() == 4 and x.shape[-1] in (64, 128, 256)
+            and isinstance(norm, torch.nn.LayerNorm) and isinstance(act, torch.nn.GELU)
+            and getattr(act, "approximate", "none") == "none" and k[0] == k[1] and k[0] % 2 == 1 and k[0] <= 7
+            and conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.padding == ((k[0] - 1) // 2,) * 2
+            and conv.groups == x.shape[-1] and conv.bias is not None and norm.elementwise_affine)
+
+
+def _unfused(x, w, b, gamma, beta, eps):
+    """The reference's sequence on a channels-last tensor (used by the backward)."""
+    c = x.shape[-1]
+    y = F.conv2d(x.permute(0, 3, 1, 2), w, b, padding=(w.shape[-1] - 1) // 2, groups=c).permute(0, 2, 3, 1)
+    return F.gelu(F.layer_norm(y, (c,), gamma, beta, eps))
+
+
+_PACKED = {}   # id(conv weight) -> (weak refs, versions, dtype, packed tensors)
+
+
+def _pack(w, b, gamma, beta, dtype):
+    """Kernel-layout copies of the parameters ([k*k][C] taps in the I/O dtype, fp32 vectors),
+    rebuilt only when one of the four tensors is another object or was modified in place."""
+    tensors = (w, b, gamma, beta)
+    ver = tuple(t._version for t in tensors)
+    hit = _PACKED.get(id(w))
+    if hit is not None and hit[1] == ver and hit[2] == dtype and all(r() is t for r, t in zip(hit[0], tensors)):
+        return hit[3]
+    c, k = w.shape[0], w.shape[-1]
+    packed = (w.detach().reshape(c, k * k).t().to(dtype).contiguous(),
+              *(t.detach().float().contiguous() for t in (b, gamma, beta)))
+    if len(_PACKED) > 64:
+        _PACKED.clear()
+    _PACKED[id(w)] = (tuple(weakref.ref(t) for t in tensors), ver, dtype, packed)
+    return packed
+
+
+class DwConvLnGelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, gamma, beta, eps, dtype):
+        lib = _native.load()
+        n, h, wd, c = x.shape
+        k = w.shape[-1]
+        x16 = x.to(dtype).contiguous()
+        wk, bf, gf, tf = _pack(w, b, gamma, beta, dtype)   # named: they outlive the launch
+        out = torch.empty_like(x16)
+        with torch.cuda.device(x.device):
+            rc = lib.dcnv3_dwconv_ln_gelu_sm100(
+                x16.data_ptr(), wk.data_ptr(), bf.data_ptr(), gf.data_ptr(), tf.data_ptr(),
+                out.data_ptr(), n, h, wd, c, k, float(eps), _DT[dtype], torch.cuda.current_stream().cuda_stream)
+        _native.check(rc, "dcnv3_dwconv_ln_gelu_sm100")
+        ctx.save_for_backward(x, w, b, gamma, beta)
+        ctx.eps, ctx.dtype = eps, dtype
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, w, b, gamma, beta = ctx.saved_tensors
+        with torch.enable_grad():
+            leaves = [t.detach().requires_grad_(True) for t in (x, w, b, gamma, beta)]
+            xin = leaves[0].to(ctx.dtype)
+            y = _unfused(xin, *(t.to(ctx.dtype) for t in leaves[1:]), ctx.eps)
+            grads = torch.autograd.grad(y, leaves, g.to(y.dtype), allow_unused=True)
+        return (*grads, None, None)
+
+
+def dwconv_ln_gelu(x, conv, norm, dtype):
+    """x1 [N,H,W,C] in ``dtype`` from the channels-last input x."""
+    return DwConvLnGelu.apply(x, conv.weight, conv.bias, norm.weight, norm.bias, norm.eps, dtype)

@@ -22,7 +22,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from ..functions import DCNv3Function
-from ..functions import offset_mask_proj
+from ..functions import dwconv_ln_gelu, offset_mask_proj
 
 
 class to_channels_first(nn.Module):
@@ -125,7 +125,12 @@ class DCNv3(nn.Module):
         """input, output: (N, H, W, C)."""
         n, h, w, _ = input.shape
         x = self.input_proj(input)
-        x1 = self.dw_conv(input.permute(0, 3, 1, 2))
+        conv, norm, act = self.dw_conv[0], self.dw_conv[1][-1], self.dw_conv[2]
+        if dwconv_ln_gelu.eligible(input, conv, norm, act, x.dtype):
+            # depthwise conv + LayerNorm + GELU in one channels-last pass (csrc/dcnv3_dwconv.cu)
+            x1 = dwconv_ln_gelu.dwconv_ln_gelu(input, conv, norm, x.dtype)
+        else:
+            x1 = self.dw_conv(input.permute(0, 3, 1, 2))
         if offset_mask_proj.eligible(x1, self.group, self.kernel_size * self.kernel_size, x.dtype):
             # one tcgen05 GEMM with bias, softmax and cast in its epilogue (csrc/dcnv3_proj.cu)
             offset, mask = offset_mask_proj.offset_mask_proj(x1, self.offset, self.mask, self.group, x.dtype)
