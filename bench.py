@@ -238,6 +238,46 @@ def proj_row(dev, dtype):
                     "tcgen05 GEMM with TMEM accumulators and a bias/softmax/cast epilogue"}
 
 
+def layer_row(dev, dtype):
+    """The whole DCNv3 layer (modules/dcnv3.py:222-379) forward + backward at the bench shape: the
+    mirrored layer with both fused producers (dwconv+LN+GELU, offset/mask projection) on, and with
+    them off (the reference's own sequence of PyTorch ops around the same sampler; the bias
+    gradients of the tall projections are ones-row GEMMs in both columns)."""
+    from yolo_somi_b200.ops_dcnv3.modules import DCNv3 as Layer
+    torch.manual_seed(0)
+    layer = Layer(channels=CFG["C"], group=CFG["G"], kernel_size=CFG["K"], offset_scale=CFG["sigma"]).to(dev).to(dtype)
+    with torch.no_grad():
+        layer.offset.weight.normal_(0, 0.02); layer.mask.weight.normal_(0, 0.1)
+    xs = [torch.randn(CFG["N"], CFG["H"], CFG["W"], CFG["C"], device=dev, dtype=dtype, requires_grad=True) for _ in range(2)]
+    go = torch.randn(CFG["N"], CFG["H"], CFG["W"], CFG["C"], device=dev, dtype=dtype)
+
+    def timed(n=10):
+        for i in range(3):
+            layer(xs[i % 2]).backward(go)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            layer(xs[i % 2]).backward(go)
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    fused_ms = timed()
+    old = {k: os.environ.get(k) for k in ("DCNV3_FUSED_PROJ", "DCNV3_FUSED_DWCONV")}
+    os.environ["DCNV3_FUSED_PROJ"] = "0"; os.environ["DCNV3_FUSED_DWCONV"] = "0"
+    try:
+        unfused_ms = timed()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return {"fwd_bwd_ms_fused_producers": fused_ms, "fwd_bwd_ms_pytorch_producers": unfused_ms,
+            "what": "DCNv3 layer forward + backward (input_proj, dwconv+LN+GELU, offset/mask, sampler, "
+                    "output_proj), N=16 80x80 C=256 G=16 bf16; sampler = this library in both columns"}
+
+
 # ------------------------------------------------------------------------------- our arm
 def run_ours(args, rank, world, local_rank):
     import DCNv3  # the drop-in shim (repo root) over libdcnv3_sm100.so; raises if the .so is absent
@@ -325,6 +365,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- SURVEY 8(f) rank 1, measured beside the sampler: the fused offset/mask projection
     # (tcgen05 GEMM + bias + softmax epilogue) against the layer's two linears + softmax, same shape
     proj = proj_row(dev, dtype) if rank == 0 else None
+    layer = layer_row(dev, dtype) if rank == 0 else None
 
     if rank != 0:
         return
@@ -360,7 +401,7 @@ def run_ours(args, rank, world, local_rank):
                    "step_frac": (ab["fwd"] + ab["bwd"]) / (ms / args.steps * 1e-3) / 1e9 / peak},
     }
     if proj is not None:
-        line["next_rows"] = {"offset_mask_proj": proj}
+        line["next_rows"] = {"offset_mask_proj": proj, "layer": layer}
     if world == 1 and not args.no_cpu:
         t, threads = cpu_reference_run(2, 3)
         line["cpu_baseline"] = {

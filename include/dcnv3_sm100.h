@@ -155,12 +155,14 @@ DCNV3_API int dcnv3_offset_mask_proj_sm100(const void *x, const void *w_cat, con
  * (models/ops_dcnv3/modules/dcnv3.py:276-289,328-329; build_norm_layer :41-62).
  *
  *   x [N,H,W,C] 16-bit;  w_dw [k*k][C] in the dtype of x (= conv.weight[c,0,j,i] at [(j*k+i)*C + c]);
- *   b_dw, gamma, beta [C] fp32;  out [N,H,W,C] in the dtype of x.
+ *   b_dw, gamma, beta [C] fp32;  out [N,H,W,C] in the dtype of x;  conv_out: NULL, or [N,H,W,C]
+ *   receiving the convolution's output before the LayerNorm (what a backward pass needs).
  * Eligible: C in {64, 128, 256}, odd k <= 7, fp16 / bf16; DCNV3_E_SHAPE otherwise.
  */
 DCNV3_API int dcnv3_dwconv_ln_gelu_sm100(const void *x, const void *w_dw, const float *b_dw,
-                        const float *gamma, const float *beta, void *out, int N, int H, int W, int C,
-                        int k, float eps, int dtype, void *stream /* cudaStream_t */);
+                        const float *gamma, const float *beta, void *out, void *conv_out,
+                        int N, int H, int W, int C, int k, float eps, int dtype,
+                        void *stream /* cudaStream_t */);
 
 #ifdef __cplusplus
 }

@@ -65,7 +65,7 @@ def load() -> ctypes.CDLL:
     lib.dcnv3_offset_mask_proj_sm100.restype = c_int
     lib.dcnv3_offset_mask_proj_sm100.argtypes = [c_vp] * 5 + [ctypes.c_longlong] + [c_int] * 4 + [c_vp]
     lib.dcnv3_dwconv_ln_gelu_sm100.restype = c_int
-    lib.dcnv3_dwconv_ln_gelu_sm100.argtypes = [c_vp] * 6 + [c_int] * 5 + [c_f, c_int, c_vp]
+    lib.dcnv3_dwconv_ln_gelu_sm100.argtypes = [c_vp] * 7 + [c_int] * 5 + [c_f, c_int, c_vp]
     got = lib.dcnv3_sm100_abi_version()
     if got != ABI_VERSION:
         raise DCNv3NativeError(f"{LIB_PATH}: ABI version {got}, expected {ABI_VERSION}; rebuild")

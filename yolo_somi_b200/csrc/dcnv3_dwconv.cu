@@ -55,7 +55,8 @@ template <typename T, int K /* compile-time kernel size (weights live in registe
 __global__ void __launch_bounds__(kThreads)
 dwconv_ln_gelu(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ wdw /* [k*k][C], I/O dtype */,
                const float *__restrict__ bdw, const float *__restrict__ gamma, const float *__restrict__ beta,
-               T *__restrict__ out, const Params pp) {
+               T *__restrict__ out, T *__restrict__ conv_out /* pre-LayerNorm values for the backward, or null */,
+               const Params pp) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x;
@@ -131,13 +132,16 @@ dwconv_ln_gelu(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ w
 #pragma unroll
         for (int e = 0; e < 8; ++e) y[e] = gelu_erf((acc[e] - mean) * rstd * g8[e] + b8[e]);
         const int ox = x0 + px, oy = y0 + py;
-        if (ox < pp.W && oy < pp.H)
-            *reinterpret_cast<uint4 *>(out + (((size_t)n * pp.H + oy) * pp.W + ox) * pp.C + ch0) = pack<T>(y);
+        if (ox < pp.W && oy < pp.H) {
+            const size_t at = (((size_t)n * pp.H + oy) * pp.W + ox) * pp.C + ch0;
+            *reinterpret_cast<uint4 *>(out + at) = pack<T>(y);
+            if (conv_out) *reinterpret_cast<uint4 *>(conv_out + at) = pack<T>(acc);
+        }
     }
 }
 
 template <typename T>
-static int launch(const void *x, const void *wdw_v, const float *bdw, const float *gamma, const float *beta, void *out,
+static int launch(const void *x, const void *wdw_v, const float *bdw, const float *gamma, const float *beta, void *out, void *conv_out,
                   int N, int H, int W, int C, int k, float eps, int dtype, cudaStream_t stream) {
     const T *wdw = static_cast<const T *>(wdw_v);
     Params pp;
@@ -152,7 +156,7 @@ static int launch(const void *x, const void *wdw_v, const float *bdw, const floa
     const dim3 grid(pp.tiles_x * pp.tiles_y, N);
     auto go = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<grid, kThreads, smem, stream>>>(tmap, wdw, bdw, gamma, beta, static_cast<T *>(out), pp);
+        kern<<<grid, kThreads, smem, stream>>>(tmap, wdw, bdw, gamma, beta, static_cast<T *>(out), static_cast<T *>(conv_out), pp);
     };
     if (k == 3) {
         if (C == 256) go(dwconv_ln_gelu<T, 3, 32>); else if (C == 128) go(dwconv_ln_gelu<T, 3, 16>); else go(dwconv_ln_gelu<T, 3, 8>);
@@ -166,14 +170,14 @@ static int launch(const void *x, const void *wdw_v, const float *bdw, const floa
 }  // namespace dcnv3
 
 extern "C" int dcnv3_dwconv_ln_gelu_sm100(const void *x, const void *w_dw, const float *b_dw, const float *gamma,
-                                          const float *beta, void *out, int N, int H, int W, int C, int k, float eps,
+                                          const float *beta, void *out, void *conv_out, int N, int H, int W, int C, int k, float eps,
                                           int dtype, void *stream) {
     if (dtype != DCNV3_F16 && dtype != DCNV3_BF16) return DCNV3_E_DTYPE;
     if (N < 0 || H <= 0 || W <= 0 || k <= 0 || k % 2 == 0 || k > 7 || !(C == 64 || C == 128 || C == 256)) return DCNV3_E_SHAPE;
     if (N == 0) return DCNV3_OK;
     if (!x || !w_dw || !b_dw || !gamma || !beta || !out) return DCNV3_E_NULL;
-    if (((uintptr_t)x | (uintptr_t)out | (uintptr_t)w_dw) % 16) return DCNV3_E_ALIGN;
+    if (((uintptr_t)x | (uintptr_t)out | (uintptr_t)w_dw | (uintptr_t)conv_out) % 16) return DCNV3_E_ALIGN;
     if (dtype == DCNV3_F16)
-        return dcnv3::dwc::launch<__half>(x, w_dw, b_dw, gamma, beta, out, N, H, W, C, k, eps, dtype, (cudaStream_t)stream);
-    return dcnv3::dwc::launch<__nv_bfloat16>(x, w_dw, b_dw, gamma, beta, out, N, H, W, C, k, eps, dtype, (cudaStream_t)stream);
+        return dcnv3::dwc::launch<__half>(x, w_dw, b_dw, gamma, beta, out, conv_out, N, H, W, C, k, eps, dtype, (cudaStream_t)stream);
+    return dcnv3::dwc::launch<__nv_bfloat16>(x, w_dw, b_dw, gamma, beta, out, conv_out, N, H, W, C, k, eps, dtype, (cudaStream_t)stream);
 }

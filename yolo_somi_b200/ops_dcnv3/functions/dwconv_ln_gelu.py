@@ -63,25 +63,35 @@ class DwConvLnGelu(torch.autograd.Function):
         x16 = x.to(dtype).contiguous()
         wk, bf, gf, tf = _pack(w, b, gamma, beta, dtype)   # named: they outlive the launch
         out = torch.empty_like(x16)
+        need_grad = any(ctx.needs_input_grad[:5])
+        conv_out = torch.empty_like(x16) if need_grad else None     # pre-LayerNorm values for the backward
         with torch.cuda.device(x.device):
             rc = lib.dcnv3_dwconv_ln_gelu_sm100(
                 x16.data_ptr(), wk.data_ptr(), bf.data_ptr(), gf.data_ptr(), tf.data_ptr(),
-                out.data_ptr(), n, h, wd, c, k, float(eps), _DT[dtype], torch.cuda.current_stream().cuda_stream)
+                out.data_ptr(), conv_out.data_ptr() if need_grad else None, n, h, wd, c, k, float(eps),
+                _DT[dtype], torch.cuda.current_stream().cuda_stream)
         _native.check(rc, "dcnv3_dwconv_ln_gelu_sm100")
-        ctx.save_for_backward(x, w, b, gamma, beta)
-        ctx.eps, ctx.dtype = eps, dtype
+        ctx.save_for_backward(x16, w, b, gamma, beta, conv_out)
+        ctx.eps, ctx.dtype, ctx.in_dtype = eps, dtype, x.dtype
         return out
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g):
-        x, w, b, gamma, beta = ctx.saved_tensors
+        x16, w, b, gamma, beta, conv_out = ctx.saved_tensors
+        c, k = x16.shape[-1], w.shape[-1]
+        # LayerNorm + GELU re-derived from the saved convolution output (two cheap passes) ...
         with torch.enable_grad():
-            leaves = [t.detach().requires_grad_(True) for t in (x, w, b, gamma, beta)]
-            xin = leaves[0].to(ctx.dtype)
-            y = _unfused(xin, *(t.to(ctx.dtype) for t in leaves[1:]), ctx.eps)
-            grads = torch.autograd.grad(y, leaves, g.to(y.dtype), allow_unused=True)
-        return (*grads, None, None)
+            y = conv_out.detach().requires_grad_(True)
+            gl, bl = gamma.detach().to(ctx.dtype).requires_grad_(True), beta.detach().to(ctx.dtype).requires_grad_(True)
+            z = F.gelu(F.layer_norm(y, (c,), gl, bl, ctx.eps))
+            g_y, g_gamma, g_beta = torch.autograd.grad(z, (y, gl, bl), g.to(z.dtype))
+        # ... and the convolution's own backward, without re-running its forward
+        g_x, g_w, g_b = torch.ops.aten.convolution_backward(
+            g_y.permute(0, 3, 1, 2), x16.permute(0, 3, 1, 2), w.detach().to(ctx.dtype), [c], [1, 1],
+            [(k - 1) // 2] * 2, [1, 1], False, [0, 0], c, [True, True, True])
+        return (g_x.permute(0, 2, 3, 1).to(ctx.in_dtype), g_w.to(w.dtype), g_b.to(b.dtype), g_gamma.to(gamma.dtype),
+                g_beta.to(beta.dtype), None, None)
 
 
 def dwconv_ln_gelu(x, conv, norm, dtype):

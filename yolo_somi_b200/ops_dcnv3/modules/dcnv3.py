@@ -67,6 +67,36 @@ def _is_power_of_2(n):
     return n != 0 and (n & (n - 1)) == 0
 
 
+class _TallLinear(torch.autograd.Function):
+    """``F.linear`` for tall 16-bit activations [M, C] with M >> C: identical forward; the backward
+    takes the bias gradient as a ones-row GEMM instead of autograd's dim-0 reduction kernel, which at
+    the layer's M = N*H*W = 102,400 costs 100-300 us per projection (profiles/README.md, r1_v4)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return F.linear(x, weight, bias)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g2, x2 = g.reshape(-1, g.shape[-1]), x.reshape(-1, x.shape[-1])
+        gx = (g2 @ weight).reshape(x.shape) if ctx.needs_input_grad[0] else None
+        gw = g2.t() @ x2 if ctx.needs_input_grad[1] else None
+        gb = None
+        if ctx.needs_input_grad[2]:
+            gb = (torch.ones(1, g2.shape[0], dtype=g2.dtype, device=g2.device) @ g2).reshape(-1)
+        return gx, gw, gb
+
+
+def _linear(x, lin):
+    if (x.is_cuda and x.dtype in (torch.float16, torch.bfloat16) and lin.bias is not None
+            and lin.weight.dtype == x.dtype and torch.is_grad_enabled() and x.numel() // x.shape[-1] >= 4096):
+        return _TallLinear.apply(x, lin.weight, lin.bias)
+    return lin(x)
+
+
 class CenterFeatureScaleModule(nn.Module):
     def forward(self, query, center_feature_scale_proj_weight, center_feature_scale_proj_bias):
         return F.linear(query, center_feature_scale_proj_weight,
@@ -124,7 +154,7 @@ class DCNv3(nn.Module):
     def forward(self, input):
         """input, output: (N, H, W, C)."""
         n, h, w, _ = input.shape
-        x = self.input_proj(input)
+        x = _linear(input, self.input_proj)
         conv, norm, act = self.dw_conv[0], self.dw_conv[1][-1], self.dw_conv[2]
         if dwconv_ln_gelu.eligible(input, conv, norm, act, x.dtype):
             # depthwise conv + LayerNorm + GELU in one channels-last pass (csrc/dcnv3_dwconv.cu)
@@ -146,4 +176,4 @@ class DCNv3(nn.Module):
                                                    self.center_feature_scale_proj_bias)
             cfs = cfs.repeat_interleave(self.group_channels, dim=-1)  # per group -> per channel
             y = y * (1 - cfs) + x * cfs
-        return self.output_proj(y)
+        return _linear(y, self.output_proj)
