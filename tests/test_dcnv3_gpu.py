@@ -571,3 +571,41 @@ def test_layer_with_fused_producer_trains(monkeypatch):
     for name, a, w in zip(("y", "grad_x", "grad_dw", "grad_mask_w"), fused, ref):
         rel = float(np.linalg.norm(a - w) / (np.linalg.norm(w) + 1e-30))
         assert rel <= (2e-2 if name == "y" else 8e-2), (name, rel)
+
+
+# ----------------------------------------------------------------------------- NCHW hosting modules
+@pytest.mark.parametrize("name", ["DCNv3_YOLO", "Bottleneck_DCNv3", "C3_DCNv3", "C2f_DCNv3"])
+def test_nchw_hosting_modules_forward_backward(name):
+    """the zoo-style NCHW wrappers around the channels-last layer -- shapes, dtype,
+    gradient flow to every parameter, and the init property of the reference layer (zero offset /
+    mask linears => DCNv3 core == 3x3 average pool of input_proj's output)."""
+    from yolo_somi_b200 import hosting
+    torch.manual_seed(0)
+    c1, c2 = (64, 128) if name in ("DCNv3_YOLO", "C3_DCNv3", "C2f_DCNv3") else (128, 128)
+    mod = getattr(hosting, name)(c1, c2).cuda().to(torch.bfloat16).train()
+    x = torch.randn(2, c1, 24, 20, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    y = mod(x)
+    assert y.shape == (2, c2, 24, 20) and y.dtype == torch.bfloat16
+    y.float().square().mean().backward()
+    assert x.grad is not None and torch.isfinite(x.grad.float()).all()
+    missing = [n for n, p in mod.named_parameters() if p.grad is None
+               and not n.endswith(("offset.weight", "offset.bias"))]   # zero mask => no signal into offsets at init
+    assert not missing, missing
+
+
+def test_hosting_wrapper_is_average_pool_at_init():
+    from yolo_somi_b200 import hosting
+    torch.manual_seed(1)
+    w = hosting.DCNv3_YOLO(64, 64, act=nn_identity()).cuda().float().eval()
+    x = torch.randn(1, 64, 12, 12, device="cuda")
+    with torch.no_grad():
+        y = w(x)
+        l = w.dcn
+        xp = l.input_proj(x.permute(0, 2, 3, 1))
+        pooled = torch.nn.functional.avg_pool2d(xp.permute(0, 3, 1, 2), 3, 1, 1, count_include_pad=True)
+        want = w.bn(l.output_proj(pooled.permute(0, 2, 3, 1)).permute(0, 3, 1, 2))
+    assert float((y - want).abs().max()) < 1e-4
+
+
+def nn_identity():
+    return torch.nn.Identity()
