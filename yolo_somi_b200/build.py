@@ -20,7 +20,7 @@ INCLUDE = PKG.parent / "include"
 LIB = PKG / "libdcnv3_sm100.so"
 OBJ_DIR = PKG / "csrc" / "_obj"
 
-SOURCES = ["dcnv3_forward.cu", "dcnv3_forward_tile.cu", "dcnv3_forward_gs.cu", "dcnv3_forward_mma.cu", "dcnv3_backward.cu", "dcnv3_backward_tile.cu", "dcnv3_backward_mma.cu", "dcnv3_backward_mma2.cu", "dcnv3_backward_strip.cu", "dcnv3_host_pipeline.cu", "dcnv3_proj.cu", "dcnv3_dwconv.cu", "dcnv3_capi.cu"]
+SOURCES = ["dcnv3_forward.cu", "dcnv3_forward_tile.cu", "dcnv3_forward_gs.cu", "dcnv3_forward_mma.cu", "dcnv3_backward.cu", "dcnv3_backward_tile.cu", "dcnv3_backward_mma.cu", "dcnv3_backward_mma2.cu", "dcnv3_backward_strip.cu", "dcnv3_backward_dots.cu", "dcnv3_backward_vmma.cu", "dcnv3_host_pipeline.cu", "dcnv3_proj.cu", "dcnv3_dwconv.cu", "dcnv3_capi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",   # no --use_fast_math: IEEE div/sqrt, denormals kept

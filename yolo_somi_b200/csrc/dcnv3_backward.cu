@@ -460,6 +460,27 @@ static cudaError_t backward_typed(const void *value, const void *offset, const v
         float *acc = reinterpret_cast<float *>(static_cast<char *>(workspace) + kWorkspaceHeader);
         if ((err = cudaMemsetAsync(acc, 0, plane * sizeof(float), stream)) != cudaSuccess) return err;
         const int dtype_tag = std::is_same<T, __half>::value ? 1 : 2;
+        // DCNV3_BWD=split (development knob while it is being measured): channel sums and grad_value
+        // in two high-occupancy kernels instead of the fused strip kernel
+        {
+            const char *e = std::getenv("DCNV3_BWD");
+            const bool split = e && e[0] == 's' && e[1] == 'p';
+            if (split && vec_ok && q.G % 8 == 0) {
+                cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
+                // eligibility of both halves is the same set of shapes; check the value half first
+                const char *ev = std::getenv("DCNV3_VALUE");   // "hmma": register-accumulator value kernel
+                const bool hmma = ev && ev[0] == 'h';
+                if ((!hmma && try_launch_backward_vmma(offset, mask, grad_out, acc, q, dtype_tag, stream, &e2)) ||
+                    try_launch_backward_vstrip(offset, mask, grad_out, acc, q, dtype_tag, stream, &e2)) {
+                    if (e2 != cudaSuccess) return e2;
+                    if (!try_launch_backward_dots(value, offset, mask, grad_out, grad_offset, grad_mask, q, dtype_tag, stream, &e1))
+                        return cudaErrorInvalidConfiguration;
+                    if (e1 != cudaSuccess) return e1;
+                    narrow_f32_kernel<T><<<aux_blocks, 256, 0, stream>>>(acc, gv, plane);
+                    return cudaGetLastError();
+                }
+            }
+        }
         if (!(vec_ok && (try_launch_backward_strip(value, offset, mask, grad_out, acc, grad_offset, grad_mask, q, dtype_tag, stream, &err) ||
                          try_launch_backward_mma2(value, offset, mask, grad_out, acc, grad_offset, grad_mask, q, dtype_tag, stream, &err) ||
                          try_launch_backward_mma(value, offset, mask, grad_out, acc, grad_offset, grad_mask, q, dtype_tag, stream, &err) ||

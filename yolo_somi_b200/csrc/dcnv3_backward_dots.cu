@@ -1,0 +1,266 @@
+// dcnv3_backward_dots.cu -- first half of the split DCNv3 backward for 16-bit I/O, group_channels == 16,
+// 3x3 / stride 1 / dilation 1, G % 8 == 0: grad_offset and grad_mask (the per-point channel sums
+// of dcnv3_im2col_cuda.cuh:106-146, 278-370) with the forward's group-slice layout.
+//
+// Why split (profiles/README.md, r1_v4): the fused strip backward holds a 12 KB coefficient tile
+// per warp, so only 8 warps fit an SM and every warp issues one instruction per ~4.4 cycles; its
+// gather also needs the per-point corner rotation.  The channel sums need no coefficient tile at
+// all, so they run here exactly like the forward (dcnv3_forward_gs.cu): a CTA of 512 threads owns
+// 8x8 pixels x 8 groups, a quarter-warp is the 8 groups of one pixel (bank slot fixed by the
+// group: conflict-free gather without rotation), window / offsets / masks arrive as three TMA
+// boxes, 32 warps per SM.  Per point: four corner dot products grad_out . value (exact FHFMA
+// products, fp32 sums) -> grad_mask, grad_offset.  Results overwrite the staged offsets / masks in
+// shared memory and leave as two TMA stores (a pixel's 8 groups are 288 / 144 contiguous bytes).
+// grad_value is produced by dcnv3_backward_vstrip.cu.
+#include "dcnv3_common.cuh"
+#include "dcnv3_launch.h"
+#include "dcnv3_tma.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+namespace dcnv3 {
+namespace bdots {
+
+constexpr int kTile = 8;                       // output pixels per tile side
+constexpr int kWin = 18;                       // value window side
+constexpr int kGroups = 8;                     // groups per CTA
+constexpr int kCh = 16;                        // channels per group (32 bytes of 16-bit data)
+constexpr int kCellBytes = kGroups * 32;       // 256
+constexpr int kPix = kTile * kTile;            // 64
+constexpr int kThreads = kPix * kGroups;       // 512
+constexpr int kP = 9;
+constexpr int kWinBytes = kWin * kWin * kCellBytes;          // 82944
+constexpr int kOffBytes = kPix * kGroups * kP * 4;           // 18432
+constexpr int kMskBytes = kPix * kGroups * kP * 2;           // 9216
+constexpr int kSmemBytes = kWinBytes + kOffBytes + kMskBytes;
+
+struct Params {
+    int ox_rel, oy_rel;      // window origin relative to the tile origin
+    int tiles_x;
+    int gblocks;             // G / 8
+    int n0;
+};
+
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void *src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(src)) : "memory");
+}
+
+// 4-D tensor maps over the offset / mask (and their gradient) tensors: dims (G*K elements, Wo, Ho, N)
+static bool make_rows_tensor_map(CUtensorMap *map, const void *base, int dtype, int N, int Ho, int Wo,
+                                 int row_elems, int box_elems) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t es = 2;
+    const CUtensorMapDataType dt = dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const cuuint64_t dims[4] = {(cuuint64_t)row_elems, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)row_elems * es, (cuuint64_t)Wo * row_elems * es,
+                                   (cuuint64_t)Ho * Wo * row_elems * es};
+    const cuuint32_t box[4] = {(cuuint32_t)box_elems, (cuuint32_t)kTile, (cuuint32_t)kTile, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    return fn(map, dt, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 2)
+bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
+         const __grid_constant__ CUtensorMap tmap_m, const __grid_constant__ CUtensorMap tmap_go,
+         const __grid_constant__ CUtensorMap tmap_gm, const T *__restrict__ value, const T *__restrict__ offset,
+         const T *__restrict__ mask, const T *__restrict__ grad_out, const Geom q, const Params tp) {
+    constexpr int E = 8;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    unsigned char *win = smem;
+    unsigned char *off_tile = smem + kWinBytes;                      // [64 px][8 g][9] (dx, dy) pairs -> results
+    unsigned char *msk_tile = smem + kWinBytes + kOffBytes;          // [64 px][8 g][9] masks -> results
+    const uint32_t s_off = smem_u32(off_tile), s_msk = smem_u32(msk_tile);
+
+    const int tid = threadIdx.x;
+    const int g = tid & 7, pix = tid >> 3, px = pix & 7, py = pix >> 3;
+    const int tile_x = blockIdx.x % tp.tiles_x, tile_y = blockIdx.x / tp.tiles_x;
+    const int g0 = blockIdx.y * kGroups;
+    const int n = tp.n0 + blockIdx.z;
+    const int wo0 = tile_x * kTile, ho0 = tile_y * kTile;
+    const int ox = wo0 + tp.ox_rel, oy = ho0 + tp.oy_rel;
+
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar, kSmemBytes);
+        tma_load_4d(off_tile, &tmap_o, &bar, g0 * kP * 2, wo0, ho0, n);
+        tma_load_4d(msk_tile, &tmap_m, &bar, g0 * kP, wo0, ho0, n);
+        tma_load_4d(win, &tmap_v, &bar, g0 * kCh, ox, oy, n);
+    }
+
+    const int wo = wo0 + px, ho = ho0 + py;
+    const bool live = wo < q.Wo && ho < q.Ho;
+    const int half = (g >> 2) & 1;                   // 16-byte chunk this lane reads FIRST
+    const float base_w = axis_base(wo, 3, 1, q.pw, 1, q.sigma);
+    const float base_h = axis_base(ho, 3, 1, q.ph, 1, q.sigma);
+    const float bw = base_w - (float)ox, bh = base_h - (float)oy;     // window-relative anchors
+    const uint32_t win_addr = smem_u32(win) + g * 32 + half * 16;
+    const uint32_t my_off = s_off + (pix * kGroups + g) * (kP * 4);
+    const uint32_t my_msk = s_msk + (pix * kGroups + g) * (kP * 2);
+
+    // upstream gradient of this (pixel, group): chunk `half` and the other chunk (a warp reads four
+    // runs of 256 contiguous bytes)
+    uint4 gq_a = make_uint4(0u, 0u, 0u, 0u), gq_b = gq_a;
+    if (live) {
+        const T *gp = grad_out + ((((size_t)n * q.Ho + ho) * q.Wo + wo) * q.G + (g0 + g)) * kCh;
+        gq_a = __ldg(reinterpret_cast<const uint4 *>(gp + half * E));
+        gq_b = __ldg(reinterpret_cast<const uint4 *>(gp + (half ^ 1) * E));
+    }
+
+    mbar_wait(&bar, 0);
+
+    if (live) {
+        unsigned miss = 0;
+#pragma unroll
+        for (int p = 0; p < kP; ++p) {
+            const int i = p / 3, jj = p % 3;
+            uint32_t o2;
+            uint16_t m16;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(o2) : "r"(my_off + p * 4));
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(m16) : "r"(my_msk + p * 2));
+            const float2 d = unpack2(o2, T());
+            const float m = f32_of(m16, T());
+            float u = bw + ((float)i + d.x) * q.sigma;
+            float v = bh + ((float)jj + d.y) * q.sigma;
+            // 0 <= x < kWin-1 on the bit pattern: negative values and NaN compare as large unsigned
+            const bool hit = __float_as_uint(u) < __float_as_uint((float)(kWin - 1)) &&
+                             __float_as_uint(v) < __float_as_uint((float)(kWin - 1));
+            if (!hit) {
+                miss |= 1u << p;
+                u = 0.f; v = 0.f;
+            }
+            const float fu = floorf(u), fv = floorf(v);
+            const float lw = u - fu, lh = v - fv, hw = 1.f - lw, hh = 1.f - lh;
+            const uint32_t tl = win_addr + (uint32_t)((int)fv * kWin + (int)fu) * kCellBytes;
+            const uint32_t o[4] = {0u, (uint32_t)kCellBytes, (uint32_t)(kWin * kCellBytes), (uint32_t)((kWin + 1) * kCellBytes)};
+            float dr[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const uint4 qa = lds128(tl + o[t]), qb = lds128((tl ^ 16u) + o[t]);
+                dr[t] = dot<T>(gq_a, qa, 0.f) + dot<T>(gq_b, qb, 0.f);
+            }
+            const float gm = hh * (hw * dr[0] + lw * dr[1]) + lh * (hw * dr[2] + lw * dr[3]);
+            const float gx = m * (hh * (dr[1] - dr[0]) + lh * (dr[3] - dr[2]));
+            const float gy = m * (hw * (dr[2] - dr[0]) + lw * (dr[3] - dr[1]));
+            // results overwrite the staged inputs of this point (a miss is redone below)
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(my_off + p * 4), "r"(pack2(q.sigma * gx, q.sigma * gy, T())) : "memory");
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(my_msk + p * 2), "h"(bits16(gm, T())) : "memory");
+        }
+
+        if (miss) {
+            // ---- points whose corner block leaves the window: clamped global reads
+            const int C = q.G * q.gc, row_stride = q.W * C;
+            const T *img = value + (size_t)n * q.H * row_stride + (g0 + g) * kCh;
+            // (the staged inputs of a missed point were overwritten above: re-read them from the tensors)
+            for (int p = 0; p < kP; ++p) {
+                if (!((miss >> p) & 1u)) continue;
+                const int i = p / 3, jj = p % 3;
+                const size_t e0 = ((((size_t)n * q.Ho + ho) * q.Wo + wo) * q.G + (g0 + g)) * kP + p;
+                const float2 d = load_pair(offset + e0 * 2);
+                const float m = to_f32(__ldg(mask + e0));
+                const float loc_w = base_w + ((float)i + d.x) * q.sigma;
+                const float loc_h = base_h + ((float)jj + d.y) * q.sigma;
+                const ClampedTap ct = make_clamped_tap(loc_h, loc_w, q.H, q.W);
+                float gm = 0.f, gx = 0.f, gy = 0.f;
+                if (ct.inside) {
+                    const int r_lo = ct.row_lo * row_stride, r_hi = ct.row_hi * row_stride;
+                    const int c_lo = ct.col_lo * C, c_hi = ct.col_hi * C;
+                    const int at[4] = {r_lo + c_lo, r_lo + c_hi, r_hi + c_lo, r_hi + c_hi};
+                    const int ea = half * E, eb = (half ^ 1) * E;
+                    float dk[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const uint4 qa = __ldg(reinterpret_cast<const uint4 *>(img + at[t] + ea));
+                        const uint4 qb = __ldg(reinterpret_cast<const uint4 *>(img + at[t] + eb));
+                        dk[t] = dot<T>(gq_a, qa, 0.f) + dot<T>(gq_b, qb, 0.f);
+                    }
+                    const float fy_lo = ct.hh * ct.top, fy_hi = ct.lh * ct.bot;
+                    const float fx_lo = ct.hw * ct.lef, fx_hi = ct.lw * ct.rig;
+                    gm = fy_lo * (fx_lo * dk[0] + fx_hi * dk[1]) + fy_hi * (fx_lo * dk[2] + fx_hi * dk[3]);
+                    gx = m * (fy_lo * (ct.rig * dk[1] - ct.lef * dk[0]) + fy_hi * (ct.rig * dk[3] - ct.lef * dk[2]));
+                    gy = m * (fx_lo * (ct.bot * dk[2] - ct.top * dk[0]) + fx_hi * (ct.bot * dk[3] - ct.top * dk[1]));
+                }
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(my_off + p * 4), "r"(pack2(q.sigma * gx, q.sigma * gy, T())) : "memory");
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(my_msk + p * 2), "h"(bits16(gm, T())) : "memory");
+            }
+        }
+    }
+    // ---- the tile's results leave as two TMA stores (pixels beyond the map are clipped)
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+        tma_store_4d(&tmap_go, off_tile, g0 * kP * 2, wo0, ho0, n);
+        tma_store_4d(&tmap_gm, msk_tile, g0 * kP, wo0, ho0, n);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory outlives the reads
+    }
+}
+
+template <typename T>
+static bool launch_typed(const void *value, const void *offset, const void *mask, const void *grad_out,
+                         void *grad_offset, void *grad_mask, const Geom &q, int dtype, cudaStream_t stream,
+                         cudaError_t *err) {
+    if (q.gc != kCh || q.G % kGroups != 0 || q.kh != 3 || q.kw != 3 || q.sh != 1 || q.sw != 1 || q.dh != 1 ||
+        q.dw != 1)
+        return false;
+    if (((uintptr_t)value | (uintptr_t)grad_out | (uintptr_t)offset | (uintptr_t)mask | (uintptr_t)grad_offset |
+         (uintptr_t)grad_mask) % 16)
+        return false;
+    const float span = (kTile - 1) + 2 * q.sigma;
+    if (!(q.sigma > 0.f) || span + 4 > kWin - 2) return false;
+    const int C = q.G * q.gc;
+    CUtensorMap tv, to, tm, tgo, tgm;
+    if (!make_nhwc_tensor_map(&tv, value, dtype, q.N, q.H, q.W, C, kGroups * kCh, kWin, kWin)) return false;
+    if (!make_rows_tensor_map(&to, offset, dtype, q.N, q.Ho, q.Wo, q.G * kP * 2, kGroups * kP * 2)) return false;
+    if (!make_rows_tensor_map(&tm, mask, dtype, q.N, q.Ho, q.Wo, q.G * kP, kGroups * kP)) return false;
+    if (!make_rows_tensor_map(&tgo, grad_offset, dtype, q.N, q.Ho, q.Wo, q.G * kP * 2, kGroups * kP * 2)) return false;
+    if (!make_rows_tensor_map(&tgm, grad_mask, dtype, q.N, q.Ho, q.Wo, q.G * kP, kGroups * kP)) return false;
+    Params tp;
+    const float a_w = (float)(1 - q.pw) - q.sigma, a_h = (float)(1 - q.ph) - q.sigma;
+    tp.ox_rel = (int)std::floor(a_w + 0.5f * span - 0.5f * (kWin - 2));
+    tp.oy_rel = (int)std::floor(a_h + 0.5f * span - 0.5f * (kWin - 2));
+    tp.tiles_x = (q.Wo + kTile - 1) / kTile;
+    tp.gblocks = q.G / kGroups;
+    const int tiles_y = (q.Ho + kTile - 1) / kTile;
+    if (tp.gblocks > 65535) return false;
+    cudaFuncSetAttribute(bwd_dots<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    for (int n0 = 0; n0 < q.N; n0 += 65535) {
+        tp.n0 = n0;
+        const dim3 grid((unsigned)(tp.tiles_x * tiles_y), (unsigned)tp.gblocks, (unsigned)std::min(65535, q.N - n0));
+        bwd_dots<T><<<grid, kThreads, kSmemBytes, stream>>>(tv, to, tm, tgo, tgm, static_cast<const T *>(value),
+                                                            static_cast<const T *>(offset), static_cast<const T *>(mask),
+                                                            static_cast<const T *>(grad_out), q, tp);
+    }
+    *err = cudaGetLastError();
+    return true;
+}
+
+}  // namespace bdots
+
+// grad_offset / grad_mask only.  Returns false if the shape is not eligible.
+bool try_launch_backward_dots(const void *value, const void *offset, const void *mask, const void *grad_out,
+                              void *grad_offset, void *grad_mask, const Geom &q, int dtype, cudaStream_t stream,
+                              cudaError_t *err) {
+    if ((long long)q.N * q.Ho * q.Wo == 0) return false;
+    if (dtype == 1) return bdots::launch_typed<__half>(value, offset, mask, grad_out, grad_offset, grad_mask, q, dtype, stream, err);
+    if (dtype == 2) return bdots::launch_typed<__nv_bfloat16>(value, offset, mask, grad_out, grad_offset, grad_mask, q, dtype, stream, err);
+    return false;
+}
+
+}  // namespace dcnv3

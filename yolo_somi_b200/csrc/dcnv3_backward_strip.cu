@@ -33,6 +33,7 @@
 #include "dcnv3_common.cuh"
 #include "dcnv3_launch.h"
 #include "dcnv3_tma.cuh"
+#include "dcnv3_strip_io.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -41,27 +42,19 @@
 namespace dcnv3 {
 namespace strip {
 
-constexpr int kStripW = 8, kPatchH = 4, kSteps = 4;
+constexpr int kSteps = 4;
 constexpr int kWarps = 2;
 constexpr int kTileW = kStripW * kWarps, kTileH = kPatchH * kSteps;   // 16 x 16 output pixels
 constexpr int kThreads = kWarps * 32;
 constexpr int kWinW = 26, kWinH = 26;            // value window (2 mod 4: conflict-free corners)
 constexpr int kBandW = 16, kBandH = 12;          // cells one step of one warp scatters into (taps +- 3 px)
 constexpr int kMTiles = kBandH;                  // one m-tile (16 cells) per band row
-constexpr int kCh = 16, kSliceBytes = 32;
-constexpr int kP = 9;
 constexpr int kSpillCap = 32;
 static_assert(kWinW % 4 == 2, "window width must be 2 mod 4");
 
 constexpr int kWinBytes = kWinW * kWinH * kSliceBytes;          // 21632
 constexpr int kABytes = kBandH * kBandW * 64;                   // 12288 per warp
-constexpr int kMskWords = 7;                                    // per pixel: 5 words used, odd stride
-constexpr int kStageOff = 0;                                    // [32][9] u32
-constexpr int kStageMsk = kStageOff + 32 * kP * 4;              // [32][7] u32
-constexpr int kStageGout = kStageMsk + 32 * kMskWords * 4;      // [32][32 B]
-constexpr int kStageBytes = kStageGout + 32 * kSliceBytes;      // 3072 per warp
 constexpr int kSpillBytes = 16 + kSpillCap * 32;                // 272 per warp
-constexpr int kIoTblBytes = (kP + 5) * 32 * 4;                  // staging I/O index table, per CTA
 constexpr int kSmemBytes = kWinBytes + kWarps * (kABytes + kStageBytes + kSpillBytes) + kIoTblBytes;
 
 struct Params {
@@ -91,20 +84,10 @@ struct SpillEntry {   // 32 bytes
     float c[4];
 };
 
-__device__ __forceinline__ uint4 lds128(uint32_t a) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void sts128_zero(uint32_t a) {
-    asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(a), "r"(0u) : "memory");
-}
 template <typename V> __device__ __forceinline__ void rotate4(V (&x)[4], int r) {  // out[t] = in[(t+r)&3]
     if (r & 1) { const V t = x[0]; x[0] = x[1]; x[1] = x[2]; x[2] = x[3]; x[3] = t; }
     if (r & 2) { V t = x[0]; x[0] = x[2]; x[2] = t; t = x[1]; x[1] = x[3]; x[3] = t; }
 }
-__device__ __forceinline__ void red_add2(float *p, float a, float b) { atomicAdd(reinterpret_cast<float2 *>(p), make_float2(a, b)); }
-__device__ __forceinline__ void red_add4(float *p, float4 v) { atomicAdd(reinterpret_cast<float4 *>(p), v); }
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -125,15 +108,6 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// cp.async with zero fill: copies `src_bytes` (<= size) and zero-fills the rest
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src, int src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // byte offset of A[cell][pixel] inside a warp's A tile: 64-byte rows, 16-byte chunks swizzled
 __device__ __forceinline__ uint32_t a_elem_off(int cell, int pixel) {
@@ -296,18 +270,6 @@ template <typename T> struct StepCtx {
     int lane;
 };
 
-__device__ __forceinline__ uint32_t lds32(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds16(uint32_t a) {
-    uint16_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
 
 // The NP points (tap column i, tap rows 0..NP-1) of this lane's pixel at once: independent
 // instruction streams for the scheduler.  Returns false, having done nothing, if any of them
@@ -435,144 +397,6 @@ __device__ __forceinline__ void flush_rows(const float (&acc)[kMTiles][2][4], fl
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Staging I/O of one warp, out of line (one copy of the code, called once per step): write the
-// finished step's grad_offset / grad_mask out of the staging buffer, then request the next step's
-// offsets / masks / grad_out with cp.async (no registers held while they are in flight).
-template <typename T> struct IoCtx {   // kernel-constant, one copy per CTA in shared memory
-    const T *offset, *mask, *grad_out;
-    T *grad_offset, *grad_mask;
-    const unsigned char *mask_end;
-    int Wo, Ho, G, C;
-};
-
-// Index table (shared memory, built once per CTA): element k = lane + 32 it of a patch's 32 x 9
-// staged values belongs to pixel k / 9, point k % 9 -- consecutive lanes walk a pixel's contiguous
-// 36-byte (offsets) / 18-byte (masks) run, so a warp access touches the minimal number of 32-byte
-// sectors (one LSU wavefront each).  Entry = element offset from the patch's first run | pixel << 27;
-// rows 9..13: the same for the mask runs' 5 enclosing words (k / 5, k % 5 << 24).
-__device__ __forceinline__ void build_io_table(uint32_t *tbl, int Wo, int G9, int tid, int nthreads) {
-    for (int e = tid; e < (kP + 5) * 32; e += nthreads) {
-        const int it = e >> 5, lane = e & 31;
-        uint32_t v;
-        if (it < kP) {
-            const int k = lane + 32 * it, px = k / kP, p = k - px * kP;
-            v = (uint32_t)(((px >> 3) * Wo + (px & 7)) * G9 + p) | ((uint32_t)px << 27);
-        } else {
-            const int k = lane + 32 * (it - kP), px = k / 5, wd = k - px * 5;
-            v = (uint32_t)(((px >> 3) * Wo + (px & 7)) * G9) | ((uint32_t)wd << 24) | ((uint32_t)px << 27);
-        }
-        tbl[e] = v;
-    }
-}
-
-template <typename T>
-__device__ __noinline__ void stage_io(const IoCtx<T> *io_s, const uint32_t *tbl, uint32_t sa /* staging buffer */,
-                                      size_t pix_w, int g_w, int wb_w, int hb_w, int do_w, size_t pix_p, int g_p,
-                                      int wb_p, int hb_p, int do_p) {
-    const IoCtx<T> io = *io_s;     // registers from here on (the asm statements below clobber memory)
-    const int lane = threadIdx.x & 31;
-    const int Wo = io.Wo, Ho = io.Ho;
-    uint32_t ent[kP];
-#pragma unroll
-    for (int it = 0; it < kP; ++it) ent[it] = tbl[it * 32 + lane];
-    // Patches that lie fully inside the output map (the common case) take warp-uniform branches with
-    // unconditional accesses; a per-element guard costs a divergence barrier around every access.
-    if (do_w) {
-        const size_t e0 = (pix_w * io.G + g_w) * kP;             // first element of the patch's first run
-        uint32_t *ob = reinterpret_cast<uint32_t *>(io.grad_offset) + e0;
-        uint16_t *mb = reinterpret_cast<uint16_t *>(io.grad_mask) + e0;
-        const unsigned par0 = (unsigned)e0 & 1u;
-        const bool full = wb_w + kStripW <= Wo && hb_w + kPatchH <= Ho;
-        uint32_t vo[kP], vm[kP];
-        // all reads first (independent), then the stores
-#pragma unroll
-        for (int it = 0; it < kP; ++it) {
-            const int px = (int)(ent[it] >> 27), rel = (int)(ent[it] & 0x7ffffffu);
-            const int p = lane + 32 * it - px * kP;
-            const unsigned shp = (par0 + (unsigned)(rel - p)) & 1u;   // misalignment of the staged mask run
-            vo[it] = lds32(sa + kStageOff + (lane + 32 * it) * 4);
-            vm[it] = lds16(sa + kStageMsk + px * (kMskWords * 4) + (shp + p) * 2);
-        }
-        if (full) {
-#pragma unroll
-            for (int it = 0; it < kP; ++it) {
-                const int rel = (int)(ent[it] & 0x7ffffffu);
-                ob[rel] = vo[it];
-                mb[rel] = (uint16_t)vm[it];
-            }
-        } else {
-#pragma unroll 1
-            for (int it = 0; it < kP; ++it) {
-                const int px = (int)(ent[it] >> 27), rel = (int)(ent[it] & 0x7ffffffu);
-                if (wb_w + (px & 7) < Wo && hb_w + (px >> 3) < Ho) {
-                    ob[rel] = vo[it];
-                    mb[rel] = (uint16_t)vm[it];
-                }
-            }
-        }
-    }
-    __syncwarp();   // every lane is done reading the staging buffer (gather results, B fragments)
-    if (do_p) {
-        const size_t e0 = (pix_p * io.G + g_p) * kP;
-        const uint32_t *os = reinterpret_cast<const uint32_t *>(io.offset) + e0;
-        const unsigned char *ms = reinterpret_cast<const unsigned char *>(io.mask) + e0 * 2;
-        const unsigned mlow = (unsigned)(uintptr_t)ms & 3u;
-        const bool full = wb_p + kStripW <= Wo && hb_p + kPatchH <= Ho;
-        const T *g_first = io.grad_out + pix_p * io.C + g_p * kCh;
-        if (full) {
-#pragma unroll
-            for (int it = 0; it < kP; ++it)
-                cp_async4(sa + kStageOff + (lane + 32 * it) * 4, os + (ent[it] & 0x7ffffffu), 4);
-            // the 18-byte mask run of a pixel is staged from its 5 enclosing 4-byte words; only the
-            // tensor's very last word can be half outside (warp-uniform test for the whole patch)
-            const bool tail = ms + ((size_t)((kPatchH - 1) * Wo + kStripW) * (io.G * kP)) * 2 + 4 > io.mask_end;
-#pragma unroll
-            for (int it = 0; it < 5; ++it) {
-                const uint32_t en = tbl[(kP + it) * 32 + lane];
-                const int px = (int)(en >> 27), wd = (int)((en >> 24) & 7u);
-                const unsigned relb = (en & 0xffffffu) * 2u;                      // byte offset of the run
-                const unsigned low = (mlow + relb) & 3u;                          // its misalignment (0 or 2)
-                const unsigned char *src = ms + ((ptrdiff_t)relb - (ptrdiff_t)low + wd * 4);
-                if (!tail) cp_async4(sa + kStageMsk + (px * kMskWords + wd) * 4, src, 4);
-                else cp_async4(sa + kStageMsk + (px * kMskWords + wd) * 4, src, src + 4 <= io.mask_end ? 4 : 2);
-            }
-#pragma unroll
-            for (int r2 = 0; r2 < 2; ++r2) {
-                const int px = r2 * 16 + (lane >> 1), row = px >> 3, c8 = px & 7, ck = lane & 1;
-                cp_async16(sa + kStageGout + px * kSliceBytes + ck * 16, g_first + (size_t)(row * Wo + c8) * io.C + ck * 8, 16);
-            }
-        } else {
-            // ragged patch: copies of pixels outside the map are skipped by a zero source size
-            // (offsets / masks of such pixels are never read; their grad_out must read as zero:
-            // the A columns are zero, but the product must not see NaN bits)
-#pragma unroll 1
-            for (int it = 0; it < kP; ++it) {
-                const int px = (int)(ent[it] >> 27);
-                const bool ok = wb_p + (px & 7) < Wo && hb_p + (px >> 3) < Ho;
-                cp_async4(sa + kStageOff + (lane + 32 * it) * 4, os + (ok ? (ent[it] & 0x7ffffffu) : 0u), ok ? 4 : 0);
-            }
-#pragma unroll 1
-            for (int it = 0; it < 5; ++it) {
-                const uint32_t en = tbl[(kP + it) * 32 + lane];
-                const int px = (int)(en >> 27), wd = (int)((en >> 24) & 7u);
-                const bool ok = wb_p + (px & 7) < Wo && hb_p + (px >> 3) < Ho;
-                const unsigned relb = (en & 0xffffffu) * 2u;
-                const unsigned low = (mlow + relb) & 3u;
-                const unsigned char *src = ok ? ms + ((ptrdiff_t)relb - (ptrdiff_t)low + wd * 4) : reinterpret_cast<const unsigned char *>(io.mask);
-                cp_async4(sa + kStageMsk + (px * kMskWords + wd) * 4, src, ok ? (src + 4 <= io.mask_end ? 4 : 2) : 0);
-            }
-#pragma unroll
-            for (int r2 = 0; r2 < 2; ++r2) {
-                const int px = r2 * 16 + (lane >> 1), row = px >> 3, c8 = px & 7, ck = lane & 1;
-                const bool ok = wb_p + c8 < Wo && hb_p + row < Ho;
-                cp_async16(sa + kStageGout + px * kSliceBytes + ck * 16,
-                           ok ? g_first + (size_t)(row * Wo + c8) * io.C + ck * 8 : io.grad_out, ok ? 16 : 0);
-            }
-        }
-    }
-    cp_async_commit();
-}
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 4)
@@ -846,6 +670,309 @@ static bool launch_typed(const void *value, const void *offset, const void *mask
     return true;
 }
 
+
+// ================================================================================================
+// Value-only form: second half of the SPLIT backward (grad_offset / grad_mask come from
+// dcnv3_backward_dots.cu).  grad_value needs no value window and no channel sums: a step is
+// coordinates -> A build -> acc += A x grad_out -> finished rows leave as reductions.  Without the
+// 21 KB window a two-warp CTA needs 35 KB of shared memory, so 12 warps fit an SM instead of 8, and
+// the per-point work drops to the coordinate arithmetic and four 16-bit read-modify-writes.
+constexpr int kVSmemBytes = kWarps * (kABytes + kStageBytes + kSpillBytes) + kIoTblBytes;
+
+struct VParams {
+    int bx_rel, by_rel;      // band origin relative to the first pixel of a warp's patch (map coordinates)
+    int tiles_x, tiles_xy, total_tiles;
+    int steps;               // 4-row steps per tile: without a window the strip can be as tall as the map
+    unsigned long long mask_bytes;
+};
+
+// One sampling point, general path (band overflow of the spill list, rare): coefficients into the
+// A tile or straight to the global accumulator.
+template <typename T>
+__device__ __noinline__ void slow_vpoint(const SlowCtx<T> *cp, int band_y0, int band_x0, float loc_h, float loc_w, float m) {
+    const SlowCtx<T> &c = *cp;
+    const bool inside = loc_h > -1.f && loc_w > -1.f && loc_h < (float)c.H && loc_w < (float)c.W;
+    if (!inside) return;
+    const float fh = floorf(loc_h), fw = floorf(loc_w);
+    const float lh = loc_h - fh, lw = loc_w - fw, hh = 1.f - lh, hw = 1.f - lw;
+    const int h0 = (int)fh, w0 = (int)fw;
+    const int br = h0 - band_y0, bc = w0 - band_x0;
+    const float cf[4] = {hh * hw * m, hh * lw * m, lh * hw * m, lh * lw * m};
+    if ((unsigned)br < (unsigned)(kBandH - 1) && (unsigned)bc < (unsigned)(kBandW - 1)) {
+        const int cb = br * kBandW + bc;
+        T *e0 = reinterpret_cast<T *>(c.abuf + a_elem_off(cb, c.lane));
+        T *e1 = reinterpret_cast<T *>(c.abuf + a_elem_off(cb + 1, c.lane));
+        T *e2 = reinterpret_cast<T *>(c.abuf + a_elem_off(cb + kBandW, c.lane));
+        T *e3 = reinterpret_cast<T *>(c.abuf + a_elem_off(cb + kBandW + 1, c.lane));
+        const float a0 = to_f32(*e0), a1 = to_f32(*e1), a2 = to_f32(*e2), a3 = to_f32(*e3);
+        *e0 = from_f32<T>(a0 + cf[0]);
+        *e1 = from_f32<T>(a1 + cf[1]);
+        *e2 = from_f32<T>(a2 + cf[2]);
+        *e3 = from_f32<T>(a3 + cf[3]);
+    } else {
+        const uint4 gq_a = *reinterpret_cast<const uint4 *>(c.s_gout + c.lane * kSliceBytes + c.half * 16);
+        const uint4 gq_b = *reinterpret_cast<const uint4 *>(c.s_gout + c.lane * kSliceBytes + (c.half ^ 1) * 16);
+        const bool top = h0 >= 0, bot = h0 + 1 < c.H, lef = w0 >= 0, rig = w0 + 1 < c.W;
+        const int at[4] = {h0 * c.row_stride + w0 * c.C, h0 * c.row_stride + (w0 + 1) * c.C,
+                           (h0 + 1) * c.row_stride + w0 * c.C, (h0 + 1) * c.row_stride + (w0 + 1) * c.C};
+        const float cg[4] = {top && lef ? cf[0] : 0.f, top && rig ? cf[1] : 0.f, bot && lef ? cf[2] : 0.f, bot && rig ? cf[3] : 0.f};
+        direct_scatter<T>(c, gq_a, gq_b, at, cg);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 6)
+bwd_vstrip(const T *__restrict__ offset, const T *__restrict__ mask, const T *__restrict__ grad_out,
+           float *__restrict__ gv_acc, const Geom q, const VParams pp) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned char *abuf = smem + warp * kABytes;
+    unsigned char *stage = smem + kWarps * kABytes + warp * kStageBytes;
+    unsigned char *spill = smem + kWarps * (kABytes + kStageBytes) + warp * kSpillBytes;
+    uint32_t *io_tbl = reinterpret_cast<uint32_t *>(smem + kWarps * (kABytes + kStageBytes + kSpillBytes));
+    const uint32_t stage_addr = smem_u32(stage), a_base = smem_u32(abuf), spill_addr = smem_u32(spill);
+
+    const int C = q.G * q.gc, row_stride = q.W * C;
+    const int half = lane & 1;
+    const int px_x = lane & 7, px_y = lane >> 3;
+
+    int t = blockIdx.x;
+    if (t >= pp.total_tiles) return;
+    auto decode = [&](int tt, int &n, int &g, int &wo0, int &ho0) {
+        const int txy = tt % pp.tiles_xy, r = tt / pp.tiles_xy;
+        g = r % q.G; n = r / q.G;
+        wo0 = (txy % pp.tiles_x) * kTileW; ho0 = (txy / pp.tiles_x) * (pp.steps * kPatchH);
+    };
+    int n, g, wo0, ho0;
+    decode(t, n, g, wo0, ho0);
+    auto patch_pix = [&](int nn, int w0, int h0, int s) -> size_t {
+        return ((size_t)nn * q.Ho + (h0 + s * kPatchH)) * q.Wo + (w0 + warp * kStripW);
+    };
+    __shared__ __align__(16) IoCtx<T> io;
+    if (tid == 0) {
+        io.offset = offset; io.mask = mask; io.grad_out = grad_out; io.grad_offset = nullptr; io.grad_mask = nullptr;
+        io.mask_end = reinterpret_cast<const unsigned char *>(mask) + pp.mask_bytes;
+        io.Wo = q.Wo; io.Ho = q.Ho; io.G = q.G; io.C = C;
+    }
+    build_io_table(io_tbl, q.Wo, q.G * kP, tid, kThreads);
+    __syncthreads();
+    for (int i = lane; i < kABytes / 16; i += 32) sts128_zero(a_base + i * 16);
+    if (lane == 0) *reinterpret_cast<unsigned *>(spill) = 0u;
+    stage_io<T>(&io, io_tbl, stage_addr, 0, 0, 0, 0, 0, patch_pix(n, wo0, ho0, 0), g, wo0 + warp * kStripW, ho0, 1);
+
+    SlowCtx<T> sc;
+    sc.H = q.H; sc.W = q.W; sc.C = C; sc.row_stride = row_stride;
+    sc.lane = lane; sc.j = lane & 7; sc.half = half; sc.win_addr = 0;
+    sc.abuf = abuf; sc.spill = spill; sc.s_gout = stage + kStageGout; sc.img = nullptr; sc.oy = 0; sc.ox = 0;
+
+    float acc[kMTiles][2][4];
+    for (;;) {
+        const int t_next = t + gridDim.x;
+        const bool has_next = t_next < pp.total_tiles;
+        int n2 = n, g2 = g, wo2 = wo0, ho2 = ho0;
+        if (has_next) decode(t_next, n2, g2, wo2, ho2);
+        float *gv_img = gv_acc + (size_t)n * q.H * row_stride + g * q.gc;
+        sc.gv_img = gv_img;
+#pragma unroll
+        for (int b = 0; b < kMTiles; ++b)
+#pragma unroll
+            for (int nn = 0; nn < 2; ++nn)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[b][nn][e] = 0.f;
+
+#pragma unroll 1
+        for (int s = 0; s < pp.steps; ++s) {
+            const int wb = wo0 + warp * kStripW, hb = ho0 + s * kPatchH;
+            const int wo = wb + px_x, ho = hb + px_y;
+            const bool live = wo < q.Wo && ho < q.Ho;
+            const int band_x0 = wb + pp.bx_rel, band_y0 = hb + pp.by_rel;   // band origin, map coordinates
+            const size_t pix = patch_pix(n, wo0, ho0, s);
+            cp_async_wait_all();
+            __syncwarp();
+
+            // ------------------------------------------------------------ A build (no gather here)
+            if (live) {
+                const float base_w = axis_base(wo, 3, 1, q.pw, 1, q.sigma), base_h = axis_base(ho, 3, 1, q.ph, 1, q.sigma);
+                const float bw = base_w - (float)band_x0, bh = base_h - (float)band_y0;   // band-relative anchors
+                const unsigned sh = (unsigned)(((pix + (size_t)(px_y * q.Wo + px_x)) * q.G + g) * kP) & 1u;
+                const uint32_t s_off_lane = stage_addr + kStageOff + lane * (kP * 4);
+                const uint32_t s_msk_lane = stage_addr + kStageMsk + lane * (kMskWords * 4) + sh * 2;
+                const uint32_t a_lane = a_base + (lane & 7) * 2, chunk = (uint32_t)lane >> 3;
+                unsigned ovf = 0;
+                // one point at a time (no per-point state is kept: the accumulators need the registers)
+#pragma unroll
+                for (int p = 0; p < kP; ++p) {
+                    const float2 d = unpack2(lds32(s_off_lane + p * 4), T());
+                    const float m = f32_of((uint16_t)lds16(s_msk_lane + p * 2), T());
+                    const float ub = bw + ((float)(p / 3) + d.x) * q.sigma;
+                    const float vb = bh + ((float)(p % 3) + d.y) * q.sigma;
+                    const float fw = floorf(ub), fh = floorf(vb);
+                    const float lw = ub - fw, lh = vb - fh;
+                    const float hm = (1.f - lh) * m, lm = lh * m, hw = 1.f - lw;
+                    // 0 <= x < limit on the float's bit pattern: negative values and NaN compare as large unsigned
+                    if (__float_as_uint(ub) < __float_as_uint((float)(kBandW - 1)) &&
+                        __float_as_uint(vb) < __float_as_uint((float)(kBandH - 1))) {
+                        const uint32_t c0 = (uint32_t)((int)fh * kBandW + (int)fw), c1 = c0 + 1u;
+                        const uint32_t e0 = a_lane + c0 * 64u + ((chunk ^ ((c0 >> 1) & 3u)) << 4);
+                        const uint32_t e1 = a_lane + c1 * 64u + ((chunk ^ ((c1 >> 1) & 3u)) << 4);
+                        const float a0 = f32_of((uint16_t)lds16(e0), T()), a1 = f32_of((uint16_t)lds16(e1), T());
+                        const float a2 = f32_of((uint16_t)lds16(e0 + kBandW * 64), T()), a3 = f32_of((uint16_t)lds16(e1 + kBandW * 64), T());
+                        sts16(e0, bits16(a0 + hm * hw, T()));
+                        sts16(e1, bits16(a1 + hm * lw, T()));
+                        sts16(e0 + kBandW * 64, bits16(a2 + lm * hw, T()));
+                        sts16(e1 + kBandW * 64, bits16(a3 + lm * lw, T()));
+                    } else {
+                        // beyond the band: the reference's range test decides whether the point counts at all
+                        const float lw_abs = ub + (float)band_x0, lh_abs = vb + (float)band_y0;
+                        if (lh_abs > -1.f && lw_abs > -1.f && lh_abs < (float)q.H && lw_abs < (float)q.W) {
+                            uint32_t pos;
+                            asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(pos) : "r"(spill_addr), "r"(1u) : "memory");
+                            if (pos < (uint32_t)kSpillCap) {
+                                const uint32_t e = spill_addr + 16 + pos * 32;
+                                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(e), "r"((int)fh + band_y0), "r"((int)fw + band_x0), "r"(lane), "r"(0) : "memory");
+                                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(e + 16), "f"(hm * hw), "f"(hm * lw), "f"(lm * hw), "f"(lm * lw) : "memory");
+                            } else {
+                                ovf |= 1u << p;   // list full: redone through the general path below
+                            }
+                        }
+                    }
+                }
+                if (ovf) {   // rare: re-derive those points from the (untouched) staging data
+#pragma unroll 1
+                    for (int p = 0; p < kP; ++p)
+                        if ((ovf >> p) & 1u) {
+                            const float2 d = unpack2(lds32(s_off_lane + p * 4), T());
+                            const float m = f32_of((uint16_t)lds16(s_msk_lane + p * 2), T());
+                            const int i = (p * 11) >> 5, jj = p - 3 * i;
+                            slow_vpoint<T>(&sc, band_y0, band_x0, base_h + ((float)jj + d.y) * q.sigma,
+                                           base_w + ((float)i + d.x) * q.sigma, m);
+                        }
+                }
+            }
+            __syncwarp();
+
+            // ---- spilled coefficients (points beyond the band): cooperative reductions
+            {
+                const unsigned cnt = min(*reinterpret_cast<volatile unsigned *>(spill), (unsigned)kSpillCap);
+                if (cnt) {
+                    const SpillEntry *se = reinterpret_cast<const SpillEntry *>(spill + 16);
+                    const int corner = lane >> 3, chp = (lane & 7) * 2;
+                    for (unsigned e = 0; e < cnt; ++e) {
+                        const int hh = se[e].h0 + (corner >> 1), ww = se[e].w0 + (corner & 1);
+                        if ((unsigned)hh < (unsigned)q.H && (unsigned)ww < (unsigned)q.W) {
+                            const float cf = se[e].c[corner];
+                            if (cf != 0.f) {
+                                const float2 gf = unpack2(lds32(stage_addr + kStageGout + (se[e].lane & 31) * kSliceBytes + chp * 2), T());
+                                red_add2(gv_img + (ptrdiff_t)hh * row_stride + (ptrdiff_t)ww * C + chp, cf * gf.x, cf * gf.y);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) *reinterpret_cast<volatile unsigned *>(spill) = 0u;
+                }
+            }
+
+            // ---- B fragments (grad_out of the 32 pixels), then request the next step's inputs
+            uint32_t bf[2][4];
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                const int pxl = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                ldmatrix_x4_trans(bf[ks], stage_addr + kStageGout + pxl * kSliceBytes + (lane >> 4) * 16);
+            }
+            {
+                const bool in_tile = s + 1 < pp.steps;
+                const int nn = in_tile ? n : n2, gg = in_tile ? g : g2, w0n = in_tile ? wo0 : wo2, h0n = in_tile ? ho0 : ho2;
+                const int ns = in_tile ? s + 1 : 0;
+                stage_io<T>(&io, io_tbl, stage_addr, 0, 0, 0, 0, 0, patch_pix(nn, w0n, h0n, ns), gg, w0n + warp * kStripW,
+                            h0n + ns * kPatchH, in_tile || has_next);
+            }
+
+            // ------------------------------------------------------------ acc += A x grad_out
+            {
+                const int r_in = (lane & 7) + ((lane >> 3) & 1) * 8;
+                const uint32_t kc_in = (uint32_t)lane >> 4;
+                const uint32_t sw = ((uint32_t)r_in >> 1) & 3u;
+                const uint32_t ra0 = a_base + (uint32_t)r_in * 64u + ((kc_in ^ sw) << 4);
+                const uint32_t ra1 = a_base + (uint32_t)r_in * 64u + (((2u + kc_in) ^ sw) << 4);
+                const uint32_t za = a_base + lane * 16;
+#pragma unroll
+                for (int b = 0; b < kMTiles; ++b) {
+                    uint32_t a0[4], a1[4];
+                    ldmatrix_x4(a0, ra0 + b * 1024);
+                    ldmatrix_x4(a1, ra1 + b * 1024);
+                    mma16816(acc[b][0], a0, bf[0][0], bf[0][1], T());
+                    mma16816(acc[b][1], a0, bf[0][2], bf[0][3], T());
+                    mma16816(acc[b][0], a1, bf[1][0], bf[1][1], T());
+                    mma16816(acc[b][1], a1, bf[1][2], bf[1][3], T());
+                    sts128_zero(za + b * 1024);
+                    sts128_zero(za + b * 1024 + 512);
+                }
+            }
+
+            // ------------------------------------------------------------ finished rows leave
+            {
+                const int gid = lane >> 2, tig = lane & 3;
+                const int mx = band_x0 + gid;
+                float *p0 = gv_img + (ptrdiff_t)band_y0 * row_stride + (ptrdiff_t)mx * C + 2 * tig;
+                const bool ok0 = (unsigned)mx < (unsigned)q.W, ok1 = (unsigned)(mx + 8) < (unsigned)q.W;
+                if (s + 1 < pp.steps) {
+                    flush_rows<kPatchH>(acc, p0, band_y0, q.H, row_stride, C, ok0, ok1);
+#pragma unroll
+                    for (int b = 0; b < kMTiles; ++b)
+#pragma unroll
+                        for (int nn = 0; nn < 2; ++nn)
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                if (b + kPatchH < kMTiles) acc[b][nn][e] = acc[b + kPatchH < kMTiles ? b + kPatchH : 0][nn][e];
+                                else acc[b][nn][e] = 0.f;
+                            }
+                } else {
+                    flush_rows<kMTiles>(acc, p0, band_y0, q.H, row_stride, C, ok0, ok1);
+                }
+            }
+        }
+        if (!has_next) break;
+        n = n2; g = g2; wo0 = wo2; ho0 = ho2;
+        t = t_next;
+    }
+}
+
+template <typename T>
+static bool launch_value_typed(const void *offset, const void *mask, const void *grad_out, float *gv_acc, const Geom &q,
+                               cudaStream_t stream, cudaError_t *err) {
+    if (q.gc != kCh || q.kh != 3 || q.kw != 3 || q.sh != 1 || q.sw != 1 || q.dh != 1 || q.dw != 1) return false;
+    if (!(q.sigma >= 0.5f && q.sigma <= 1.25f)) return false;
+    if (((uintptr_t)grad_out | (uintptr_t)gv_acc) % 16 || ((uintptr_t)offset | (uintptr_t)mask) % 4) return false;
+    VParams pp;
+    const float a_w = (float)(1 - q.pw) - q.sigma, a_h = (float)(1 - q.ph) - q.sigma;
+    pp.bx_rel = (int)std::floor(a_w + q.sigma + 0.5f * (kStripW - 1) + 0.5f - 0.5f * kBandW);
+    pp.by_rel = (int)std::floor(a_h + q.sigma + 0.5f * (kPatchH - 1) + 0.5f - 0.5f * kBandH);
+    pp.tiles_x = (q.Wo + kTileW - 1) / kTileW;
+    // tall tiles: the rows a strip flushes are (4 steps + 8) per (4 steps) rows -- 1.5x at 4 steps, 1.2x at 10
+    pp.steps = std::max(1, std::min((q.Ho + kPatchH - 1) / kPatchH, 10));
+    if (const char *e = std::getenv("DCNV3_VSTEPS")) pp.steps = std::max(1, std::min(64, atoi(e)));
+    const int tile_h = pp.steps * kPatchH;
+    const int tiles_y = (q.Ho + tile_h - 1) / tile_h;
+    const long long total = (long long)pp.tiles_x * tiles_y * q.G * q.N;
+    if (total >= (1LL << 31)) return false;
+    pp.tiles_xy = pp.tiles_x * tiles_y;
+    pp.total_tiles = (int)total;
+    pp.mask_bytes = (unsigned long long)q.N * q.Ho * q.Wo * q.G * kP * 2ull;
+    if ((long long)(3 * q.Wo + 8) * q.G * kP + kP >= (1LL << 24)) return false;
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int ctas = (int)std::min<long long>(total, 6LL * num_sms);
+    cudaFuncSetAttribute(bwd_vstrip<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVSmemBytes);
+    bwd_vstrip<T><<<ctas, kThreads, kVSmemBytes, stream>>>(static_cast<const T *>(offset), static_cast<const T *>(mask),
+                                                          static_cast<const T *>(grad_out), gv_acc, q, pp);
+    *err = cudaGetLastError();
+    return true;
+}
+
 }  // namespace strip
 
 // gv_acc: zero-initialised fp32 accumulator with the shape of value.  Returns false if the shape
@@ -858,6 +985,15 @@ bool try_launch_backward_strip(const void *value, const void *offset, const void
     if ((long long)q.N * q.Ho * q.Wo == 0) return false;
     if (dtype == 1) return strip::launch_typed<__half>(value, offset, mask, grad_out, gv_acc, grad_offset, grad_mask, q, dtype, stream, err);
     if (dtype == 2) return strip::launch_typed<__nv_bfloat16>(value, offset, mask, grad_out, gv_acc, grad_offset, grad_mask, q, dtype, stream, err);
+    return false;
+}
+
+// grad_value only (accumulated into the zeroed fp32 plane gv_acc); the split backward's second half.
+bool try_launch_backward_vstrip(const void *offset, const void *mask, const void *grad_out, float *gv_acc,
+                                const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err) {
+    if ((long long)q.N * q.Ho * q.Wo == 0) return false;
+    if (dtype == 1) return strip::launch_value_typed<__half>(offset, mask, grad_out, gv_acc, q, stream, err);
+    if (dtype == 2) return strip::launch_value_typed<__nv_bfloat16>(offset, mask, grad_out, gv_acc, q, stream, err);
     return false;
 }
 

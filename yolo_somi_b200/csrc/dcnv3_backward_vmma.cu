@@ -1,0 +1,393 @@
+// dcnv3_backward_vmma.cu -- grad_value of the DCNv3 core backward for 16-bit I/O, group_channels == 16,
+// 3x3 / stride 1 / dilation 1, as a tcgen05 product with the accumulators in TENSOR MEMORY.
+// Second half of the split backward (grad_offset / grad_mask: dcnv3_backward_dots.cu).
+//
+// What it computes (reference dcnv3_im2col_cuda.cuh:82-147, col2im bilinear):
+//     grad_value[cell, c] += sum over (pixel, point, corner) hitting `cell` of  w_corner * m * grad_out[pixel, c]
+// i.e. for one group the sparse product  D[cells x 16 ch] = A[cells x pixels] . G[pixels x 16 ch],  A holding
+// the 36 bilinear-times-mask coefficients of every pixel.
+//
+// Why tensor memory (profiles/README.md, r1_v4): the register-accumulator strip kernel keeps 96
+// accumulator registers per thread (252 in all, 8 warps per SM), moves the A tile through ldmatrix and
+// shifts the accumulators down the strip with 64 moves per step.  Here
+//   * a CTA of four warps walks two 8-pixel-wide strips down the map, eight rows per step; a thread is
+//     one pixel of the step's 8 x 8 patch and writes that pixel's coefficients into ITS column of the
+//     strip's A tile (16-bit read-modify-writes, thread-exclusive) -- 256 band cells (16 x 16: taps +- 3 px)
+//     x 64 pixels, K-major with the 128-byte swizzle the UMMA descriptors expect; grad_out of the patch
+//     is transposed into a [16 ch][64 px] K-major B tile;
+//   * one thread issues tcgen05.mma.cta_group::1.kind::f16 (M 128 cells, N 16 channels, K 16 pixels):
+//     the band's upper 8 rows accumulate into the TMEM block that was the LOWER block of the previous
+//     step, the lower 8 rows start a fresh block (accumulate flag off) -- "sliding the accumulator down
+//     the strip" is a swap of two TMEM column offsets, nothing is moved or zeroed;
+//   * the finished upper block leaves through tcgen05.ld (thread <-> cell, 16 fp32 channels) as four
+//     128-bit vector reductions per thread into the fp32 plane; every thread then zeroes exactly the A
+//     elements it wrote (no blanket clear, no cross-thread hazard).
+// One CTA barrier and one mbarrier wait per step; offsets / masks / grad_out of the next step arrive
+// by cp.async (dcnv3_strip_io.cuh) while the current step is built.
+//
+// A point whose corner block leaves the band (|offset| beyond ~3 px) sends its four coefficient x
+// grad_out rows straight to the plane (rare for trained offsets; correct for any).
+#include "dcnv3_common.cuh"
+#include "dcnv3_launch.h"
+#include "dcnv3_tma.cuh"
+#include "dcnv3_strip_io.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <type_traits>
+
+namespace dcnv3 {
+namespace vmma {
+
+using namespace strip;   // staging buffer layout, stage_io, PTX wrappers
+
+constexpr int kStrips = 2;                         // strips per CTA (16 output columns)
+constexpr int kWarpsV = 4, kThreadsV = 128;
+constexpr int kRows = 8;                           // output rows per step (two 8 x 4 warp patches)
+constexpr int kBandW = 16, kBandH = 16;            // band of one strip and step: 2 blocks of 8 rows x 16 columns
+constexpr int kATileBytes = kBandW * kBandH * 128; // 256 cells x 64 pixels x 2 B = 32768 per strip
+constexpr int kBlockBytes = kATileBytes / 2;       // 128 cells (one UMMA M block)
+constexpr int kBTileBytes = 16 * 128;              // 16 channels x 64 pixels x 2 B per strip
+constexpr int kSmemV = 1024 + kStrips * (kATileBytes + kBTileBytes) + kWarpsV * kStageBytes + kIoTblBytes;
+constexpr int kTmemCols = 64;                      // 2 strips x 2 blocks x 16 fp32 columns
+
+struct VParams {
+    int bx_rel, by_rel;      // band origin relative to the first pixel of a strip's 8 x 8 patch
+    int tiles_x, tiles_xy, total_tiles;
+    int steps;               // 8-row steps per work item
+    unsigned long long mask_bytes;
+};
+
+// ------------------------------------------------------------------------------------ tcgen05 wrappers
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], both K-major
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major operand tile with 128-byte swizzle (rows of 64 16-bit elements, 8-row groups of 1024 B):
+// start address >> 4 at [0,14), stride byte offset >> 4 at [32,46), version 1 at [46,48),
+// SWIZZLE_128B = 2 at [61,64)  (same encoding as dcnv3_proj.cu)
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: fp32 accumulate, a/b format (F16 = 0, BF16 = 1), K-major A and B, N >> 3, M >> 4
+__host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+#define VMMA_TMEM_LD_16(taddr, r)                                                                              \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]),    \
+                   "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]) \
+                 : "r"(taddr))
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// A point beyond the band: its four coefficient x grad_out rows go straight to the fp32 plane.
+template <typename T>
+__device__ __noinline__ void far_point(float *gv_img, int H, int W, int row_stride, int C, int h0, int w0, float c0,
+                                       float c1, float c2, float c3, uint4 ga, uint4 gb) {
+    float g[16];
+    unpack<T>(ga, g);
+    unpack<T>(gb, g + 8);
+    const float cf[4] = {c0, c1, c2, c3};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int hh = h0 + (t >> 1), ww = w0 + (t & 1);
+        if ((unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W && cf[t] != 0.f) {
+            float *dst = gv_img + (ptrdiff_t)hh * row_stride + (ptrdiff_t)ww * C;
+#pragma unroll
+            for (int e = 0; e < 16; e += 4)
+                red_add4(dst + e, make_float4(cf[t] * g[e], cf[t] * g[e + 1], cf[t] * g[e + 2], cf[t] * g[e + 3]));
+        }
+    }
+}
+
+// One finished block (8 band rows x 16 columns) of both strips: TMEM -> registers -> reductions.
+// Thread (warp, lane) holds TMEM lane 32 warp + lane = cell (row 2 warp + (lane >> 4), column lane & 15).
+__device__ __forceinline__ void drain_block(uint32_t tmem_base, int slot, int warp, int lane, float *gv_img, int y0,
+                                            int x0_strip0, int H, int W, int row_stride, int C) {
+    float r0[16], r1[16];
+    const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
+    VMMA_TMEM_LD_16(tl + (uint32_t)(slot * 16), r0);
+    VMMA_TMEM_LD_16(tl + (uint32_t)((2 + slot) * 16), r1);
+    tmem_ld_wait();
+    const int y = y0 + 2 * warp + (lane >> 4);
+    const int x = x0_strip0 + (lane & 15);
+    if ((unsigned)y < (unsigned)H) {
+        float *p = gv_img + (ptrdiff_t)y * row_stride + (ptrdiff_t)x * C;
+        if ((unsigned)x < (unsigned)W) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) red_add4(p + e, make_float4(r0[e], r0[e + 1], r0[e + 2], r0[e + 3]));
+        }
+        if ((unsigned)(x + kStripW) < (unsigned)W) {
+            p += kStripW * C;
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) red_add4(p + e, make_float4(r1[e], r1[e + 1], r1[e + 2], r1[e + 3]));
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreadsV, 2)
+bwd_vmma(const T *__restrict__ offset, const T *__restrict__ mask, const T *__restrict__ grad_out,
+         float *__restrict__ gv_acc, const Geom q, const VParams pp) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) IoCtx<T> io;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int strip_id = warp >> 1, hw = warp & 1;      // strip of the CTA, upper / lower 8 x 4 half of its patch
+    const int k = hw * 32 + lane;                       // this thread's pixel = K index inside the strip
+    const int px_x = lane & 7, px_y = hw * kPatchH + (lane >> 3);
+
+    unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t a_addr0 = smem_u32(base);                                   // A tiles: [strip][256 rows][128 B]
+    const uint32_t b_addr0 = a_addr0 + kStrips * kATileBytes;                  // B tiles: [strip][16 rows][128 B]
+    unsigned char *stage = base + kStrips * (kATileBytes + kBTileBytes) + warp * kStageBytes;
+    uint32_t *io_tbl = reinterpret_cast<uint32_t *>(base + kStrips * (kATileBytes + kBTileBytes) + kWarpsV * kStageBytes);
+    const uint32_t stage_addr = smem_u32(stage);
+    const uint32_t a_strip = a_addr0 + strip_id * kATileBytes, b_strip = b_addr0 + strip_id * kBTileBytes;
+    const uint32_t kc = (uint32_t)k >> 3, kl = ((uint32_t)k & 7u) * 2u;
+    const uint32_t a_thr = a_strip + kl, b_thr = b_strip + kl;
+
+    const int C = q.G * q.gc, row_stride = q.W * C;
+
+    int t = blockIdx.x;
+    if (t >= pp.total_tiles) return;
+    auto decode = [&](int tt, int &n, int &g, int &wo0, int &ho0) {
+        const int txy = tt % pp.tiles_xy, r = tt / pp.tiles_xy;
+        g = r % q.G; n = r / q.G;
+        wo0 = (txy % pp.tiles_x) * (kStrips * kStripW); ho0 = (txy / pp.tiles_x) * (pp.steps * kRows);
+    };
+    int n, g, wo0, ho0;
+    decode(t, n, g, wo0, ho0);
+    // first pixel of this warp's 8 x 4 patch at step s of an item
+    auto patch_pix = [&](int nn, int w0, int h0, int s) -> size_t {
+        return ((size_t)nn * q.Ho + (h0 + s * kRows + hw * kPatchH)) * q.Wo + (w0 + strip_id * kStripW);
+    };
+
+    if (tid == 0) {
+        io.offset = offset; io.mask = mask; io.grad_out = grad_out; io.grad_offset = nullptr; io.grad_mask = nullptr;
+        io.mask_end = reinterpret_cast<const unsigned char *>(mask) + pp.mask_bytes;
+        io.Wo = q.Wo; io.Ho = q.Ho; io.G = q.G; io.C = C;
+        mbar_init(&mma_bar, 1);
+        fence_barrier_init();
+    }
+    build_io_table(io_tbl, q.Wo, q.G * kP, tid, kThreadsV);
+    for (int i = tid; i < kStrips * kATileBytes / 16; i += kThreadsV) sts128_zero(a_addr0 + i * 16);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t idesc = umma_idesc(std::is_same<T, __nv_bfloat16>::value ? 1 : 0, 128, 16);
+
+    stage_io<T>(&io, io_tbl, stage_addr, 0, 0, 0, 0, 0, patch_pix(n, wo0, ho0, 0), g, wo0 + strip_id * kStripW,
+                ho0 + hw * kPatchH, 1);
+
+    unsigned commits = 0;
+    for (;;) {
+        const int t_next = t + gridDim.x;
+        const bool has_next = t_next < pp.total_tiles;
+        int n2 = n, g2 = g, wo2 = wo0, ho2 = ho0;
+        if (has_next) decode(t_next, n2, g2, wo2, ho2);
+        float *gv_img = gv_acc + (size_t)n * q.H * row_stride + g * q.gc;
+        const int band_x0 = wo0 + strip_id * kStripW + pp.bx_rel;      // this thread's strip
+
+#pragma unroll 1
+        for (int s = 0; s < pp.steps; ++s) {
+            const int hb = ho0 + s * kRows;
+            const int wo = wo0 + strip_id * kStripW + px_x, ho = hb + px_y;
+            const bool live = wo < q.Wo && ho < q.Ho;
+            const int band_y0 = hb + pp.by_rel;
+            cp_async_wait_all();
+            __syncwarp();
+
+            // ---- this pixel's staged inputs into registers, then the buffer is free for the next step
+            uint32_t off[kP], msk[kP];
+            uint4 ga, gb;
+            {
+                const size_t pix = patch_pix(n, wo0, ho0, s);
+                const unsigned sh = (unsigned)(((pix + (size_t)((lane >> 3) * q.Wo + px_x)) * q.G + g) * kP) & 1u;
+                const uint32_t s_off_lane = stage_addr + kStageOff + lane * (kP * 4);
+                const uint32_t s_msk_lane = stage_addr + kStageMsk + lane * (kMskWords * 4) + sh * 2;
+#pragma unroll
+                for (int p = 0; p < kP; ++p) {
+                    off[p] = lds32(s_off_lane + p * 4);
+                    msk[p] = lds16(s_msk_lane + p * 2);
+                }
+                ga = lds128(stage_addr + kStageGout + lane * kSliceBytes);
+                gb = lds128(stage_addr + kStageGout + lane * kSliceBytes + 16);
+                if (!live) { ga = make_uint4(0, 0, 0, 0); gb = ga; }
+            }
+            __syncwarp();
+            {
+                const bool in_item = s + 1 < pp.steps;
+                const int nn = in_item ? n : n2, gg = in_item ? g : g2, w0n = in_item ? wo0 : wo2, h0n = in_item ? ho0 : ho2;
+                const int ns = in_item ? s + 1 : 0;
+                stage_io<T>(&io, io_tbl, stage_addr, 0, 0, 0, 0, 0, patch_pix(nn, w0n, h0n, ns), gg, w0n + strip_id * kStripW,
+                            h0n + ns * kRows + hw * kPatchH, in_item || has_next);
+            }
+
+            // ---- B tile: grad_out of the pixel, transposed to [channel][pixel]
+            {
+                const uint32_t w[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const uint32_t v = (c & 1) ? (w[c >> 1] >> 16) : (w[c >> 1] & 0xffffu);
+                    sts16(b_thr + c * 128 + ((kc ^ (uint32_t)(c & 7)) << 4), v);
+                }
+            }
+
+            // ---- A build: the pixel's 36 coefficients into its column of the strip's tile
+            uint32_t rec[kP];      // offsets of the point's two upper cells inside the tile (lo | hi << 16), ~0: none
+            if (live) {
+                const float bw = axis_base(wo, 3, 1, q.pw, 1, q.sigma) - (float)band_x0;
+                const float bh = axis_base(ho, 3, 1, q.ph, 1, q.sigma) - (float)band_y0;
+#pragma unroll
+                for (int p = 0; p < kP; ++p) {
+                    const float2 d = unpack2(off[p], T());
+                    const float m = f32_of((uint16_t)msk[p], T());
+                    const float ub = bw + ((float)(p / 3) + d.x) * q.sigma;
+                    const float vb = bh + ((float)(p % 3) + d.y) * q.sigma;
+                    const float fw = floorf(ub), fh = floorf(vb);
+                    const float lw = ub - fw, lh = vb - fh;
+                    const float hm = (1.f - lh) * m, lm = lh * m, hwt = 1.f - lw;
+                    // 0 <= x < limit on the float's bit pattern: negative values and NaN compare as large unsigned
+                    if (__float_as_uint(ub) < __float_as_uint((float)(kBandW - 1)) &&
+                        __float_as_uint(vb) < __float_as_uint((float)(kBandH - 1))) {
+                        const uint32_t cx = (uint32_t)(int)fw, ry = (uint32_t)(int)fh;
+                        const uint32_t o0 = (ry * kBandW + cx) * 128u + ((kc ^ (cx & 7u)) << 4);
+                        const uint32_t o1 = (ry * kBandW + cx + 1u) * 128u + ((kc ^ ((cx + 1u) & 7u)) << 4);
+                        const uint32_t e0 = a_thr + o0, e1 = a_thr + o1;
+                        const float a0 = f32_of((uint16_t)lds16(e0), T()), a1 = f32_of((uint16_t)lds16(e1), T());
+                        const float a2 = f32_of((uint16_t)lds16(e0 + kBandW * 128), T()), a3 = f32_of((uint16_t)lds16(e1 + kBandW * 128), T());
+                        sts16(e0, bits16(a0 + hm * hwt, T()));
+                        sts16(e1, bits16(a1 + hm * lw, T()));
+                        sts16(e0 + kBandW * 128, bits16(a2 + lm * hwt, T()));
+                        sts16(e1 + kBandW * 128, bits16(a3 + lm * lw, T()));
+                        rec[p] = o0 | (o1 << 16);
+                    } else {
+                        rec[p] = 0xffffffffu;
+                        // beyond the band: the reference's range test decides whether the point counts at all
+                        const float lw_abs = ub + (float)band_x0, lh_abs = vb + (float)band_y0;
+                        if (lh_abs > -1.f && lw_abs > -1.f && lh_abs < (float)q.H && lw_abs < (float)q.W)
+                            far_point<T>(gv_img, q.H, q.W, row_stride, C, (int)fh + band_y0, (int)fw + band_x0, hm * hwt, hm * lw,
+                                         lm * hwt, lm * lw, ga, gb);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int p = 0; p < kP; ++p) rec[p] = 0xffffffffu;
+            }
+
+            // ---- the tiles are complete: hand them to the tensor core
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+#pragma unroll
+                for (int st = 0; st < kStrips; ++st)
+#pragma unroll
+                    for (int blk = 0; blk < 2; ++blk) {
+                        const uint32_t d = tmem_base + (uint32_t)((st * 2 + ((s + blk) & 1)) * 16);
+                        const uint32_t aa = a_addr0 + st * kATileBytes + blk * kBlockBytes, bb = b_addr0 + st * kBTileBytes;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            tc_mma(d, umma_desc_k_sw128(aa + j * 32), umma_desc_k_sw128(bb + j * 32), idesc,
+                                   (uint32_t)(j > 0 || (blk == 0 && s > 0)));
+                    }
+                tc_commit(&mma_bar);
+            }
+            mbar_wait(&mma_bar, commits & 1u);
+            ++commits;
+            tc_fence_after();
+
+            // ---- the band's upper block is final: reductions; zero what this thread wrote into A
+            drain_block(tmem_base, s & 1, warp, lane, gv_img, band_y0, wo0 + pp.bx_rel, q.H, q.W, row_stride, C);
+#pragma unroll
+            for (int p = 0; p < kP; ++p) {
+                if (rec[p] != 0xffffffffu) {
+                    const uint32_t e0 = a_thr + (rec[p] & 0xffffu), e1 = a_thr + (rec[p] >> 16);
+                    sts16(e0, 0u);
+                    sts16(e1, 0u);
+                    sts16(e0 + kBandW * 128, 0u);
+                    sts16(e1 + kBandW * 128, 0u);
+                }
+            }
+        }
+        // ---- the last step's lower block
+        drain_block(tmem_base, pp.steps & 1, warp, lane, gv_img, ho0 + (pp.steps - 1) * kRows + pp.by_rel + 8,
+                    wo0 + pp.bx_rel, q.H, q.W, row_stride, C);
+        if (!has_next) break;
+        n = n2; g = g2; wo0 = wo2; ho0 = ho2;
+        t = t_next;
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+}
+
+template <typename T>
+static bool launch_typed(const void *offset, const void *mask, const void *grad_out, float *gv_acc, const Geom &q,
+                         cudaStream_t stream, cudaError_t *err) {
+    if (q.gc != kCh || q.kh != 3 || q.kw != 3 || q.sh != 1 || q.sw != 1 || q.dh != 1 || q.dw != 1) return false;
+    if (!(q.sigma >= 0.5f && q.sigma <= 1.25f)) return false;   // band = taps +- 3 px
+    if (((uintptr_t)grad_out | (uintptr_t)gv_acc) % 16 || ((uintptr_t)offset | (uintptr_t)mask) % 4) return false;
+    VParams pp;
+    // nominal taps of a pixel x along an axis: x + a + i*sigma, i = 0..2, a = (1 - pad) - sigma; band centred on them
+    const float a_w = (float)(1 - q.pw) - q.sigma, a_h = (float)(1 - q.ph) - q.sigma;
+    pp.bx_rel = (int)std::floor(a_w + q.sigma + 0.5f * (kStripW - 1) + 0.5f - 0.5f * kBandW);
+    pp.by_rel = (int)std::floor(a_h + q.sigma + 0.5f * (kRows - 1) + 0.5f - 0.5f * kBandH);
+    pp.tiles_x = (q.Wo + kStrips * kStripW - 1) / (kStrips * kStripW);
+    // tall items: an item drains (steps + 1) blocks for `steps` patches
+    const int max_steps = (q.Ho + kRows - 1) / kRows;
+    pp.steps = std::max(1, std::min(max_steps, 5));
+    if (const char *e = std::getenv("DCNV3_VSTEPS")) pp.steps = std::max(1, std::min(max_steps, atoi(e)));
+    const int tile_h = pp.steps * kRows;
+    const int tiles_y = (q.Ho + tile_h - 1) / tile_h;
+    const long long total = (long long)pp.tiles_x * tiles_y * q.G * q.N;
+    if (total >= (1LL << 31)) return false;
+    pp.tiles_xy = pp.tiles_x * tiles_y;
+    pp.total_tiles = (int)total;
+    pp.mask_bytes = (unsigned long long)q.N * q.Ho * q.Wo * q.G * kP * 2ull;
+    if ((long long)(3 * q.Wo + 8) * q.G * kP + kP >= (1LL << 24)) return false;   // staging index table packing
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int ctas = (int)std::min<long long>(total, 2LL * num_sms);
+    cudaFuncSetAttribute(bwd_vmma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemV);
+    bwd_vmma<T><<<ctas, kThreadsV, kSmemV, stream>>>(static_cast<const T *>(offset), static_cast<const T *>(mask),
+                                                     static_cast<const T *>(grad_out), gv_acc, q, pp);
+    *err = cudaGetLastError();
+    return true;
+}
+
+}  // namespace vmma
+
+// grad_value only (accumulated into the zeroed fp32 plane gv_acc); tcgen05 / TMEM form.
+bool try_launch_backward_vmma(const void *offset, const void *mask, const void *grad_out, float *gv_acc,
+                              const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err) {
+    if ((long long)q.N * q.Ho * q.Wo == 0) return false;
+    if (dtype == 1) return vmma::launch_typed<__half>(offset, mask, grad_out, gv_acc, q, stream, err);
+    if (dtype == 2) return vmma::launch_typed<__nv_bfloat16>(offset, mask, grad_out, gv_acc, q, stream, err);
+    return false;
+}
+
+}  // namespace dcnv3

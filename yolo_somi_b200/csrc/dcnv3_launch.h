@@ -40,6 +40,16 @@ bool try_launch_backward_strip(const void *value, const void *offset, const void
                                const void *grad_out, float *gv_acc, void *grad_offset, void *grad_mask,
                                const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err);
 
+// split backward: grad_offset / grad_mask (dcnv3_backward_dots.cu) + grad_value (value-only strip kernel)
+bool try_launch_backward_dots(const void *value, const void *offset, const void *mask, const void *grad_out,
+                              void *grad_offset, void *grad_mask, const Geom &q, int dtype, cudaStream_t stream,
+                              cudaError_t *err);
+bool try_launch_backward_vstrip(const void *offset, const void *mask, const void *grad_out, float *gv_acc,
+                                const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err);
+// grad_value as a tcgen05 product with TMEM accumulators (dcnv3_backward_vmma.cu)
+bool try_launch_backward_vmma(const void *offset, const void *mask, const void *grad_out, float *gv_acc,
+                              const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err);
+
 bool try_launch_backward_mma2(const void *value, const void *offset, const void *mask,
                               const void *grad_out, float *gv_acc, void *grad_offset, void *grad_mask,
                               const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err);
