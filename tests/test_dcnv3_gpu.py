@@ -127,7 +127,7 @@ _TILE_CASES = [
 
 
 @pytest.mark.parametrize("fwd", ["default", "tile", "mma"])
-@pytest.mark.parametrize("bwd", ["default", "split", "mma", "tile", "scatter", "mma2"])
+@pytest.mark.parametrize("bwd", ["default", "strip", "mma", "tile", "scatter", "mma2"])
 @pytest.mark.parametrize("spread", [1.0, 4.0], ids=["near", "far"])
 @pytest.mark.parametrize("case", _TILE_CASES, ids=lambda c: c.name)
 def test_tiled_kernels_vs_oracle(case, spread, bwd, fwd, monkeypatch):

@@ -422,6 +422,30 @@ static cudaError_t launch_scatter(const T *v, const T *o, const T *m, const T *g
     return cudaGetLastError();
 }
 
+// A side stream per device for work that may run beside the main stream inside one call (fork / join
+// with events: no host synchronisation, legal under stream capture).  nullptr if creation fails.
+struct SideStream {
+    cudaStream_t stream;
+    cudaEvent_t fork, join;
+};
+static SideStream *side_stream() {
+    constexpr int kMaxDev = 64;
+    static SideStream tab[kMaxDev];
+    static int state[kMaxDev];   // 0 = not tried, 1 = ready, -1 = failed
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
+    if (state[dev] == 0) {
+        SideStream s{};
+        const bool ok = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess &&
+                        cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) == cudaSuccess &&
+                        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess;
+        tab[dev] = s;
+        state[dev] = ok ? 1 : -1;
+        if (!ok) (void)cudaGetLastError();
+    }
+    return state[dev] == 1 ? &tab[dev] : nullptr;
+}
+
 template <typename T>
 static cudaError_t backward_typed(const void *value, const void *offset, const void *mask,
                                   const void *grad_out, void *grad_value, void *grad_offset,
@@ -458,27 +482,44 @@ static cudaError_t backward_typed(const void *value, const void *offset, const v
         return launch_scatter<T>(v, o, m, go, AccumF32{reinterpret_cast<float *>(gv)}, nullptr, goff, gmsk, q, vec_ok, stream);
     } else {  // 16-bit I/O: fp32 scratch plane, then one narrowing pass
         float *acc = reinterpret_cast<float *>(static_cast<char *>(workspace) + kWorkspaceHeader);
-        if ((err = cudaMemsetAsync(acc, 0, plane * sizeof(float), stream)) != cudaSuccess) return err;
         const int dtype_tag = std::is_same<T, __half>::value ? 1 : 2;
-        // DCNV3_BWD=split (development knob while it is being measured): channel sums and grad_value
-        // in two high-occupancy kernels instead of the fused strip kernel
+        // Default for eligible shapes (gc == 16, G % 8 == 0, 3x3 / stride 1 / dilation 1): the SPLIT backward --
+        // channel sums (grad_offset / grad_mask) in the forward's group-slice layout (dcnv3_backward_dots.cu),
+        // grad_value as a tcgen05 product with TMEM accumulators (dcnv3_backward_vmma.cu).  The channel-sum
+        // kernel does not touch the fp32 plane, so the plane's memset runs beside it on a side stream.
+        // DCNV3_BWD=strip selects the fused register-accumulator kernel, DCNV3_VALUE=hmma the HMMA value kernel.
         {
             const char *e = std::getenv("DCNV3_BWD");
-            const bool split = e && e[0] == 's' && e[1] == 'p';
-            if (split && vec_ok && q.G % 8 == 0) {
+            const bool split = !(e && e[0]) || (e[0] == 's' && e[1] == 'p');
+            const char *ev = std::getenv("DCNV3_VALUE");
+            const bool hmma = ev && ev[0] == 'h';
+            if (split && vec_ok && q.G % 8 == 0 && (hmma || backward_vmma_eligible(offset, mask, grad_out, acc, q))) {
+                SideStream *ss = side_stream();
                 cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
-                // eligibility of both halves is the same set of shapes; check the value half first
-                const char *ev = std::getenv("DCNV3_VALUE");   // "hmma": register-accumulator value kernel
-                const bool hmma = ev && ev[0] == 'h';
-                if ((!hmma && try_launch_backward_vmma(offset, mask, grad_out, acc, q, dtype_tag, stream, &e2)) ||
-                    try_launch_backward_vstrip(offset, mask, grad_out, acc, q, dtype_tag, stream, &e2)) {
-                    if (e2 != cudaSuccess) return e2;
-                    if (!try_launch_backward_dots(value, offset, mask, grad_out, grad_offset, grad_mask, q, dtype_tag, stream, &e1))
-                        return cudaErrorInvalidConfiguration;
-                    if (e1 != cudaSuccess) return e1;
-                    narrow_f32_kernel<T><<<aux_blocks, 256, 0, stream>>>(acc, gv, plane);
-                    return cudaGetLastError();
+                if (ss) {   // fork: memset of the plane || channel sums
+                    if ((err = cudaEventRecord(ss->fork, stream)) != cudaSuccess) return err;
+                    if ((err = cudaStreamWaitEvent(ss->stream, ss->fork, 0)) != cudaSuccess) return err;
+                    if ((err = cudaMemsetAsync(acc, 0, plane * sizeof(float), ss->stream)) != cudaSuccess) return err;
+                    if ((err = cudaEventRecord(ss->join, ss->stream)) != cudaSuccess) return err;
                 }
+                const bool dots = try_launch_backward_dots(value, offset, mask, grad_out, grad_offset, grad_mask, q, dtype_tag, stream, &e1);
+                if (ss) {   // join (also when the channel-sum kernel declined: the plane is needed either way)
+                    if ((err = cudaStreamWaitEvent(stream, ss->join, 0)) != cudaSuccess) return err;
+                } else if ((err = cudaMemsetAsync(acc, 0, plane * sizeof(float), stream)) != cudaSuccess) {
+                    return err;
+                }
+                if (dots) {
+                    if (e1 != cudaSuccess) return e1;
+                    if ((!hmma && try_launch_backward_vmma(offset, mask, grad_out, acc, q, dtype_tag, stream, &e2)) ||
+                        try_launch_backward_vstrip(offset, mask, grad_out, acc, q, dtype_tag, stream, &e2)) {
+                        if (e2 != cudaSuccess) return e2;
+                        narrow_f32_kernel<T><<<aux_blocks, 256, 0, stream>>>(acc, gv, plane);
+                        return cudaGetLastError();
+                    }
+                }
+                // (not reached for eligible shapes) fall through: the fused kernels recompute everything
+            } else if ((err = cudaMemsetAsync(acc, 0, plane * sizeof(float), stream)) != cudaSuccess) {
+                return err;
             }
         }
         if (!(vec_ok && (try_launch_backward_strip(value, offset, mask, grad_out, acc, grad_offset, grad_mask, q, dtype_tag, stream, &err) ||

@@ -20,8 +20,9 @@
 //     step, the lower 8 rows start a fresh block (accumulate flag off) -- "sliding the accumulator down
 //     the strip" is a swap of two TMEM column offsets, nothing is moved or zeroed;
 //   * the finished upper block leaves through tcgen05.ld (thread <-> cell, 16 fp32 channels) as four
-//     128-bit vector reductions per thread into the fp32 plane; every thread then zeroes exactly the A
-//     elements it wrote (no blanket clear, no cross-thread hazard).
+//     128-bit vector reductions per thread into the fp32 plane (lane pairs swap halves: whole sectors);
+//     the A tiles are re-zeroed by a 64 KB bulk copy from an L2-resident zero page (async proxy, no
+//     LSU instructions) that lands while the block is drained and the next step's inputs are read.
 // One CTA barrier and one mbarrier wait per step; offsets / masks / grad_out of the next step arrive
 // by cp.async (dcnv3_strip_io.cuh) while the current step is built.
 //
@@ -51,6 +52,13 @@ constexpr int kBlockBytes = kATileBytes / 2;       // 128 cells (one UMMA M bloc
 constexpr int kBTileBytes = 16 * 128;              // 16 channels x 64 pixels x 2 B per strip
 constexpr int kSmemV = 1024 + kStrips * (kATileBytes + kBTileBytes) + kWarpsV * kStageBytes + kIoTblBytes;
 constexpr int kTmemCols = 64;                      // 2 strips x 2 blocks x 16 fp32 columns
+
+// zeros for the bulk re-fill of the A tiles (L2-resident)
+__device__ __align__(128) unsigned char g_zero_tile[kStrips * kATileBytes];
+__device__ __forceinline__ void bulk_fill(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 struct VParams {
     int bx_rel, by_rel;      // band origin relative to the first pixel of a strip's 8 x 8 patch
@@ -110,7 +118,28 @@ __device__ __noinline__ void far_point(float *gv_img, int H, int W, int row_stri
 }
 
 // One finished block (8 band rows x 16 columns) of both strips: TMEM -> registers -> reductions.
-// Thread (warp, lane) holds TMEM lane 32 warp + lane = cell (row 2 warp + (lane >> 4), column lane & 15).
+// Thread (warp, lane) holds TMEM lane 32 warp + lane = cell (row 2 warp + (lane >> 4), column lane & 15),
+// 16 fp32 channels = two 32-byte sectors.  A lane pair (two adjacent cells) swaps halves so that the two
+// lanes of a pair write the two halves of ONE sector in the same instruction (whole-sector reductions).
+__device__ __forceinline__ void drain_cells(const float (&r)[16], int lane, float *p_even, bool ok_even, bool ok_odd, int C) {
+    const bool odd = lane & 1;
+    float rv[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        rv[j] = __shfl_xor_sync(0xffffffffu, odd ? r[j] : r[4 + j], 1);
+        rv[4 + j] = __shfl_xor_sync(0xffffffffu, odd ? r[8 + j] : r[12 + j], 1);
+    }
+    // even lane: E[0:4] own, O[0:4] recv, E[8:12] own, O[8:12] recv; odd lane: E[4:8] recv, O[4:8] own, E[12:16] recv, O[12:16] own
+    float *pe = p_even + (odd ? 4 : 0), *po = p_even + C + (odd ? 4 : 0);
+    if (ok_even) {
+        red_add4(pe, odd ? make_float4(rv[0], rv[1], rv[2], rv[3]) : make_float4(r[0], r[1], r[2], r[3]));
+        red_add4(pe + 8, odd ? make_float4(rv[4], rv[5], rv[6], rv[7]) : make_float4(r[8], r[9], r[10], r[11]));
+    }
+    if (ok_odd) {
+        red_add4(po, odd ? make_float4(r[4], r[5], r[6], r[7]) : make_float4(rv[0], rv[1], rv[2], rv[3]));
+        red_add4(po + 8, odd ? make_float4(r[12], r[13], r[14], r[15]) : make_float4(rv[4], rv[5], rv[6], rv[7]));
+    }
+}
 __device__ __forceinline__ void drain_block(uint32_t tmem_base, int slot, int warp, int lane, float *gv_img, int y0,
                                             int x0_strip0, int H, int W, int row_stride, int C) {
     float r0[16], r1[16];
@@ -119,19 +148,12 @@ __device__ __forceinline__ void drain_block(uint32_t tmem_base, int slot, int wa
     VMMA_TMEM_LD_16(tl + (uint32_t)((2 + slot) * 16), r1);
     tmem_ld_wait();
     const int y = y0 + 2 * warp + (lane >> 4);
-    const int x = x0_strip0 + (lane & 15);
-    if ((unsigned)y < (unsigned)H) {
-        float *p = gv_img + (ptrdiff_t)y * row_stride + (ptrdiff_t)x * C;
-        if ((unsigned)x < (unsigned)W) {
-#pragma unroll
-            for (int e = 0; e < 16; e += 4) red_add4(p + e, make_float4(r0[e], r0[e + 1], r0[e + 2], r0[e + 3]));
-        }
-        if ((unsigned)(x + kStripW) < (unsigned)W) {
-            p += kStripW * C;
-#pragma unroll
-            for (int e = 0; e < 16; e += 4) red_add4(p + e, make_float4(r1[e], r1[e + 1], r1[e + 2], r1[e + 3]));
-        }
-    }
+    const int xe = x0_strip0 + (lane & 14);            // column of the pair's even cell
+    const bool oky = (unsigned)y < (unsigned)H;
+    float *p = gv_img + (ptrdiff_t)y * row_stride + (ptrdiff_t)xe * C;
+    drain_cells(r0, lane, p, oky && (unsigned)xe < (unsigned)W, oky && (unsigned)(xe + 1) < (unsigned)W, C);
+    drain_cells(r1, lane, p + kStripW * C, oky && (unsigned)(xe + kStripW) < (unsigned)W,
+                oky && (unsigned)(xe + kStripW + 1) < (unsigned)W, C);
 }
 
 template <typename T>
@@ -139,7 +161,7 @@ __global__ void __launch_bounds__(kThreadsV, 2)
 bwd_vmma(const T *__restrict__ offset, const T *__restrict__ mask, const T *__restrict__ grad_out,
          float *__restrict__ gv_acc, const Geom q, const VParams pp) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ __align__(8) uint64_t mma_bar, zero_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) IoCtx<T> io;
 
@@ -179,10 +201,11 @@ bwd_vmma(const T *__restrict__ offset, const T *__restrict__ mask, const T *__re
         io.mask_end = reinterpret_cast<const unsigned char *>(mask) + pp.mask_bytes;
         io.Wo = q.Wo; io.Ho = q.Ho; io.G = q.G; io.C = C;
         mbar_init(&mma_bar, 1);
+        mbar_init(&zero_bar, 1);
         fence_barrier_init();
     }
     build_io_table(io_tbl, q.Wo, q.G * kP, tid, kThreadsV);
-    for (int i = tid; i < kStrips * kATileBytes / 16; i += kThreadsV) sts128_zero(a_addr0 + i * 16);
+    unsigned fills = 0;
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -191,6 +214,10 @@ bwd_vmma(const T *__restrict__ offset, const T *__restrict__ mask, const T *__re
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    if (tid == 0) {   // the A tiles start (and after every product restart) as zeros: bulk copy, async proxy
+        mbar_expect_tx(&zero_bar, kStrips * kATileBytes);
+        bulk_fill(a_addr0, g_zero_tile, kStrips * kATileBytes, &zero_bar);
+    }
     const uint32_t idesc = umma_idesc(std::is_same<T, __nv_bfloat16>::value ? 1 : 0, 128, 16);
 
     stage_io<T>(&io, io_tbl, stage_addr, 0, 0, 0, 0, 0, patch_pix(n, wo0, ho0, 0), g, wo0 + strip_id * kStripW,
@@ -251,7 +278,8 @@ bwd_vmma(const T *__restrict__ offset, const T *__restrict__ mask, const T *__re
             }
 
             // ---- A build: the pixel's 36 coefficients into its column of the strip's tile
-            uint32_t rec[kP];      // offsets of the point's two upper cells inside the tile (lo | hi << 16), ~0: none
+            mbar_wait(&zero_bar, fills & 1u);
+            ++fills;
             if (live) {
                 const float bw = axis_base(wo, 3, 1, q.pw, 1, q.sigma) - (float)band_x0;
                 const float bh = axis_base(ho, 3, 1, q.ph, 1, q.sigma) - (float)band_y0;
@@ -277,9 +305,7 @@ bwd_vmma(const T *__restrict__ offset, const T *__restrict__ mask, const T *__re
                         sts16(e1, bits16(a1 + hm * lw, T()));
                         sts16(e0 + kBandW * 128, bits16(a2 + lm * hwt, T()));
                         sts16(e1 + kBandW * 128, bits16(a3 + lm * lw, T()));
-                        rec[p] = o0 | (o1 << 16);
                     } else {
-                        rec[p] = 0xffffffffu;
                         // beyond the band: the reference's range test decides whether the point counts at all
                         const float lw_abs = ub + (float)band_x0, lh_abs = vb + (float)band_y0;
                         if (lh_abs > -1.f && lw_abs > -1.f && lh_abs < (float)q.H && lw_abs < (float)q.W)
@@ -287,9 +313,6 @@ bwd_vmma(const T *__restrict__ offset, const T *__restrict__ mask, const T *__re
                                          lm * hwt, lm * lw, ga, gb);
                     }
                 }
-            } else {
-#pragma unroll
-                for (int p = 0; p < kP; ++p) rec[p] = 0xffffffffu;
             }
 
             // ---- the tiles are complete: hand them to the tensor core
@@ -315,18 +338,12 @@ bwd_vmma(const T *__restrict__ offset, const T *__restrict__ mask, const T *__re
             ++commits;
             tc_fence_after();
 
-            // ---- the band's upper block is final: reductions; zero what this thread wrote into A
-            drain_block(tmem_base, s & 1, warp, lane, gv_img, band_y0, wo0 + pp.bx_rel, q.H, q.W, row_stride, C);
-#pragma unroll
-            for (int p = 0; p < kP; ++p) {
-                if (rec[p] != 0xffffffffu) {
-                    const uint32_t e0 = a_thr + (rec[p] & 0xffffu), e1 = a_thr + (rec[p] >> 16);
-                    sts16(e0, 0u);
-                    sts16(e1, 0u);
-                    sts16(e0 + kBandW * 128, 0u);
-                    sts16(e1 + kBandW * 128, 0u);
-                }
+            if (tid == 0) {   // the tensor core is done with the tiles: refill them with zeros
+                mbar_expect_tx(&zero_bar, kStrips * kATileBytes);
+                bulk_fill(a_addr0, g_zero_tile, kStrips * kATileBytes, &zero_bar);
             }
+            // ---- the band's upper block is final: reductions
+            drain_block(tmem_base, s & 1, warp, lane, gv_img, band_y0, wo0 + pp.bx_rel, q.H, q.W, row_stride, C);
         }
         // ---- the last step's lower block
         drain_block(tmem_base, pp.steps & 1, warp, lane, gv_img, ho0 + (pp.steps - 1) * kRows + pp.by_rel + 8,
@@ -336,6 +353,7 @@ bwd_vmma(const T *__restrict__ offset, const T *__restrict__ mask, const T *__re
         t = t_next;
     }
 
+    mbar_wait(&zero_bar, fills & 1u);   // the last refill must land before the CTA's memory is released
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
@@ -344,9 +362,7 @@ bwd_vmma(const T *__restrict__ offset, const T *__restrict__ mask, const T *__re
 template <typename T>
 static bool launch_typed(const void *offset, const void *mask, const void *grad_out, float *gv_acc, const Geom &q,
                          cudaStream_t stream, cudaError_t *err) {
-    if (q.gc != kCh || q.kh != 3 || q.kw != 3 || q.sh != 1 || q.sw != 1 || q.dh != 1 || q.dw != 1) return false;
-    if (!(q.sigma >= 0.5f && q.sigma <= 1.25f)) return false;   // band = taps +- 3 px
-    if (((uintptr_t)grad_out | (uintptr_t)gv_acc) % 16 || ((uintptr_t)offset | (uintptr_t)mask) % 4) return false;
+    if (!backward_vmma_eligible(offset, mask, grad_out, gv_acc, q)) return false;
     VParams pp;
     // nominal taps of a pixel x along an axis: x + a + i*sigma, i = 0..2, a = (1 - pad) - sigma; band centred on them
     const float a_w = (float)(1 - q.pw) - q.sigma, a_h = (float)(1 - q.ph) - q.sigma;
@@ -364,7 +380,6 @@ static bool launch_typed(const void *offset, const void *mask, const void *grad_
     pp.tiles_xy = pp.tiles_x * tiles_y;
     pp.total_tiles = (int)total;
     pp.mask_bytes = (unsigned long long)q.N * q.Ho * q.Wo * q.G * kP * 2ull;
-    if ((long long)(3 * q.Wo + 8) * q.G * kP + kP >= (1LL << 24)) return false;   // staging index table packing
     static int num_sms = 0;
     if (num_sms == 0) {
         int dev = 0;
@@ -380,6 +395,17 @@ static bool launch_typed(const void *offset, const void *mask, const void *grad_
 }
 
 }  // namespace vmma
+
+bool backward_vmma_eligible(const void *offset, const void *mask, const void *grad_out, const float *gv_acc, const Geom &q) {
+    using namespace strip;
+    if (q.gc != kCh || q.kh != 3 || q.kw != 3 || q.sh != 1 || q.sw != 1 || q.dh != 1 || q.dw != 1) return false;
+    if (!(q.sigma >= 0.5f && q.sigma <= 1.25f)) return false;   // band = taps +- 3 px
+    if (((uintptr_t)grad_out | (uintptr_t)gv_acc) % 16 || ((uintptr_t)offset | (uintptr_t)mask) % 4) return false;
+    if ((long long)q.N * q.Ho * q.Wo == 0) return false;
+    if ((long long)((q.Wo + 15) / 16) * ((q.Ho + 7) / 8) * q.G * q.N >= (1LL << 31)) return false;
+    if ((long long)(3 * q.Wo + 8) * q.G * kP + kP >= (1LL << 24)) return false;   // staging index table packing
+    return true;
+}
 
 // grad_value only (accumulated into the zeroed fp32 plane gv_acc); tcgen05 / TMEM form.
 bool try_launch_backward_vmma(const void *offset, const void *mask, const void *grad_out, float *gv_acc,

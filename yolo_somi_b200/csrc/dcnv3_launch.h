@@ -47,6 +47,7 @@ bool try_launch_backward_dots(const void *value, const void *offset, const void 
 bool try_launch_backward_vstrip(const void *offset, const void *mask, const void *grad_out, float *gv_acc,
                                 const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err);
 // grad_value as a tcgen05 product with TMEM accumulators (dcnv3_backward_vmma.cu)
+bool backward_vmma_eligible(const void *offset, const void *mask, const void *grad_out, const float *gv_acc, const Geom &q);
 bool try_launch_backward_vmma(const void *offset, const void *mask, const void *grad_out, float *gv_acc,
                               const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err);
 
