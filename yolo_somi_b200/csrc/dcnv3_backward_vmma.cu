@@ -24,7 +24,9 @@
 //     the A tiles are re-zeroed by a 64 KB bulk copy from an L2-resident zero page (async proxy, no
 //     LSU instructions) that lands while the block is drained and the next step's inputs are read.
 // One CTA barrier and one mbarrier wait per step; offsets / masks / grad_out of the next step arrive
-// by cp.async (dcnv3_strip_io.cuh) while the current step is built.
+// as six TMA boxes (8 x 8 pixels x this group's 36 / 18 / 32-byte run, padded to 48 / 32 / 32 bytes per
+// pixel: the box may start at any element) into the other of two stages while the current step is built;
+// pixels beyond the output map read zeros (TMA fill), so ragged tiles need no guards.
 //
 // A point whose corner block leaves the band (|offset| beyond ~3 px) sends its four coefficient x
 // grad_out rows straight to the plane (rare for trained offsets; correct for any).
@@ -50,7 +52,13 @@ constexpr int kBandW = 16, kBandH = 16;            // band of one strip and step
 constexpr int kATileBytes = kBandW * kBandH * 128; // 256 cells x 64 pixels x 2 B = 32768 per strip
 constexpr int kBlockBytes = kATileBytes / 2;       // 128 cells (one UMMA M block)
 constexpr int kBTileBytes = 16 * 128;              // 16 channels x 64 pixels x 2 B per strip
-constexpr int kSmemV = 1024 + kStrips * (kATileBytes + kBTileBytes) + kWarpsV * kStageBytes + kIoTblBytes;
+// staging of one step's inputs, filled by TMA (three boxes per strip: 8 x 8 pixels x this group's run)
+constexpr int kOffRow = 48, kMskRow = 32;          // bytes per pixel: 36 / 18 used, padded to 16-byte multiples
+constexpr int kStOff = 0, kStMsk = 64 * kOffRow, kStGout = kStMsk + 64 * kMskRow;
+constexpr int kStStrip = kStGout + 64 * kSliceBytes;                 // 7168 per strip
+constexpr int kStBytes = kStrips * kStStrip;                         // 14336 per stage
+constexpr int kStages = 2;
+constexpr int kSmemV = 1024 + kStrips * (kATileBytes + kBTileBytes) + kStages * kStBytes;
 constexpr int kTmemCols = 64;                      // 2 strips x 2 blocks x 16 fp32 columns
 
 // zeros for the bulk re-fill of the A tiles (L2-resident)
@@ -64,7 +72,6 @@ struct VParams {
     int bx_rel, by_rel;      // band origin relative to the first pixel of a strip's 8 x 8 patch
     int tiles_x, tiles_xy, total_tiles;
     int steps;               // 8-row steps per work item
-    unsigned long long mask_bytes;
 };
 
 // ------------------------------------------------------------------------------------ tcgen05 wrappers
@@ -156,14 +163,31 @@ __device__ __forceinline__ void drain_block(uint32_t tmem_base, int slot, int wa
                 oky && (unsigned)(xe + kStripW + 1) < (unsigned)W, C);
 }
 
+// 4-D tensor map over a [N, Ho, Wo, row_elems] tensor of 16-bit elements, box (box_elems, 8, 8, 1).  The box
+// may start at any element (a group's run) and run past the row / the map: the hardware zero-fills.
+static bool make_run_tensor_map(CUtensorMap *map, const void *base, int dtype, int N, int Ho, int Wo, int row_elems,
+                                int box_elems) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t es = 2;
+    const CUtensorMapDataType dt = dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const cuuint64_t dims[4] = {(cuuint64_t)row_elems, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)row_elems * es, (cuuint64_t)Wo * row_elems * es,
+                                   (cuuint64_t)Ho * Wo * row_elems * es};
+    const cuuint32_t box[4] = {(cuuint32_t)box_elems, (cuuint32_t)kStripW, (cuuint32_t)kRows, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    return fn(map, dt, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreadsV, 2)
-bwd_vmma(const T *__restrict__ offset, const T *__restrict__ mask, const T *__restrict__ grad_out,
-         float *__restrict__ gv_acc, const Geom q, const VParams pp) {
+bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ CUtensorMap tmap_msk,
+         const __grid_constant__ CUtensorMap tmap_gout, float *__restrict__ gv_acc, const Geom q, const VParams pp) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t mma_bar, zero_bar;
+    __shared__ __align__(8) uint64_t mma_bar, zero_bar, full_bar[kStages];
     __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(16) IoCtx<T> io;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int strip_id = warp >> 1, hw = warp & 1;      // strip of the CTA, upper / lower 8 x 4 half of its patch
@@ -173,9 +197,8 @@ bwd_vmma(const T *__restrict__ offset, const T *__restrict__ mask, const T *__re
     unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t a_addr0 = smem_u32(base);                                   // A tiles: [strip][256 rows][128 B]
     const uint32_t b_addr0 = a_addr0 + kStrips * kATileBytes;                  // B tiles: [strip][16 rows][128 B]
-    unsigned char *stage = base + kStrips * (kATileBytes + kBTileBytes) + warp * kStageBytes;
-    uint32_t *io_tbl = reinterpret_cast<uint32_t *>(base + kStrips * (kATileBytes + kBTileBytes) + kWarpsV * kStageBytes);
-    const uint32_t stage_addr = smem_u32(stage);
+    unsigned char *stages = base + kStrips * (kATileBytes + kBTileBytes);      // [stage][strip][off | msk | gout]
+    const uint32_t st_thr = smem_u32(stages) + strip_id * kStStrip;            // + stage * kStBytes
     const uint32_t a_strip = a_addr0 + strip_id * kATileBytes, b_strip = b_addr0 + strip_id * kBTileBytes;
     const uint32_t kc = (uint32_t)k >> 3, kl = ((uint32_t)k & 7u) * 2u;
     const uint32_t a_thr = a_strip + kl, b_thr = b_strip + kl;
@@ -191,21 +214,30 @@ bwd_vmma(const T *__restrict__ offset, const T *__restrict__ mask, const T *__re
     };
     int n, g, wo0, ho0;
     decode(t, n, g, wo0, ho0);
-    // first pixel of this warp's 8 x 4 patch at step s of an item
-    auto patch_pix = [&](int nn, int w0, int h0, int s) -> size_t {
-        return ((size_t)nn * q.Ho + (h0 + s * kRows + hw * kPatchH)) * q.Wo + (w0 + strip_id * kStripW);
+    // one step's inputs of both strips: six TMA boxes (offsets, masks, grad_out of the 8 x 8 patches) into a stage
+    auto request = [&](unsigned stage, int nn, int gg, int w0, int h0) {
+        uint64_t *bar = &full_bar[stage];
+        unsigned char *dst = stages + stage * kStBytes;
+        mbar_expect_tx(bar, kStBytes);
+#pragma unroll
+        for (int st = 0; st < kStrips; ++st) {
+            // a box starts on a 16-byte boundary of the row: the group's run begins 0..3 words / 0..7 elements in
+            tma_load_4d(dst + st * kStStrip + kStOff, &tmap_off, bar, (gg * kP * 4 & ~15) >> 1, w0 + st * kStripW, h0, nn);
+            tma_load_4d(dst + st * kStStrip + kStMsk, &tmap_msk, bar, (gg * kP * 2 & ~15) >> 1, w0 + st * kStripW, h0, nn);
+            tma_load_4d(dst + st * kStStrip + kStGout, &tmap_gout, bar, gg * kCh, w0 + st * kStripW, h0, nn);
+        }
     };
 
     if (tid == 0) {
-        io.offset = offset; io.mask = mask; io.grad_out = grad_out; io.grad_offset = nullptr; io.grad_mask = nullptr;
-        io.mask_end = reinterpret_cast<const unsigned char *>(mask) + pp.mask_bytes;
-        io.Wo = q.Wo; io.Ho = q.Ho; io.G = q.G; io.C = C;
         mbar_init(&mma_bar, 1);
         mbar_init(&zero_bar, 1);
+        for (int i = 0; i < kStages; ++i) mbar_init(&full_bar[i], 1);
         fence_barrier_init();
+        prefetch_tensormap(&tmap_off);
+        prefetch_tensormap(&tmap_msk);
+        prefetch_tensormap(&tmap_gout);
     }
-    build_io_table(io_tbl, q.Wo, q.G * kP, tid, kThreadsV);
-    unsigned fills = 0;
+    unsigned fills = 0, gstep = 0;
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -220,8 +252,7 @@ bwd_vmma(const T *__restrict__ offset, const T *__restrict__ mask, const T *__re
     }
     const uint32_t idesc = umma_idesc(std::is_same<T, __nv_bfloat16>::value ? 1 : 0, 128, 16);
 
-    stage_io<T>(&io, io_tbl, stage_addr, 0, 0, 0, 0, 0, patch_pix(n, wo0, ho0, 0), g, wo0 + strip_id * kStripW,
-                ho0 + hw * kPatchH, 1);
+    if (tid == 0) request(0, n, g, wo0, ho0);
 
     unsigned commits = 0;
     for (;;) {
@@ -238,33 +269,38 @@ bwd_vmma(const T *__restrict__ offset, const T *__restrict__ mask, const T *__re
             const int wo = wo0 + strip_id * kStripW + px_x, ho = hb + px_y;
             const bool live = wo < q.Wo && ho < q.Ho;
             const int band_y0 = hb + pp.by_rel;
-            cp_async_wait_all();
-            __syncwarp();
-
-            // ---- this pixel's staged inputs into registers, then the buffer is free for the next step
-            uint32_t off[kP], msk[kP];
+            // ---- this step's inputs have landed; the other stage (read one step ago by every thread, all of
+            // which have passed that step's barrier) takes the next step's
+            const unsigned stage = gstep & 1u;
+            mbar_wait(&full_bar[stage], (gstep >> 1) & 1u);
+            ++gstep;
+            if (tid == 0) {
+                const bool in_item = s + 1 < pp.steps;
+                if (in_item) request(stage ^ 1u, n, g, wo0, hb + kRows);
+                else if (has_next) request(stage ^ 1u, n2, g2, wo2, ho2);
+            }
+            uint32_t off[kP], mw[5];
             uint4 ga, gb;
             {
-                const size_t pix = patch_pix(n, wo0, ho0, s);
-                const unsigned sh = (unsigned)(((pix + (size_t)((lane >> 3) * q.Wo + px_x)) * q.G + g) * kP) & 1u;
-                const uint32_t s_off_lane = stage_addr + kStageOff + lane * (kP * 4);
-                const uint32_t s_msk_lane = stage_addr + kStageMsk + lane * (kMskWords * 4) + sh * 2;
+                const uint32_t sa = st_thr + stage * kStBytes;
+                const uint4 o0 = lds128(sa + kStOff + k * kOffRow), o1 = lds128(sa + kStOff + k * kOffRow + 16),
+                            o2 = lds128(sa + kStOff + k * kOffRow + 32);
+                const uint32_t w[12] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w, o2.x, o2.y, o2.z, o2.w};
+                const unsigned osh = ((unsigned)(g * kP * 4) & 15u) >> 2;         // warp-uniform: 0..3 words
 #pragma unroll
-                for (int p = 0; p < kP; ++p) {
-                    off[p] = lds32(s_off_lane + p * 4);
-                    msk[p] = lds16(s_msk_lane + p * 2);
-                }
-                ga = lds128(stage_addr + kStageGout + lane * kSliceBytes);
-                gb = lds128(stage_addr + kStageGout + lane * kSliceBytes + 16);
-                if (!live) { ga = make_uint4(0, 0, 0, 0); gb = ga; }
-            }
-            __syncwarp();
-            {
-                const bool in_item = s + 1 < pp.steps;
-                const int nn = in_item ? n : n2, gg = in_item ? g : g2, w0n = in_item ? wo0 : wo2, h0n = in_item ? ho0 : ho2;
-                const int ns = in_item ? s + 1 : 0;
-                stage_io<T>(&io, io_tbl, stage_addr, 0, 0, 0, 0, 0, patch_pix(nn, w0n, h0n, ns), gg, w0n + strip_id * kStripW,
-                            h0n + ns * kRows + hw * kPatchH, in_item || has_next);
+                for (int p = 0; p < kP; ++p) off[p] = osh == 0 ? w[p] : osh == 1 ? w[p + 1] : osh == 2 ? w[p + 2] : w[p + 3];
+                const uint4 m0 = lds128(sa + kStMsk + k * kMskRow), m1 = lds128(sa + kStMsk + k * kMskRow + 16);
+                const uint32_t v[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+                const unsigned esh = ((unsigned)(g * kP * 2) & 15u) >> 1;         // warp-uniform: 0..7 elements
+                uint32_t u[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) u[j] = (esh & 1u) ? __funnelshift_r(v[j], j + 1 < 8 ? v[j + 1] : 0u, 16) : v[j];
+                const unsigned ws = esh >> 1;
+#pragma unroll
+                for (int j = 0; j < 5; ++j)
+                    mw[j] = ws == 0 ? u[j] : ws == 1 ? u[j + 1] : ws == 2 ? u[j + 2] : (j + 3 < 8 ? u[j + 3] : 0u);
+                ga = lds128(sa + kStGout + k * kSliceBytes);
+                gb = lds128(sa + kStGout + k * kSliceBytes + 16);
             }
 
             // ---- B tile: grad_out of the pixel, transposed to [channel][pixel]
@@ -286,7 +322,7 @@ bwd_vmma(const T *__restrict__ offset, const T *__restrict__ mask, const T *__re
 #pragma unroll
                 for (int p = 0; p < kP; ++p) {
                     const float2 d = unpack2(off[p], T());
-                    const float m = f32_of((uint16_t)msk[p], T());
+                    const float m = f32_of((uint16_t)(mw[p >> 1] >> (16 * (p & 1))), T());
                     const float ub = bw + ((float)(p / 3) + d.x) * q.sigma;
                     const float vb = bh + ((float)(p % 3) + d.y) * q.sigma;
                     const float fw = floorf(ub), fh = floorf(vb);
@@ -379,7 +415,11 @@ static bool launch_typed(const void *offset, const void *mask, const void *grad_
     if (total >= (1LL << 31)) return false;
     pp.tiles_xy = pp.tiles_x * tiles_y;
     pp.total_tiles = (int)total;
-    pp.mask_bytes = (unsigned long long)q.N * q.Ho * q.Wo * q.G * kP * 2ull;
+    CUtensorMap to, tm, tg;
+    const int dtype = std::is_same<T, __half>::value ? 1 : 2;
+    if (!make_run_tensor_map(&to, offset, dtype, q.N, q.Ho, q.Wo, q.G * kP * 2, kOffRow / 2)) return false;
+    if (!make_run_tensor_map(&tm, mask, dtype, q.N, q.Ho, q.Wo, q.G * kP, kMskRow / 2)) return false;
+    if (!make_run_tensor_map(&tg, grad_out, dtype, q.N, q.Ho, q.Wo, q.G * kCh, kCh)) return false;
     static int num_sms = 0;
     if (num_sms == 0) {
         int dev = 0;
@@ -388,8 +428,7 @@ static bool launch_typed(const void *offset, const void *mask, const void *grad_
     }
     const int ctas = (int)std::min<long long>(total, 2LL * num_sms);
     cudaFuncSetAttribute(bwd_vmma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemV);
-    bwd_vmma<T><<<ctas, kThreadsV, kSmemV, stream>>>(static_cast<const T *>(offset), static_cast<const T *>(mask),
-                                                     static_cast<const T *>(grad_out), gv_acc, q, pp);
+    bwd_vmma<T><<<ctas, kThreadsV, kSmemV, stream>>>(to, tm, tg, gv_acc, q, pp);
     *err = cudaGetLastError();
     return true;
 }
@@ -400,10 +439,10 @@ bool backward_vmma_eligible(const void *offset, const void *mask, const void *gr
     using namespace strip;
     if (q.gc != kCh || q.kh != 3 || q.kw != 3 || q.sh != 1 || q.sw != 1 || q.dh != 1 || q.dw != 1) return false;
     if (!(q.sigma >= 0.5f && q.sigma <= 1.25f)) return false;   // band = taps +- 3 px
-    if (((uintptr_t)grad_out | (uintptr_t)gv_acc) % 16 || ((uintptr_t)offset | (uintptr_t)mask) % 4) return false;
+    // TMA staging: 16-byte aligned bases and row strides (G * 18 B for the masks: G % 8 == 0)
+    if (((uintptr_t)grad_out | (uintptr_t)gv_acc | (uintptr_t)offset | (uintptr_t)mask) % 16 || q.G % 8) return false;
     if ((long long)q.N * q.Ho * q.Wo == 0) return false;
     if ((long long)((q.Wo + 15) / 16) * ((q.Ho + 7) / 8) * q.G * q.N >= (1LL << 31)) return false;
-    if ((long long)(3 * q.Wo + 8) * q.G * kP + kP >= (1LL << 24)) return false;   // staging index table packing
     return true;
 }
 
