@@ -45,7 +45,8 @@ namespace vmma {
 
 using namespace strip;   // staging buffer layout, stage_io, PTX wrappers
 
-constexpr int kStrips = 2;                         // strips per CTA (16 output columns)
+constexpr int kStrips = 1;                         // strips per CTA
+constexpr int kCtasPerSm = 4;
 constexpr int kWarpsV = 4, kThreadsV = 128;
 constexpr int kRows = 8;                           // output rows per step (two 8 x 4 warp patches)
 constexpr int kBandW = 16, kBandH = 16;            // band of one strip and step: 2 blocks of 8 rows x 16 columns
@@ -59,7 +60,7 @@ constexpr int kStStrip = kStGout + 64 * kSliceBytes;                 // 7168 per
 constexpr int kStBytes = kStrips * kStStrip;                         // 14336 per stage
 constexpr int kStages = 2;
 constexpr int kSmemV = 1024 + kStrips * (kATileBytes + kBTileBytes) + kStages * kStBytes;
-constexpr int kTmemCols = 64;                      // 2 strips x 2 blocks x 16 fp32 columns
+constexpr int kTmemCols = 32;                      // 2 blocks x 16 fp32 columns
 
 // zeros for the bulk re-fill of the A tiles (L2-resident)
 __device__ __align__(128) unsigned char g_zero_tile[kStrips * kATileBytes];
@@ -148,19 +149,15 @@ __device__ __forceinline__ void drain_cells(const float (&r)[16], int lane, floa
     }
 }
 __device__ __forceinline__ void drain_block(uint32_t tmem_base, int slot, int warp, int lane, float *gv_img, int y0,
-                                            int x0_strip0, int H, int W, int row_stride, int C) {
-    float r0[16], r1[16];
-    const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
-    VMMA_TMEM_LD_16(tl + (uint32_t)(slot * 16), r0);
-    VMMA_TMEM_LD_16(tl + (uint32_t)((2 + slot) * 16), r1);
+                                            int x0, int H, int W, int row_stride, int C) {
+    float r0[16];
+    VMMA_TMEM_LD_16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(slot * 16), r0);
     tmem_ld_wait();
     const int y = y0 + 2 * warp + (lane >> 4);
-    const int xe = x0_strip0 + (lane & 14);            // column of the pair's even cell
+    const int xe = x0 + (lane & 14);            // column of the pair's even cell
     const bool oky = (unsigned)y < (unsigned)H;
     float *p = gv_img + (ptrdiff_t)y * row_stride + (ptrdiff_t)xe * C;
     drain_cells(r0, lane, p, oky && (unsigned)xe < (unsigned)W, oky && (unsigned)(xe + 1) < (unsigned)W, C);
-    drain_cells(r1, lane, p + kStripW * C, oky && (unsigned)(xe + kStripW) < (unsigned)W,
-                oky && (unsigned)(xe + kStripW + 1) < (unsigned)W, C);
 }
 
 // 4-D tensor map over a [N, Ho, Wo, row_elems] tensor of 16-bit elements, box (box_elems, 8, 8, 1).  The box
@@ -182,7 +179,7 @@ static bool make_run_tensor_map(CUtensorMap *map, const void *base, int dtype, i
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreadsV, 2)
+__global__ void __launch_bounds__(kThreadsV, kCtasPerSm)
 bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ CUtensorMap tmap_msk,
          const __grid_constant__ CUtensorMap tmap_gout, float *__restrict__ gv_acc, const Geom q, const VParams pp) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -190,8 +187,10 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int strip_id = warp >> 1, hw = warp & 1;      // strip of the CTA, upper / lower 8 x 4 half of its patch
-    const int k = hw * 32 + lane;                       // this thread's pixel = K index inside the strip
+    // two threads per pixel: warp = (half patch hw, row parity par); a thread owns the cells of ITS parity of band
+    // rows in the pixel's column of A (a point's upper and lower corner rows differ in parity: no races)
+    const int strip_id = 0, hw = warp & 1, par = warp >> 1;
+    const int k = hw * 32 + lane;                       // the pixel = K index inside the strip
     const int px_x = lane & 7, px_y = hw * kPatchH + (lane >> 3);
 
     unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -303,13 +302,14 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                 gb = lds128(sa + kStGout + k * kSliceBytes + 16);
             }
 
-            // ---- B tile: grad_out of the pixel, transposed to [channel][pixel]
+            // ---- B tile: grad_out of the pixel, transposed to [channel][pixel]; this thread's 8 channels
             {
-                const uint32_t w[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+                const uint4 gq = par ? gb : ga;
+                const uint32_t w[4] = {gq.x, gq.y, gq.z, gq.w};
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
+                for (int c = 0; c < 8; ++c) {
                     const uint32_t v = (c & 1) ? (w[c >> 1] >> 16) : (w[c >> 1] & 0xffffu);
-                    sts16(b_thr + c * 128 + ((kc ^ (uint32_t)(c & 7)) << 4), v);
+                    sts16(b_thr + (uint32_t)(par * 8 + c) * 128u + ((kc ^ (uint32_t)c) << 4), v);
                 }
             }
 
@@ -327,26 +327,26 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                     const float vb = bh + ((float)(p % 3) + d.y) * q.sigma;
                     const float fw = floorf(ub), fh = floorf(vb);
                     const float lw = ub - fw, lh = vb - fh;
-                    const float hm = (1.f - lh) * m, lm = lh * m, hwt = 1.f - lw;
                     // 0 <= x < limit on the float's bit pattern: negative values and NaN compare as large unsigned
                     if (__float_as_uint(ub) < __float_as_uint((float)(kBandW - 1)) &&
                         __float_as_uint(vb) < __float_as_uint((float)(kBandH - 1))) {
                         const uint32_t cx = (uint32_t)(int)fw, ry = (uint32_t)(int)fh;
-                        const uint32_t o0 = (ry * kBandW + cx) * 128u + ((kc ^ (cx & 7u)) << 4);
-                        const uint32_t o1 = (ry * kBandW + cx + 1u) * 128u + ((kc ^ ((cx + 1u) & 7u)) << 4);
-                        const uint32_t e0 = a_thr + o0, e1 = a_thr + o1;
+                        const uint32_t low = (ry ^ (uint32_t)par) & 1u;      // 1: this thread's row is the point's lower one
+                        const uint32_t r = ry + low;
+                        const float wr = (low ? lh : 1.f - lh) * m;
+                        const uint32_t e0 = a_thr + (r * kBandW + cx) * 128u + ((kc ^ (cx & 7u)) << 4);
+                        const uint32_t e1 = a_thr + (r * kBandW + cx + 1u) * 128u + ((kc ^ ((cx + 1u) & 7u)) << 4);
                         const float a0 = f32_of((uint16_t)lds16(e0), T()), a1 = f32_of((uint16_t)lds16(e1), T());
-                        const float a2 = f32_of((uint16_t)lds16(e0 + kBandW * 128), T()), a3 = f32_of((uint16_t)lds16(e1 + kBandW * 128), T());
-                        sts16(e0, bits16(a0 + hm * hwt, T()));
-                        sts16(e1, bits16(a1 + hm * lw, T()));
-                        sts16(e0 + kBandW * 128, bits16(a2 + lm * hwt, T()));
-                        sts16(e1 + kBandW * 128, bits16(a3 + lm * lw, T()));
-                    } else {
+                        sts16(e0, bits16(a0 + wr * (1.f - lw), T()));
+                        sts16(e1, bits16(a1 + wr * lw, T()));
+                    } else if (par == 0) {
                         // beyond the band: the reference's range test decides whether the point counts at all
                         const float lw_abs = ub + (float)band_x0, lh_abs = vb + (float)band_y0;
-                        if (lh_abs > -1.f && lw_abs > -1.f && lh_abs < (float)q.H && lw_abs < (float)q.W)
+                        if (lh_abs > -1.f && lw_abs > -1.f && lh_abs < (float)q.H && lw_abs < (float)q.W) {
+                            const float hm = (1.f - lh) * m, lm = lh * m, hwt = 1.f - lw;
                             far_point<T>(gv_img, q.H, q.W, row_stride, C, (int)fh + band_y0, (int)fw + band_x0, hm * hwt, hm * lw,
                                          lm * hwt, lm * lw, ga, gb);
+                        }
                     }
                 }
             }
@@ -426,7 +426,7 @@ static bool launch_typed(const void *offset, const void *mask, const void *grad_
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    const int ctas = (int)std::min<long long>(total, 2LL * num_sms);
+    const int ctas = (int)std::min<long long>(total, (long long)kCtasPerSm * num_sms);
     cudaFuncSetAttribute(bwd_vmma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemV);
     bwd_vmma<T><<<ctas, kThreadsV, kSmemV, stream>>>(to, tm, tg, gv_acc, q, pp);
     *err = cudaGetLastError();
@@ -442,7 +442,7 @@ bool backward_vmma_eligible(const void *offset, const void *mask, const void *gr
     // TMA staging: 16-byte aligned bases and row strides (G * 18 B for the masks: G % 8 == 0)
     if (((uintptr_t)grad_out | (uintptr_t)gv_acc | (uintptr_t)offset | (uintptr_t)mask) % 16 || q.G % 8) return false;
     if ((long long)q.N * q.Ho * q.Wo == 0) return false;
-    if ((long long)((q.Wo + 15) / 16) * ((q.Ho + 7) / 8) * q.G * q.N >= (1LL << 31)) return false;
+    if ((long long)((q.Wo + 7) / 8) * ((q.Ho + 7) / 8) * q.G * q.N >= (1LL << 31)) return false;
     return true;
 }
 
