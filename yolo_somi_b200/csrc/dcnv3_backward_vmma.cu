@@ -14,7 +14,8 @@
 //     one pixel of the step's 8 x 8 patch and writes that pixel's coefficients into ITS column of the
 //     strip's A tile (16-bit read-modify-writes, thread-exclusive) -- 256 band cells (16 x 16: taps +- 3 px)
 //     x 64 pixels, K-major with the 128-byte swizzle the UMMA descriptors expect; grad_out of the patch
-//     is transposed into a [16 ch][64 px] K-major B tile;
+//     is the B operand exactly as two TMA boxes deliver it ([8-channel half][64 px][16 B] = the MN-major
+//     canonical layout without swizzle), nothing is transposed;
 //   * one thread issues tcgen05.mma.cta_group::1.kind::f16 (M 128 cells, N 16 channels, K 16 pixels):
 //     the band's upper 8 rows accumulate into the TMEM block that was the LOWER block of the previous
 //     step, the lower 8 rows start a fresh block (accumulate flag off) -- "sliding the accumulator down
@@ -59,7 +60,7 @@ constexpr int kStOff = 0, kStMsk = 64 * kOffRow, kStGout = kStMsk + 64 * kMskRow
 constexpr int kStStrip = kStGout + 64 * kSliceBytes;                 // 7168 per strip
 constexpr int kStBytes = kStrips * kStStrip;                         // 14336 per stage
 constexpr int kStages = 2;
-constexpr int kSmemV = 1024 + kStrips * (kATileBytes + kBTileBytes) + kStages * kStBytes;
+constexpr int kSmemV = 1024 + kStrips * kATileBytes + kStages * kStBytes;
 constexpr int kTmemCols = 32;                      // 2 blocks x 16 fp32 columns
 
 // zeros for the bulk re-fill of the A tiles (L2-resident)
@@ -93,9 +94,16 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// instruction descriptor: fp32 accumulate, a/b format (F16 = 0, BF16 = 1), K-major A and B, N >> 3, M >> 4
+// MN-major operand without swizzle (cute/atom/mma_traits_sm100.hpp, Major::MN / INTERLEAVE): core matrices of
+// 8 K-rows x 16 bytes (8 MN elements) stored contiguously (128 B); `lbo` = byte distance between core matrices
+// along K (leading byte offset, [16,30)), `sbo` = along MN (stride byte offset, [32,46)); layout type 0.
+__device__ __forceinline__ uint64_t umma_desc_mn_plain(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+// instruction descriptor: fp32 accumulate, a/b format (F16 = 0, BF16 = 1), K-major A (bit 15 = 0), MN-major B
+// (bit 16 = 1: grad_out stays pixel-major, as the TMA delivers it), N >> 3, M >> 4
 __host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {
-    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 #define VMMA_TMEM_LD_16(taddr, r)                                                                              \
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
@@ -195,12 +203,11 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
 
     unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t a_addr0 = smem_u32(base);                                   // A tiles: [strip][256 rows][128 B]
-    const uint32_t b_addr0 = a_addr0 + kStrips * kATileBytes;                  // B tiles: [strip][16 rows][128 B]
-    unsigned char *stages = base + kStrips * (kATileBytes + kBTileBytes);      // [stage][strip][off | msk | gout]
+    unsigned char *stages = base + kStrips * kATileBytes;                      // [stage][strip][off | msk | gout]
     const uint32_t st_thr = smem_u32(stages) + strip_id * kStStrip;            // + stage * kStBytes
-    const uint32_t a_strip = a_addr0 + strip_id * kATileBytes, b_strip = b_addr0 + strip_id * kBTileBytes;
+    const uint32_t a_strip = a_addr0 + strip_id * kATileBytes;
     const uint32_t kc = (uint32_t)k >> 3, kl = ((uint32_t)k & 7u) * 2u;
-    const uint32_t a_thr = a_strip + kl, b_thr = b_strip + kl;
+    const uint32_t a_thr = a_strip + kl;
 
     const int C = q.G * q.gc, row_stride = q.W * C;
 
@@ -223,7 +230,9 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
             // a box starts on a 16-byte boundary of the row: the group's run begins 0..3 words / 0..7 elements in
             tma_load_4d(dst + st * kStStrip + kStOff, &tmap_off, bar, (gg * kP * 4 & ~15) >> 1, w0 + st * kStripW, h0, nn);
             tma_load_4d(dst + st * kStStrip + kStMsk, &tmap_msk, bar, (gg * kP * 2 & ~15) >> 1, w0 + st * kStripW, h0, nn);
+            // grad_out as two boxes of 8 channels: [half][64 px][16 B] is the MMA's B operand as it lands (MN-major)
             tma_load_4d(dst + st * kStStrip + kStGout, &tmap_gout, bar, gg * kCh, w0 + st * kStripW, h0, nn);
+            tma_load_4d(dst + st * kStStrip + kStGout + 1024, &tmap_gout, bar, gg * kCh + 8, w0 + st * kStripW, h0, nn);
         }
     };
 
@@ -279,9 +288,8 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                 else if (has_next) request(stage ^ 1u, n2, g2, wo2, ho2);
             }
             uint32_t off[kP], mw[5];
-            uint4 ga, gb;
+            const uint32_t sa = st_thr + stage * kStBytes;
             {
-                const uint32_t sa = st_thr + stage * kStBytes;
                 const uint4 o0 = lds128(sa + kStOff + k * kOffRow), o1 = lds128(sa + kStOff + k * kOffRow + 16),
                             o2 = lds128(sa + kStOff + k * kOffRow + 32);
                 const uint32_t w[12] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w, o2.x, o2.y, o2.z, o2.w};
@@ -298,19 +306,6 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
 #pragma unroll
                 for (int j = 0; j < 5; ++j)
                     mw[j] = ws == 0 ? u[j] : ws == 1 ? u[j + 1] : ws == 2 ? u[j + 2] : (j + 3 < 8 ? u[j + 3] : 0u);
-                ga = lds128(sa + kStGout + k * kSliceBytes);
-                gb = lds128(sa + kStGout + k * kSliceBytes + 16);
-            }
-
-            // ---- B tile: grad_out of the pixel, transposed to [channel][pixel]; this thread's 8 channels
-            {
-                const uint4 gq = par ? gb : ga;
-                const uint32_t w[4] = {gq.x, gq.y, gq.z, gq.w};
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint32_t v = (c & 1) ? (w[c >> 1] >> 16) : (w[c >> 1] & 0xffffu);
-                    sts16(b_thr + (uint32_t)(par * 8 + c) * 128u + ((kc ^ (uint32_t)c) << 4), v);
-                }
             }
 
             // ---- A build: the pixel's 36 coefficients into its column of the strip's tile
@@ -345,7 +340,7 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                         if (lh_abs > -1.f && lw_abs > -1.f && lh_abs < (float)q.H && lw_abs < (float)q.W) {
                             const float hm = (1.f - lh) * m, lm = lh * m, hwt = 1.f - lw;
                             far_point<T>(gv_img, q.H, q.W, row_stride, C, (int)fh + band_y0, (int)fw + band_x0, hm * hwt, hm * lw,
-                                         lm * hwt, lm * lw, ga, gb);
+                                         lm * hwt, lm * lw, lds128(sa + kStGout + k * 16), lds128(sa + kStGout + 1024 + k * 16));
                         }
                     }
                 }
@@ -362,10 +357,11 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
 #pragma unroll
                     for (int blk = 0; blk < 2; ++blk) {
                         const uint32_t d = tmem_base + (uint32_t)((st * 2 + ((s + blk) & 1)) * 16);
-                        const uint32_t aa = a_addr0 + st * kATileBytes + blk * kBlockBytes, bb = b_addr0 + st * kBTileBytes;
+                        const uint32_t aa = a_addr0 + st * kATileBytes + blk * kBlockBytes;
+                        const uint32_t bb = smem_u32(stages) + stage * kStBytes + st * kStStrip + kStGout;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            tc_mma(d, umma_desc_k_sw128(aa + j * 32), umma_desc_k_sw128(bb + j * 32), idesc,
+                        for (int j = 0; j < 4; ++j)   // K step = 16 pixels: 32 B of an A row, 256 B of the pixel-major B
+                            tc_mma(d, umma_desc_k_sw128(aa + j * 32), umma_desc_mn_plain(bb + j * 256, 128, 1024), idesc,
                                    (uint32_t)(j > 0 || (blk == 0 && s > 0)));
                     }
                 tc_commit(&mma_bar);
@@ -419,7 +415,7 @@ static bool launch_typed(const void *offset, const void *mask, const void *grad_
     const int dtype = std::is_same<T, __half>::value ? 1 : 2;
     if (!make_run_tensor_map(&to, offset, dtype, q.N, q.Ho, q.Wo, q.G * kP * 2, kOffRow / 2)) return false;
     if (!make_run_tensor_map(&tm, mask, dtype, q.N, q.Ho, q.Wo, q.G * kP, kMskRow / 2)) return false;
-    if (!make_run_tensor_map(&tg, grad_out, dtype, q.N, q.Ho, q.Wo, q.G * kCh, kCh)) return false;
+    if (!make_run_tensor_map(&tg, grad_out, dtype, q.N, q.Ho, q.Wo, q.G * kCh, 8)) return false;
     static int num_sms = 0;
     if (num_sms == 0) {
         int dev = 0;
