@@ -10,24 +10,29 @@
 // Why tensor memory (profiles/README.md, r1_v4): the register-accumulator strip kernel keeps 96
 // accumulator registers per thread (252 in all, 8 warps per SM), moves the A tile through ldmatrix and
 // shifts the accumulators down the strip with 64 moves per step.  Here
-//   * a CTA of four warps walks two 8-pixel-wide strips down the map, eight rows per step; a thread is
-//     one pixel of the step's 8 x 8 patch and writes that pixel's coefficients into ITS column of the
-//     strip's A tile (16-bit read-modify-writes, thread-exclusive) -- 256 band cells (16 x 16: taps +- 3 px)
-//     x 64 pixels, K-major with the 128-byte swizzle the UMMA descriptors expect; grad_out of the patch
-//     is the B operand exactly as two TMA boxes deliver it ([8-channel half][64 px][16 B] = the MN-major
-//     canonical layout without swizzle), nothing is transposed;
+//   * a CTA of four warps walks ONE 8-pixel-wide strip down the map, eight rows per step, four CTAs per SM;
+//     a thread of warps 0-1 is one pixel of the step's 8 x 8 patch and writes that pixel's 36 coefficients
+//     into ITS column of the A tile (16-bit read-modify-writes, thread-exclusive) -- 256 band cells
+//     (16 x 16: taps +- 3 px) x 64 pixels, K-major with the 128-byte swizzle the UMMA descriptors expect;
+//     grad_out of the patch is the B operand exactly as two TMA boxes deliver it ([8-channel half][64 px]
+//     [16 B] = the MN-major canonical layout without swizzle), nothing is transposed;
 //   * one thread issues tcgen05.mma.cta_group::1.kind::f16 (M 128 cells, N 16 channels, K 16 pixels):
 //     the band's upper 8 rows accumulate into the TMEM block that was the LOWER block of the previous
 //     step, the lower 8 rows start a fresh block (accumulate flag off) -- "sliding the accumulator down
 //     the strip" is a swap of two TMEM column offsets, nothing is moved or zeroed;
-//   * the finished upper block leaves through tcgen05.ld (thread <-> cell, 16 fp32 channels) as four
-//     128-bit vector reductions per thread into the fp32 plane (lane pairs swap halves: whole sectors);
-//     the A tiles are re-zeroed by a 64 KB bulk copy from an L2-resident zero page (async proxy, no
-//     LSU instructions) that lands while the block is drained and the next step's inputs are read.
-// One CTA barrier and one mbarrier wait per step; offsets / masks / grad_out of the next step arrive
-// as six TMA boxes (8 x 8 pixels x this group's 36 / 18 / 32-byte run, padded to 48 / 32 / 32 bytes per
-// pixel: the box may start at any element) into the other of two stages while the current step is built;
-// pixels beyond the output map read zeros (TMA fill), so ragged tiles need no guards.
+//   * the finished upper block leaves through tcgen05.ld by all four warps (thread <-> cell, 16 fp32
+//     channels) as four 128-bit vector reductions per thread into the fp32 plane (lane pairs swap halves:
+//     whole sectors); the A tile is re-zeroed by a 32 KB bulk copy from an L2-resident zero page (async
+//     proxy, no LSU instructions) that lands while the block is drained and the next inputs are read.
+// One CTA barrier and one mbarrier wait per step; offsets / masks / grad_out of the next step arrive as
+// four TMA boxes (8 x 8 pixels x this group's 36 / 18 / 2 x 16-byte run; the offset / mask boxes start on
+// the 16-byte boundary below the run and are 48 / 32 bytes wide, the run's start inside them is a
+// warp-uniform shift) into the other of two stages while the current step is built; pixels beyond the
+// output map read zeros (TMA fill), so ragged tiles need no guards.
+//
+// Measured on cfg2 bf16 (profiles/README.md, r1_v5): 158 us against 230 us for the HMMA value-only strip
+// kernel; variants tried on the way: two strips per CTA / 2 CTAs per SM with cp.async staging 207 us, with
+// TMA staging 173 us, two threads per pixel (row-parity ownership) 160 us.
 //
 // A point whose corner block leaves the band (|offset| beyond ~3 px) sends its four coefficient x
 // grad_out rows straight to the plane (rare for trained offsets; correct for any).
@@ -53,7 +58,6 @@ constexpr int kRows = 8;                           // output rows per step (two 
 constexpr int kBandW = 16, kBandH = 16;            // band of one strip and step: 2 blocks of 8 rows x 16 columns
 constexpr int kATileBytes = kBandW * kBandH * 128; // 256 cells x 64 pixels x 2 B = 32768 per strip
 constexpr int kBlockBytes = kATileBytes / 2;       // 128 cells (one UMMA M block)
-constexpr int kBTileBytes = 16 * 128;              // 16 channels x 64 pixels x 2 B per strip
 // staging of one step's inputs, filled by TMA (three boxes per strip: 8 x 8 pixels x this group's run)
 constexpr int kOffRow = 48, kMskRow = 32;          // bytes per pixel: 36 / 18 used, padded to 16-byte multiples
 constexpr int kStOff = 0, kStMsk = 64 * kOffRow, kStGout = kStMsk + 64 * kMskRow;
@@ -195,8 +199,8 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // two threads per pixel: warp = (half patch hw, row parity par); a thread owns the cells of ITS parity of band
-    // rows in the pixel's column of A (a point's upper and lower corner rows differ in parity: no races)
+    // warps 0-1 (par == 0): builders, thread <-> pixel of the 8 x 8 patch; warps 2-3 join for the drain
+    // (a tcgen05.ld reaches the 32 TMEM lanes of the warp's quarter, so 128 cells need four warps)
     const int strip_id = 0, hw = warp & 1, par = warp >> 1;
     const int k = hw * 32 + lane;                       // the pixel = K index inside the strip
     const int px_x = lane & 7, px_y = hw * kPatchH + (lane >> 3);
@@ -311,7 +315,7 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
             // ---- A build: the pixel's 36 coefficients into its column of the strip's tile
             mbar_wait(&zero_bar, fills & 1u);
             ++fills;
-            if (live) {
+            if (live && par == 0) {
                 const float bw = axis_base(wo, 3, 1, q.pw, 1, q.sigma) - (float)band_x0;
                 const float bh = axis_base(ho, 3, 1, q.ph, 1, q.sigma) - (float)band_y0;
 #pragma unroll
@@ -326,15 +330,16 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                     if (__float_as_uint(ub) < __float_as_uint((float)(kBandW - 1)) &&
                         __float_as_uint(vb) < __float_as_uint((float)(kBandH - 1))) {
                         const uint32_t cx = (uint32_t)(int)fw, ry = (uint32_t)(int)fh;
-                        const uint32_t low = (ry ^ (uint32_t)par) & 1u;      // 1: this thread's row is the point's lower one
-                        const uint32_t r = ry + low;
-                        const float wr = (low ? lh : 1.f - lh) * m;
-                        const uint32_t e0 = a_thr + (r * kBandW + cx) * 128u + ((kc ^ (cx & 7u)) << 4);
-                        const uint32_t e1 = a_thr + (r * kBandW + cx + 1u) * 128u + ((kc ^ ((cx + 1u) & 7u)) << 4);
+                        const float hm = (1.f - lh) * m, lm = lh * m, hwt = 1.f - lw;
+                        const uint32_t e0 = a_thr + (ry * kBandW + cx) * 128u + ((kc ^ (cx & 7u)) << 4);
+                        const uint32_t e1 = a_thr + (ry * kBandW + cx + 1u) * 128u + ((kc ^ ((cx + 1u) & 7u)) << 4);
                         const float a0 = f32_of((uint16_t)lds16(e0), T()), a1 = f32_of((uint16_t)lds16(e1), T());
-                        sts16(e0, bits16(a0 + wr * (1.f - lw), T()));
-                        sts16(e1, bits16(a1 + wr * lw, T()));
-                    } else if (par == 0) {
+                        const float a2 = f32_of((uint16_t)lds16(e0 + kBandW * 128), T()), a3 = f32_of((uint16_t)lds16(e1 + kBandW * 128), T());
+                        sts16(e0, bits16(a0 + hm * hwt, T()));
+                        sts16(e1, bits16(a1 + hm * lw, T()));
+                        sts16(e0 + kBandW * 128, bits16(a2 + lm * hwt, T()));
+                        sts16(e1 + kBandW * 128, bits16(a3 + lm * lw, T()));
+                    } else {
                         // beyond the band: the reference's range test decides whether the point counts at all
                         const float lw_abs = ub + (float)band_x0, lh_abs = vb + (float)band_y0;
                         if (lh_abs > -1.f && lw_abs > -1.f && lh_abs < (float)q.H && lw_abs < (float)q.W) {
