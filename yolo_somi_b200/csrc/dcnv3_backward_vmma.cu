@@ -291,9 +291,9 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                 if (in_item) request(stage ^ 1u, n, g, wo0, hb + kRows);
                 else if (has_next) request(stage ^ 1u, n2, g2, wo2, ho2);
             }
-            uint32_t off[kP], mw[5];
+            uint32_t off[kP] = {}, mw[5] = {};
             const uint32_t sa = st_thr + stage * kStBytes;
-            {
+            if (par == 0) {   // builders only
                 const uint4 o0 = lds128(sa + kStOff + k * kOffRow), o1 = lds128(sa + kStOff + k * kOffRow + 16),
                             o2 = lds128(sa + kStOff + k * kOffRow + 32);
                 const uint32_t w[12] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w, o2.x, o2.y, o2.z, o2.w};
