@@ -406,6 +406,33 @@ def test_layer_bf16_autocast_runs_and_is_close():
     assert float((y.float() - ref).abs().max()) <= 0.08 * float(ref.abs().max())
 
 
+# ----------------------------------------------------------------------------- stream capture
+def test_forward_backward_under_cuda_graph_capture():
+    """The default 16-bit backward forks a side stream inside the call (the fp32 plane's memset runs beside
+    the channel-sum kernel) and joins it with events: that must be legal under stream capture, and a replayed
+    graph must give the eager results (out / grad_offset / grad_mask bit-identical, grad_value to its
+    accumulation-order noise).  Static-shape training loops capture exactly this."""
+    import DCNv3
+    c = cases.Case("graph", N=3, H=26, W=35, G=8, gc=16, seed=411)
+    v, o, m, g = (torch.as_tensor(a).to(device="cuda", dtype=torch.bfloat16) for a in cases.make_inputs(c))
+    want_out = DCNv3.dcnv3_forward(v, o, m, *c.geom, 256)
+    want = [want_out] + DCNv3.dcnv3_backward(v, o, m, *c.geom, g, 256)     # (also warms every lazy init up)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = DCNv3.dcnv3_forward(v, o, m, *c.geom, 256)
+        grads = DCNv3.dcnv3_backward(v, o, m, *c.geom, g, 256)
+    for _ in range(2):
+        for t in [out] + list(grads):
+            t.fill_(7.0)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, want[0])
+        assert torch.equal(grads[1], want[2]) and torch.equal(grads[2], want[3])
+        a, w = grads[0].double().cpu().numpy(), want[1].double().cpu().numpy()
+        assert max_abs(a, w) <= 2e-2 * float(np.sqrt(np.mean(w ** 2)))
+
+
 # ----------------------------------------------------------------------------- host-buffer pipeline
 @pytest.mark.parametrize("dt", ["bf16", "f32"])
 def test_host_pipeline_matches_device_path(dt):

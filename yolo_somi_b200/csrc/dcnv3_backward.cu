@@ -94,8 +94,10 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 narrow_f32_kernel(const float *__restrict__ src, T *__restrict__ dst, size_t n) {
     // 8 elements per thread per step: two 128-bit loads, one 128-bit store (src/dst 16-byte aligned)
+    // back to front: the accumulating kernels work image-major, so the END of the plane is what is still in L2
     const size_t n8 = n / 8;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n8; j += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = n8 - 1 - j;
         const float4 a = __ldcs(reinterpret_cast<const float4 *>(src) + 2 * i);
         const float4 b = __ldcs(reinterpret_cast<const float4 *>(src) + 2 * i + 1);
         if constexpr (sizeof(T) == 2) {
