@@ -123,6 +123,11 @@ _TILE_CASES = [
     # the group-slice forward needs a multiple of 8 groups: partial tiles, two group blocks
     cases.Case("gs_g16_partial", N=2, H=27, W=21, G=16, gc=16, seed=209),
     cases.Case("gs_g8_pad0", N=1, H=19, W=34, G=8, gc=16, ph=0, pw=0, sigma=0.8, seed=210),
+    # group_channels == 32 in the group-slice / split kernels: a group is two 16-channel slices (72-byte mask
+    # runs: boxes that start below the run, plain stores of grad_mask), N = 32 in the tcgen05 product
+    cases.Case("gs_g8_gc32", N=2, H=27, W=21, G=8, gc=32, seed=211),
+    cases.Case("gs_g16_gc32_pad0", N=1, H=19, W=34, G=16, gc=32, ph=0, pw=0, sigma=0.8, seed=212),
+    cases.Case("gs_g4_gc32_fwd_only", N=1, H=18, W=20, G=4, gc=32, seed=213),
 ]
 
 

@@ -39,8 +39,12 @@ constexpr int kSmemBytes = kWinBytes + kOffBytes + kMskBytes;
 struct Params {
     int ox_rel, oy_rel;      // window origin relative to the tile origin
     int tiles_x;
-    int gblocks;             // G / 8
+    int gblocks;             // 16-channel slices / 8
     int n0;
+    // group_channels == 32: a group is TWO 16-channel slices (lanes 2j, 2j+1 share the group's offsets / masks
+    // and add their partial channel sums); a CTA's 8 slices are then 4 groups
+    int gsh;                 // log2(slices per group): 0 or 1
+    int o_pitch, m_pitch;    // staged offset / mask bytes per pixel
 };
 
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
@@ -75,7 +79,8 @@ __global__ void __launch_bounds__(kThreads, 2)
 bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
          const __grid_constant__ CUtensorMap tmap_m, const __grid_constant__ CUtensorMap tmap_go,
          const __grid_constant__ CUtensorMap tmap_gm, const T *__restrict__ value, const T *__restrict__ offset,
-         const T *__restrict__ mask, const T *__restrict__ grad_out, const Geom q, const Params tp) {
+         const T *__restrict__ mask, const T *__restrict__ grad_out, T *__restrict__ grad_mask_out, const Geom q,
+         const Params tp) {
     constexpr int E = 8;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -87,7 +92,12 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
     const int tid = threadIdx.x;
     const int g = tid & 7, pix = tid >> 3, px = pix & 7, py = pix >> 3;
     const int tile_x = blockIdx.x % tp.tiles_x, tile_y = blockIdx.x / tp.tiles_x;
-    const int g0 = blockIdx.y * kGroups;
+    const int g0 = blockIdx.y * kGroups;                       // first 16-channel slice of the CTA
+    const int gr = g >> tp.gsh;                                // this lane's group inside the CTA's block
+    const int G0 = blockIdx.y * (kGroups >> tp.gsh);           // first group of the CTA
+    // the mask box starts on the 16-byte boundary below the block's run (72-byte runs when gc == 32)
+    const int m_shift = (G0 * kP * 2) & 15;
+    const int C = q.G * q.gc;
     const int n = tp.n0 + blockIdx.z;
     const int wo0 = tile_x * kTile, ho0 = tile_y * kTile;
     const int ox = wo0 + tp.ox_rel, oy = ho0 + tp.oy_rel;
@@ -98,9 +108,9 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
     }
     __syncthreads();
     if (tid == 0) {
-        mbar_expect_tx(&bar, kSmemBytes);
-        tma_load_4d(off_tile, &tmap_o, &bar, g0 * kP * 2, wo0, ho0, n);
-        tma_load_4d(msk_tile, &tmap_m, &bar, g0 * kP, wo0, ho0, n);
+        mbar_expect_tx(&bar, kWinBytes + kPix * (tp.o_pitch + tp.m_pitch));
+        tma_load_4d(off_tile, &tmap_o, &bar, G0 * kP * 2, wo0, ho0, n);
+        tma_load_4d(msk_tile, &tmap_m, &bar, (G0 * kP * 2 - m_shift) >> 1, wo0, ho0, n);
         tma_load_4d(win, &tmap_v, &bar, g0 * kCh, ox, oy, n);
     }
 
@@ -111,14 +121,14 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
     const float base_h = axis_base(ho, 3, 1, q.ph, 1, q.sigma);
     const float bw = base_w - (float)ox, bh = base_h - (float)oy;     // window-relative anchors
     const uint32_t win_addr = smem_u32(win) + g * 32 + half * 16;
-    const uint32_t my_off = s_off + (pix * kGroups + g) * (kP * 4);
-    const uint32_t my_msk = s_msk + (pix * kGroups + g) * (kP * 2);
+    const uint32_t my_off = s_off + pix * tp.o_pitch + gr * (kP * 4);
+    const uint32_t my_msk = s_msk + pix * tp.m_pitch + m_shift + gr * (kP * 2);
 
     // upstream gradient of this (pixel, group): chunk `half` and the other chunk (a warp reads four
     // runs of 256 contiguous bytes)
     uint4 gq_a = make_uint4(0u, 0u, 0u, 0u), gq_b = gq_a;
     if (live) {
-        const T *gp = grad_out + ((((size_t)n * q.Ho + ho) * q.Wo + wo) * q.G + (g0 + g)) * kCh;
+        const T *gp = grad_out + (((size_t)n * q.Ho + ho) * q.Wo + wo) * (size_t)C + (g0 + g) * kCh;
         gq_a = __ldg(reinterpret_cast<const uint4 *>(gp + half * E));
         gq_b = __ldg(reinterpret_cast<const uint4 *>(gp + (half ^ 1) * E));
     }
@@ -155,6 +165,11 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
                 const uint4 qa = lds128(tl + o[t]), qb = lds128((tl ^ 16u) + o[t]);
                 dr[t] = dot<T>(gq_a, qa, 0.f) + dot<T>(gq_b, qb, 0.f);
             }
+            if (tp.gsh) {   // the group's other 16 channels are the neighbouring lane's
+                const unsigned am = __activemask();
+#pragma unroll
+                for (int t = 0; t < 4; ++t) dr[t] += __shfl_xor_sync(am, dr[t], 1);
+            }
             const float gm = hh * (hw * dr[0] + lw * dr[1]) + lh * (hw * dr[2] + lw * dr[3]);
             const float gx = m * (hh * (dr[1] - dr[0]) + lh * (dr[3] - dr[2]));
             const float gy = m * (hw * (dr[2] - dr[0]) + lw * (dr[3] - dr[1]));
@@ -165,13 +180,13 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
 
         if (miss) {
             // ---- points whose corner block leaves the window: clamped global reads
-            const int C = q.G * q.gc, row_stride = q.W * C;
+            const int row_stride = q.W * C;
             const T *img = value + (size_t)n * q.H * row_stride + (g0 + g) * kCh;
             // (the staged inputs of a missed point were overwritten above: re-read them from the tensors)
             for (int p = 0; p < kP; ++p) {
                 if (!((miss >> p) & 1u)) continue;
                 const int i = p / 3, jj = p % 3;
-                const size_t e0 = ((((size_t)n * q.Ho + ho) * q.Wo + wo) * q.G + (g0 + g)) * kP + p;
+                const size_t e0 = ((((size_t)n * q.Ho + ho) * q.Wo + wo) * q.G + (G0 + gr)) * kP + p;
                 const float2 d = load_pair(offset + e0 * 2);
                 const float m = to_f32(__ldg(mask + e0));
                 const float loc_w = base_w + ((float)i + d.x) * q.sigma;
@@ -190,6 +205,11 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
                         const uint4 qb = __ldg(reinterpret_cast<const uint4 *>(img + at[t] + eb));
                         dk[t] = dot<T>(gq_a, qa, 0.f) + dot<T>(gq_b, qb, 0.f);
                     }
+                    if (tp.gsh) {   // (both lanes of a group take the same path: same coordinates)
+                        const unsigned am = __activemask();
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) dk[t] += __shfl_xor_sync(am, dk[t], 1);
+                    }
                     const float fy_lo = ct.hh * ct.top, fy_hi = ct.lh * ct.bot;
                     const float fx_lo = ct.hw * ct.lef, fx_hi = ct.lw * ct.rig;
                     gm = fy_lo * (fx_lo * dk[0] + fx_hi * dk[1]) + fy_hi * (fx_lo * dk[2] + fx_hi * dk[3]);
@@ -205,20 +225,34 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
-        tma_store_4d(&tmap_go, off_tile, g0 * kP * 2, wo0, ho0, n);
-        tma_store_4d(&tmap_gm, msk_tile, g0 * kP, wo0, ho0, n);
+        tma_store_4d(&tmap_go, off_tile, G0 * kP * 2, wo0, ho0, n);
+        if (!tp.gsh) tma_store_4d(&tmap_gm, msk_tile, G0 * kP, wo0, ho0, n);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory outlives the reads
     }
+    if (tp.gsh) {
+        // gc == 32: the block's mask run is 72 bytes at a 72-byte pitch -- not a legal TMA box; plain 32-bit stores
+        uint32_t *gmw = reinterpret_cast<uint32_t *>(grad_mask_out);
+        for (int idx = tid; idx < kPix * 18; idx += kThreads) {
+            const int pxl = idx / 18, w = idx - pxl * 18;
+            const int xo = wo0 + (pxl & 7), yo = ho0 + (pxl >> 3);
+            if (xo < q.Wo && yo < q.Ho) {
+                uint32_t vword;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(vword) : "r"(s_msk + pxl * tp.m_pitch + m_shift + w * 4));
+                gmw[(((((size_t)n * q.Ho + yo) * q.Wo + xo) * q.G + G0) * kP) / 2 + w] = vword;
+            }
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory outlives the reads
 }
 
 template <typename T>
 static bool launch_typed(const void *value, const void *offset, const void *mask, const void *grad_out,
                          void *grad_offset, void *grad_mask, const Geom &q, int dtype, cudaStream_t stream,
                          cudaError_t *err) {
-    if (q.gc != kCh || q.G % kGroups != 0 || q.kh != 3 || q.kw != 3 || q.sh != 1 || q.sw != 1 || q.dh != 1 ||
-        q.dw != 1)
+    if (!((q.gc == kCh && q.G % kGroups == 0) || (q.gc == 2 * kCh && q.G % (kGroups / 2) == 0)) || q.kh != 3 ||
+        q.kw != 3 || q.sh != 1 || q.sw != 1 || q.dh != 1 || q.dw != 1)
         return false;
+    const int gsh = q.gc == kCh ? 0 : 1, grp = kGroups >> gsh;     // groups per CTA
     if (((uintptr_t)value | (uintptr_t)grad_out | (uintptr_t)offset | (uintptr_t)mask | (uintptr_t)grad_offset |
          (uintptr_t)grad_mask) % 16)
         return false;
@@ -227,16 +261,19 @@ static bool launch_typed(const void *value, const void *offset, const void *mask
     const int C = q.G * q.gc;
     CUtensorMap tv, to, tm, tgo, tgm;
     if (!make_nhwc_tensor_map(&tv, value, dtype, q.N, q.H, q.W, C, kGroups * kCh, kWin, kWin)) return false;
-    if (!make_rows_tensor_map(&to, offset, dtype, q.N, q.Ho, q.Wo, q.G * kP * 2, kGroups * kP * 2)) return false;
-    if (!make_rows_tensor_map(&tm, mask, dtype, q.N, q.Ho, q.Wo, q.G * kP, kGroups * kP)) return false;
-    if (!make_rows_tensor_map(&tgo, grad_offset, dtype, q.N, q.Ho, q.Wo, q.G * kP * 2, kGroups * kP * 2)) return false;
-    if (!make_rows_tensor_map(&tgm, grad_mask, dtype, q.N, q.Ho, q.Wo, q.G * kP, kGroups * kP)) return false;
     Params tp;
+    tp.gsh = gsh;
+    tp.o_pitch = grp * kP * 4;                                  // 288 / 144 bytes
+    tp.m_pitch = gsh ? 80 : grp * kP * 2;                       // 144 bytes, or the 72-byte run + up to 8 bytes of shift
+    if (!make_rows_tensor_map(&to, offset, dtype, q.N, q.Ho, q.Wo, q.G * kP * 2, tp.o_pitch / 2)) return false;
+    if (!make_rows_tensor_map(&tm, mask, dtype, q.N, q.Ho, q.Wo, q.G * kP, tp.m_pitch / 2)) return false;
+    if (!make_rows_tensor_map(&tgo, grad_offset, dtype, q.N, q.Ho, q.Wo, q.G * kP * 2, tp.o_pitch / 2)) return false;
+    if (!make_rows_tensor_map(&tgm, grad_mask, dtype, q.N, q.Ho, q.Wo, q.G * kP, tp.m_pitch / 2)) return false;
     const float a_w = (float)(1 - q.pw) - q.sigma, a_h = (float)(1 - q.ph) - q.sigma;
     tp.ox_rel = (int)std::floor(a_w + 0.5f * span - 0.5f * (kWin - 2));
     tp.oy_rel = (int)std::floor(a_h + 0.5f * span - 0.5f * (kWin - 2));
     tp.tiles_x = (q.Wo + kTile - 1) / kTile;
-    tp.gblocks = q.G / kGroups;
+    tp.gblocks = q.G / grp;
     const int tiles_y = (q.Ho + kTile - 1) / kTile;
     if (tp.gblocks > 65535) return false;
     cudaFuncSetAttribute(bwd_dots<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
@@ -245,7 +282,7 @@ static bool launch_typed(const void *value, const void *offset, const void *mask
         const dim3 grid((unsigned)(tp.tiles_x * tiles_y), (unsigned)tp.gblocks, (unsigned)std::min(65535, q.N - n0));
         bwd_dots<T><<<grid, kThreads, kSmemBytes, stream>>>(tv, to, tm, tgo, tgm, static_cast<const T *>(value),
                                                             static_cast<const T *>(offset), static_cast<const T *>(mask),
-                                                            static_cast<const T *>(grad_out), q, tp);
+                                                            static_cast<const T *>(grad_out), static_cast<T *>(grad_mask), q, tp);
     }
     *err = cudaGetLastError();
     return true;

@@ -1,4 +1,4 @@
-// dcnv3_backward_vmma.cu -- grad_value of the DCNv3 core backward for 16-bit I/O, group_channels == 16,
+// dcnv3_backward_vmma.cu -- grad_value of the DCNv3 core backward for 16-bit I/O, group_channels 16 or 32,
 // 3x3 / stride 1 / dilation 1, as a tcgen05 product with the accumulators in TENSOR MEMORY.
 // Second half of the split backward (grad_offset / grad_mask: dcnv3_backward_dots.cu).
 //
@@ -61,11 +61,10 @@ constexpr int kBlockBytes = kATileBytes / 2;       // 128 cells (one UMMA M bloc
 // staging of one step's inputs, filled by TMA (three boxes per strip: 8 x 8 pixels x this group's run)
 constexpr int kOffRow = 48, kMskRow = 32;          // bytes per pixel: 36 / 18 used, padded to 16-byte multiples
 constexpr int kStOff = 0, kStMsk = 64 * kOffRow, kStGout = kStMsk + 64 * kMskRow;
-constexpr int kStStrip = kStGout + 64 * kSliceBytes;                 // 7168 per strip
-constexpr int kStBytes = kStrips * kStStrip;                         // 14336 per stage
+// grad_out of the patch follows: NCH / 8 boxes of [64 px][8 channels] (NCH = channels per group: 16 or 32)
+__host__ __device__ constexpr int st_bytes(int nch) { return kStGout + 64 * nch * 2; }   // 7168 / 9216 per stage
 constexpr int kStages = 2;
-constexpr int kSmemV = 1024 + kStrips * kATileBytes + kStages * kStBytes;
-constexpr int kTmemCols = 32;                      // 2 blocks x 16 fp32 columns
+__host__ __device__ constexpr int smem_bytes(int nch) { return 1024 + kStrips * kATileBytes + kStages * st_bytes(nch); }
 
 // zeros for the bulk re-fill of the A tiles (L2-resident)
 __device__ __align__(128) unsigned char g_zero_tile[kStrips * kATileBytes];
@@ -160,16 +159,20 @@ __device__ __forceinline__ void drain_cells(const float (&r)[16], int lane, floa
         red_add4(po + 8, odd ? make_float4(r[12], r[13], r[14], r[15]) : make_float4(rv[4], rv[5], rv[6], rv[7]));
     }
 }
+template <int NCH>
 __device__ __forceinline__ void drain_block(uint32_t tmem_base, int slot, int warp, int lane, float *gv_img, int y0,
                                             int x0, int H, int W, int row_stride, int C) {
-    float r0[16];
-    VMMA_TMEM_LD_16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(slot * 16), r0);
-    tmem_ld_wait();
     const int y = y0 + 2 * warp + (lane >> 4);
     const int xe = x0 + (lane & 14);            // column of the pair's even cell
     const bool oky = (unsigned)y < (unsigned)H;
     float *p = gv_img + (ptrdiff_t)y * row_stride + (ptrdiff_t)xe * C;
-    drain_cells(r0, lane, p, oky && (unsigned)xe < (unsigned)W, oky && (unsigned)(xe + 1) < (unsigned)W, C);
+#pragma unroll
+    for (int h = 0; h < NCH / 16; ++h) {
+        float r0[16];
+        VMMA_TMEM_LD_16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(slot * NCH + h * 16), r0);
+        tmem_ld_wait();
+        drain_cells(r0, lane, p + h * 16, oky && (unsigned)xe < (unsigned)W, oky && (unsigned)(xe + 1) < (unsigned)W, C);
+    }
 }
 
 // 4-D tensor map over a [N, Ho, Wo, row_elems] tensor of 16-bit elements, box (box_elems, 8, 8, 1).  The box
@@ -190,7 +193,7 @@ static bool make_run_tensor_map(CUtensorMap *map, const void *base, int dtype, i
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename T>
+template <typename T, int NCH>
 __global__ void __launch_bounds__(kThreadsV, kCtasPerSm)
 bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ CUtensorMap tmap_msk,
          const __grid_constant__ CUtensorMap tmap_gout, float *__restrict__ gv_acc, const Geom q, const VParams pp) {
@@ -208,6 +211,7 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
     unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t a_addr0 = smem_u32(base);                                   // A tiles: [strip][256 rows][128 B]
     unsigned char *stages = base + kStrips * kATileBytes;                      // [stage][strip][off | msk | gout]
+    constexpr int kStBytes = st_bytes(NCH), kStStrip = kStBytes, kTmemCols = 2 * NCH;   // (one strip per CTA)
     const uint32_t st_thr = smem_u32(stages) + strip_id * kStStrip;            // + stage * kStBytes
     const uint32_t a_strip = a_addr0 + strip_id * kATileBytes;
     const uint32_t kc = (uint32_t)k >> 3, kl = ((uint32_t)k & 7u) * 2u;
@@ -235,8 +239,9 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
             tma_load_4d(dst + st * kStStrip + kStOff, &tmap_off, bar, (gg * kP * 4 & ~15) >> 1, w0 + st * kStripW, h0, nn);
             tma_load_4d(dst + st * kStStrip + kStMsk, &tmap_msk, bar, (gg * kP * 2 & ~15) >> 1, w0 + st * kStripW, h0, nn);
             // grad_out as two boxes of 8 channels: [half][64 px][16 B] is the MMA's B operand as it lands (MN-major)
-            tma_load_4d(dst + st * kStStrip + kStGout, &tmap_gout, bar, gg * kCh, w0 + st * kStripW, h0, nn);
-            tma_load_4d(dst + st * kStStrip + kStGout + 1024, &tmap_gout, bar, gg * kCh + 8, w0 + st * kStripW, h0, nn);
+#pragma unroll
+            for (int c8 = 0; c8 < NCH / 8; ++c8)
+                tma_load_4d(dst + st * kStStrip + kStGout + c8 * 1024, &tmap_gout, bar, gg * NCH + c8 * 8, w0 + st * kStripW, h0, nn);
         }
     };
 
@@ -262,7 +267,7 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
         mbar_expect_tx(&zero_bar, kStrips * kATileBytes);
         bulk_fill(a_addr0, g_zero_tile, kStrips * kATileBytes, &zero_bar);
     }
-    const uint32_t idesc = umma_idesc(std::is_same<T, __nv_bfloat16>::value ? 1 : 0, 128, 16);
+    const uint32_t idesc = umma_idesc(std::is_same<T, __nv_bfloat16>::value ? 1 : 0, 128, NCH);
 
     if (tid == 0) request(0, n, g, wo0, ho0);
 
@@ -344,8 +349,11 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                         const float lw_abs = ub + (float)band_x0, lh_abs = vb + (float)band_y0;
                         if (lh_abs > -1.f && lw_abs > -1.f && lh_abs < (float)q.H && lw_abs < (float)q.W) {
                             const float hm = (1.f - lh) * m, lm = lh * m, hwt = 1.f - lw;
-                            far_point<T>(gv_img, q.H, q.W, row_stride, C, (int)fh + band_y0, (int)fw + band_x0, hm * hwt, hm * lw,
-                                         lm * hwt, lm * lw, lds128(sa + kStGout + k * 16), lds128(sa + kStGout + 1024 + k * 16));
+#pragma unroll 1
+                            for (int h = 0; h < NCH / 16; ++h)
+                                far_point<T>(gv_img + h * 16, q.H, q.W, row_stride, C, (int)fh + band_y0, (int)fw + band_x0,
+                                             hm * hwt, hm * lw, lm * hwt, lm * lw, lds128(sa + kStGout + (2 * h) * 1024 + k * 16),
+                                             lds128(sa + kStGout + (2 * h + 1) * 1024 + k * 16));
                         }
                     }
                 }
@@ -361,7 +369,7 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                 for (int st = 0; st < kStrips; ++st)
 #pragma unroll
                     for (int blk = 0; blk < 2; ++blk) {
-                        const uint32_t d = tmem_base + (uint32_t)((st * 2 + ((s + blk) & 1)) * 16);
+                        const uint32_t d = tmem_base + (uint32_t)((st * 2 + ((s + blk) & 1)) * NCH);
                         const uint32_t aa = a_addr0 + st * kATileBytes + blk * kBlockBytes;
                         const uint32_t bb = smem_u32(stages) + stage * kStBytes + st * kStStrip + kStGout;
 #pragma unroll
@@ -380,10 +388,10 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                 bulk_fill(a_addr0, g_zero_tile, kStrips * kATileBytes, &zero_bar);
             }
             // ---- the band's upper block is final: reductions
-            drain_block(tmem_base, s & 1, warp, lane, gv_img, band_y0, wo0 + pp.bx_rel, q.H, q.W, row_stride, C);
+            drain_block<NCH>(tmem_base, s & 1, warp, lane, gv_img, band_y0, wo0 + pp.bx_rel, q.H, q.W, row_stride, C);
         }
         // ---- the last step's lower block
-        drain_block(tmem_base, pp.steps & 1, warp, lane, gv_img, ho0 + (pp.steps - 1) * kRows + pp.by_rel + 8,
+        drain_block<NCH>(tmem_base, pp.steps & 1, warp, lane, gv_img, ho0 + (pp.steps - 1) * kRows + pp.by_rel + 8,
                     wo0 + pp.bx_rel, q.H, q.W, row_stride, C);
         if (!has_next) break;
         n = n2; g = g2; wo0 = wo2; ho0 = ho2;
@@ -420,7 +428,7 @@ static bool launch_typed(const void *offset, const void *mask, const void *grad_
     const int dtype = std::is_same<T, __half>::value ? 1 : 2;
     if (!make_run_tensor_map(&to, offset, dtype, q.N, q.Ho, q.Wo, q.G * kP * 2, kOffRow / 2)) return false;
     if (!make_run_tensor_map(&tm, mask, dtype, q.N, q.Ho, q.Wo, q.G * kP, kMskRow / 2)) return false;
-    if (!make_run_tensor_map(&tg, grad_out, dtype, q.N, q.Ho, q.Wo, q.G * kCh, 8)) return false;
+    if (!make_run_tensor_map(&tg, grad_out, dtype, q.N, q.Ho, q.Wo, q.G * q.gc, 8)) return false;
     static int num_sms = 0;
     if (num_sms == 0) {
         int dev = 0;
@@ -428,8 +436,13 @@ static bool launch_typed(const void *offset, const void *mask, const void *grad_
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const int ctas = (int)std::min<long long>(total, (long long)kCtasPerSm * num_sms);
-    cudaFuncSetAttribute(bwd_vmma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemV);
-    bwd_vmma<T><<<ctas, kThreadsV, kSmemV, stream>>>(to, tm, tg, gv_acc, q, pp);
+    if (q.gc == 16) {
+        cudaFuncSetAttribute(bwd_vmma<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(16));
+        bwd_vmma<T, 16><<<ctas, kThreadsV, smem_bytes(16), stream>>>(to, tm, tg, gv_acc, q, pp);
+    } else {
+        cudaFuncSetAttribute(bwd_vmma<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(32));
+        bwd_vmma<T, 32><<<ctas, kThreadsV, smem_bytes(32), stream>>>(to, tm, tg, gv_acc, q, pp);
+    }
     *err = cudaGetLastError();
     return true;
 }
@@ -438,7 +451,7 @@ static bool launch_typed(const void *offset, const void *mask, const void *grad_
 
 bool backward_vmma_eligible(const void *offset, const void *mask, const void *grad_out, const float *gv_acc, const Geom &q) {
     using namespace strip;
-    if (q.gc != kCh || q.kh != 3 || q.kw != 3 || q.sh != 1 || q.sw != 1 || q.dh != 1 || q.dw != 1) return false;
+    if ((q.gc != 16 && q.gc != 32) || q.kh != 3 || q.kw != 3 || q.sh != 1 || q.sw != 1 || q.dh != 1 || q.dw != 1) return false;
     if (!(q.sigma >= 0.5f && q.sigma <= 1.25f)) return false;   // band = taps +- 3 px
     // TMA staging: 16-byte aligned bases and row strides (G * 18 B for the masks: G % 8 == 0)
     if (((uintptr_t)grad_out | (uintptr_t)gv_acc | (uintptr_t)offset | (uintptr_t)mask) % 16 || q.G % 8) return false;

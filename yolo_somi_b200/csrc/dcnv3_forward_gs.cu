@@ -53,8 +53,12 @@ constexpr int kSmemBytes = kWinBytes + kOffBytes + kMskBytes;
 struct Params {
     int ox_rel, oy_rel;      // window origin relative to the tile origin
     int tiles_x;
-    int gblocks;             // G / 8
+    int gblocks;             // 16-channel slices / 8
     int n0;
+    // group_channels == 32: a group is TWO 16-channel slices (lanes 2j, 2j+1 share the group's offsets / masks);
+    // a CTA's 8 slices are then 4 groups
+    int gsh;                 // log2(slices per group): 0 or 1
+    int o_pitch, m_pitch;    // staged offset / mask bytes per pixel
 };
 
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
@@ -95,7 +99,11 @@ fwd_gs(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUten
     const int tid = threadIdx.x;
     const int g = tid & 7, pix = tid >> 3, px = pix & 7, py = pix >> 3;
     const int tile_x = blockIdx.x % tp.tiles_x, tile_y = blockIdx.x / tp.tiles_x;
-    const int g0 = blockIdx.y * kGroups;
+    const int g0 = blockIdx.y * kGroups;                       // first 16-channel slice of the CTA
+    const int gr = g >> tp.gsh;                                // this lane's group inside the CTA's block
+    const int G0 = blockIdx.y * (kGroups >> tp.gsh);           // first group of the CTA
+    // the mask box starts on the 16-byte boundary below the block's run (72-byte runs when gc == 32)
+    const int m_shift = (G0 * kP * 2) & 15;
     const int n = tp.n0 + blockIdx.z;
     const int wo0 = tile_x * kTile, ho0 = tile_y * kTile;
     const int ox = wo0 + tp.ox_rel, oy = ho0 + tp.oy_rel;
@@ -106,9 +114,9 @@ fwd_gs(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUten
     }
     __syncthreads();
     if (tid == 0) {
-        mbar_expect_tx(&bar, kSmemBytes);
-        tma_load_4d(smem + kWinBytes, &tmap_o, &bar, g0 * kP * 2, wo0, ho0, n);
-        tma_load_4d(smem + kWinBytes + kOffBytes, &tmap_m, &bar, g0 * kP, wo0, ho0, n);
+        mbar_expect_tx(&bar, kWinBytes + kPix * (tp.o_pitch + tp.m_pitch));
+        tma_load_4d(smem + kWinBytes, &tmap_o, &bar, G0 * kP * 2, wo0, ho0, n);
+        tma_load_4d(smem + kWinBytes + kOffBytes, &tmap_m, &bar, (G0 * kP * 2 - m_shift) >> 1, wo0, ho0, n);
         tma_load_4d(win, &tmap_v, &bar, g0 * kCh, ox, oy, n);
     }
 
@@ -119,8 +127,8 @@ fwd_gs(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUten
     const float base_h = axis_base(ho, 3, 1, q.ph, 1, q.sigma);
     const float bw = base_w - (float)ox, bh = base_h - (float)oy;     // window-relative anchors
     const uint32_t win_addr = smem_u32(win) + g * 32 + half * 16;
-    const uint32_t my_off = s_off + (pix * kGroups + g) * (kP * 4);
-    const uint32_t my_msk = s_msk + (pix * kGroups + g) * (kP * 2);
+    const uint32_t my_off = s_off + pix * tp.o_pitch + gr * (kP * 4);
+    const uint32_t my_msk = s_msk + pix * tp.m_pitch + m_shift + gr * (kP * 2);
 
     float acc_a[E], acc_b[E];   // acc_a: channels of chunk `half`, acc_b: the other chunk
 #pragma unroll
@@ -167,7 +175,7 @@ fwd_gs(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUten
         // ---- points whose corner block leaves the window: clamped global reads
         const int C = q.G * q.gc, row_stride = q.W * C;
         const T *img = value + (size_t)n * q.H * row_stride + (g0 + g) * kCh;
-        const size_t e0 = ((((size_t)n * q.Ho + ho) * q.Wo + wo) * q.G + (g0 + g)) * kP;
+        const size_t e0 = ((((size_t)n * q.Ho + ho) * q.Wo + wo) * q.G + (G0 + gr)) * kP;
         for (int p = 0; p < kP; ++p) {
             if (!((miss >> p) & 1u)) continue;
             const int i = p / 3, jj = p % 3;
@@ -195,7 +203,7 @@ fwd_gs(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUten
         }
     }
 
-    T *dst = out + ((((size_t)n * q.Ho + ho) * q.Wo + wo) * q.G + (g0 + g)) * kCh;
+    T *dst = out + (((size_t)n * q.Ho + ho) * q.Wo + wo) * (size_t)(q.G * q.gc) + (g0 + g) * kCh;
     *reinterpret_cast<uint4 *>(dst + half * E) = pack<T>(acc_a);
     *reinterpret_cast<uint4 *>(dst + (half ^ 1) * E) = pack<T>(acc_b);
 }
@@ -203,24 +211,28 @@ fwd_gs(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUten
 template <typename T>
 static bool launch_typed(const void *value, const void *offset, const void *mask, void *out, const Geom &q,
                          int dtype, bool fast, cudaStream_t stream, cudaError_t *err) {
-    if (q.gc != kCh || q.G % kGroups != 0 || q.kh != 3 || q.kw != 3 || q.sh != 1 || q.sw != 1 || q.dh != 1 ||
-        q.dw != 1)
+    if (!((q.gc == kCh && q.G % kGroups == 0) || (q.gc == 2 * kCh && q.G % (kGroups / 2) == 0)) || q.kh != 3 ||
+        q.kw != 3 || q.sh != 1 || q.sw != 1 || q.dh != 1 || q.dw != 1)
         return false;
     if (((uintptr_t)value | (uintptr_t)out | (uintptr_t)offset | (uintptr_t)mask) % 16) return false;
+    const int gsh = q.gc == kCh ? 0 : 1, grp = kGroups >> gsh;     // groups per CTA
     // the tile's nominal tap span must leave at least 2 pixels of offset slack on each side
     const float span = (kTile - 1) + 2 * q.sigma;
     if (!(q.sigma > 0.f) || span + 4 > kWin - 2) return false;
     const int C = q.G * q.gc;
     CUtensorMap tmap_v, tmap_o, tmap_m;
     if (!make_nhwc_tensor_map(&tmap_v, value, dtype, q.N, q.H, q.W, C, kGroups * kCh, kWin, kWin)) return false;
-    if (!make_rows_tensor_map(&tmap_o, offset, dtype, q.N, q.Ho, q.Wo, q.G * kP * 2, kGroups * kP * 2)) return false;
-    if (!make_rows_tensor_map(&tmap_m, mask, dtype, q.N, q.Ho, q.Wo, q.G * kP, kGroups * kP)) return false;
     Params tp;
+    tp.gsh = gsh;
+    tp.o_pitch = grp * kP * 4;                                  // 288 / 144 bytes
+    tp.m_pitch = gsh ? 80 : grp * kP * 2;                       // 144 bytes, or the 72-byte run + up to 8 bytes of shift
+    if (!make_rows_tensor_map(&tmap_o, offset, dtype, q.N, q.Ho, q.Wo, q.G * kP * 2, tp.o_pitch / 2)) return false;
+    if (!make_rows_tensor_map(&tmap_m, mask, dtype, q.N, q.Ho, q.Wo, q.G * kP, tp.m_pitch / 2)) return false;
     const float a_w = (float)(1 - q.pw) - q.sigma, a_h = (float)(1 - q.ph) - q.sigma;
     tp.ox_rel = (int)std::floor(a_w + 0.5f * span - 0.5f * (kWin - 2));
     tp.oy_rel = (int)std::floor(a_h + 0.5f * span - 0.5f * (kWin - 2));
     tp.tiles_x = (q.Wo + kTile - 1) / kTile;
-    tp.gblocks = q.G / kGroups;
+    tp.gblocks = q.G / grp;
     const int tiles_y = (q.Ho + kTile - 1) / kTile;
     if (tp.gblocks > 65535) return false;
     const T *v = static_cast<const T *>(value), *o = static_cast<const T *>(offset), *m = static_cast<const T *>(mask);
