@@ -411,6 +411,45 @@ def test_layer_bf16_autocast_runs_and_is_close():
     assert float((y.float() - ref).abs().max()) <= 0.08 * float(ref.abs().max())
 
 
+# ----------------------------------------------------------------------------- guard bands
+@pytest.mark.parametrize("shape", [(2, 27, 21, 16, 16), (1, 19, 34, 8, 32), (2, 30, 41, 3, 16)],
+                         ids=["split_g16", "split_g8_gc32", "strip_g3"])
+def test_outputs_and_workspace_stay_inside_their_buffers(shape):
+    """Through the C ABI with every output and the workspace embedded in a larger sentinel-filled allocation
+    (the sanitizer is not available on the GPU pool): reductions, TMA stores and bulk copies of the default
+    16-bit kernels must not touch a byte outside [ptr, ptr + size) -- ragged tiles, bands that hang over the
+    map's edge and far offsets included."""
+    from yolo_somi_b200 import _native
+    lib = _native.load()
+    N, H, W, G, gc = shape
+    c = cases.Case("guard", N=N, H=H, W=W, G=G, gc=gc, seed=77)
+    v, o, m, g = (torch.as_tensor(a).to(device="cuda", dtype=torch.bfloat16).contiguous() for a in cases.make_inputs(c))
+    o = (o.float() * 2.5).to(torch.bfloat16)            # a good share of the points leaves the band / the window
+    geom = (N, H, W, H, W, G, gc, 3, 3, 1, 1, 1, 1, 1, 1)
+    pad = 4096                                           # bytes of sentinel on either side (keeps 16-byte alignment)
+    def guarded(nbytes):
+        buf = torch.full((nbytes + 2 * pad,), 0x5A, dtype=torch.uint8, device="cuda")
+        return buf, buf.data_ptr() + pad
+    sizes = {"out": v.numel() * 2, "gv": v.numel() * 2, "go": o.numel() * 2, "gm": m.numel() * 2,
+             "ws": lib.dcnv3_backward_workspace_bytes(N, H, W, G, gc, 2, 0)}
+    bufs = {k: guarded(n) for k, n in sizes.items()}
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):
+        rc = lib.dcnv3_forward_sm100(v.data_ptr(), o.data_ptr(), m.data_ptr(), bufs["out"][1], *geom, 1.0, 2, stream)
+        assert rc == 0
+        rc = lib.dcnv3_backward_sm100(v.data_ptr(), o.data_ptr(), m.data_ptr(), g.data_ptr(), bufs["gv"][1], bufs["go"][1],
+                                      bufs["gm"][1], bufs["ws"][1], sizes["ws"], *geom, 1.0, 2, 0, stream)
+        assert rc == 0
+    torch.cuda.synchronize()
+    for k, (buf, _) in bufs.items():
+        assert bool((buf[:pad] == 0x5A).all()) and bool((buf[pad + sizes[k]:] == 0x5A).all()), k
+    # and the results are the shim's (same kernels, same inputs)
+    import DCNv3
+    want = DCNv3.dcnv3_forward(v, o, m, 3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0, 256)
+    got = bufs["out"][0][pad:pad + sizes["out"]].view(torch.bfloat16).view_as(want)
+    assert torch.equal(got, want)
+
+
 # ----------------------------------------------------------------------------- stream capture
 def test_forward_backward_under_cuda_graph_capture():
     """The default 16-bit backward forks a side stream inside the call (the fp32 plane's memset runs beside
