@@ -1,5 +1,8 @@
-// dcnv3_backward_dots.cu -- first half of the split DCNv3 backward for 16-bit I/O, group_channels == 16,
-// 3x3 / stride 1 / dilation 1, G % 8 == 0: grad_offset and grad_mask (the per-point channel sums
+// dcnv3_backward_dots.cu -- first half of the split DCNv3 backward for 16-bit I/O, group_channels == 16
+// (G % 8 == 0) or 32 (G % 4 == 0: a group is two 16-channel slices, template parameter GSH = 1 -- the two lanes
+// of a group share its offsets / masks and add their partial sums with one shuffle; the 72-byte mask runs are
+// not legal TMA boxes, so the mask box starts on the 16-byte boundary below the run and grad_mask leaves by
+// plain 32-bit stores), 3x3 / stride 1 / dilation 1: grad_offset and grad_mask (the per-point channel sums
 // of dcnv3_im2col_cuda.cuh:106-146, 278-370) with the forward's group-slice layout.
 //
 // Why split (profiles/README.md, r1_v4): the fused strip backward holds a 12 KB coefficient tile
@@ -74,7 +77,7 @@ static bool make_rows_tensor_map(CUtensorMap *map, const void *base, int dtype, 
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename T>
+template <typename T, int GSH>
 __global__ void __launch_bounds__(kThreads, 2)
 bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
          const __grid_constant__ CUtensorMap tmap_m, const __grid_constant__ CUtensorMap tmap_go,
@@ -93,10 +96,11 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
     const int g = tid & 7, pix = tid >> 3, px = pix & 7, py = pix >> 3;
     const int tile_x = blockIdx.x % tp.tiles_x, tile_y = blockIdx.x / tp.tiles_x;
     const int g0 = blockIdx.y * kGroups;                       // first 16-channel slice of the CTA
-    const int gr = g >> tp.gsh;                                // this lane's group inside the CTA's block
-    const int G0 = blockIdx.y * (kGroups >> tp.gsh);           // first group of the CTA
+    constexpr int kOPitch = (kGroups >> GSH) * kP * 4, kMPitch = GSH ? 80 : (kGroups >> GSH) * kP * 2;
+    const int gr = g >> GSH;                                   // this lane's group inside the CTA's block
+    const int G0 = blockIdx.y * (kGroups >> GSH);              // first group of the CTA
     // the mask box starts on the 16-byte boundary below the block's run (72-byte runs when gc == 32)
-    const int m_shift = (G0 * kP * 2) & 15;
+    const int m_shift = GSH ? (G0 * kP * 2) & 15 : 0;
     const int C = q.G * q.gc;
     const int n = tp.n0 + blockIdx.z;
     const int wo0 = tile_x * kTile, ho0 = tile_y * kTile;
@@ -108,7 +112,7 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
     }
     __syncthreads();
     if (tid == 0) {
-        mbar_expect_tx(&bar, kWinBytes + kPix * (tp.o_pitch + tp.m_pitch));
+        mbar_expect_tx(&bar, kWinBytes + kPix * (kOPitch + kMPitch));
         tma_load_4d(off_tile, &tmap_o, &bar, G0 * kP * 2, wo0, ho0, n);
         tma_load_4d(msk_tile, &tmap_m, &bar, (G0 * kP * 2 - m_shift) >> 1, wo0, ho0, n);
         tma_load_4d(win, &tmap_v, &bar, g0 * kCh, ox, oy, n);
@@ -121,8 +125,8 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
     const float base_h = axis_base(ho, 3, 1, q.ph, 1, q.sigma);
     const float bw = base_w - (float)ox, bh = base_h - (float)oy;     // window-relative anchors
     const uint32_t win_addr = smem_u32(win) + g * 32 + half * 16;
-    const uint32_t my_off = s_off + pix * tp.o_pitch + gr * (kP * 4);
-    const uint32_t my_msk = s_msk + pix * tp.m_pitch + m_shift + gr * (kP * 2);
+    const uint32_t my_off = s_off + pix * kOPitch + gr * (kP * 4);
+    const uint32_t my_msk = s_msk + pix * kMPitch + m_shift + gr * (kP * 2);
 
     // upstream gradient of this (pixel, group): chunk `half` and the other chunk (a warp reads four
     // runs of 256 contiguous bytes)
@@ -165,7 +169,7 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
                 const uint4 qa = lds128(tl + o[t]), qb = lds128((tl ^ 16u) + o[t]);
                 dr[t] = dot<T>(gq_a, qa, 0.f) + dot<T>(gq_b, qb, 0.f);
             }
-            if (tp.gsh) {   // the group's other 16 channels are the neighbouring lane's
+            if (GSH) {   // the group's other 16 channels are the neighbouring lane's
                 const unsigned am = __activemask();
 #pragma unroll
                 for (int t = 0; t < 4; ++t) dr[t] += __shfl_xor_sync(am, dr[t], 1);
@@ -205,7 +209,7 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
                         const uint4 qb = __ldg(reinterpret_cast<const uint4 *>(img + at[t] + eb));
                         dk[t] = dot<T>(gq_a, qa, 0.f) + dot<T>(gq_b, qb, 0.f);
                     }
-                    if (tp.gsh) {   // (both lanes of a group take the same path: same coordinates)
+                    if (GSH) {   // (both lanes of a group take the same path: same coordinates)
                         const unsigned am = __activemask();
 #pragma unroll
                         for (int t = 0; t < 4; ++t) dk[t] += __shfl_xor_sync(am, dk[t], 1);
@@ -226,10 +230,10 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
     __syncthreads();
     if (tid == 0) {
         tma_store_4d(&tmap_go, off_tile, G0 * kP * 2, wo0, ho0, n);
-        if (!tp.gsh) tma_store_4d(&tmap_gm, msk_tile, G0 * kP, wo0, ho0, n);
+        if (!GSH) tma_store_4d(&tmap_gm, msk_tile, G0 * kP, wo0, ho0, n);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-    if (tp.gsh) {
+    if (GSH) {
         // gc == 32: the block's mask run is 72 bytes at a 72-byte pitch -- not a legal TMA box; plain 32-bit stores
         uint32_t *gmw = reinterpret_cast<uint32_t *>(grad_mask_out);
         for (int idx = tid; idx < kPix * 18; idx += kThreads) {
@@ -237,7 +241,7 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
             const int xo = wo0 + (pxl & 7), yo = ho0 + (pxl >> 3);
             if (xo < q.Wo && yo < q.Ho) {
                 uint32_t vword;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(vword) : "r"(s_msk + pxl * tp.m_pitch + m_shift + w * 4));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(vword) : "r"(s_msk + pxl * kMPitch + m_shift + w * 4));
                 gmw[(((((size_t)n * q.Ho + yo) * q.Wo + xo) * q.G + G0) * kP) / 2 + w] = vword;
             }
         }
@@ -276,13 +280,14 @@ static bool launch_typed(const void *value, const void *offset, const void *mask
     tp.gblocks = q.G / grp;
     const int tiles_y = (q.Ho + kTile - 1) / kTile;
     if (tp.gblocks > 65535) return false;
-    cudaFuncSetAttribute(bwd_dots<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    auto kern = gsh ? bwd_dots<T, 1> : bwd_dots<T, 0>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     for (int n0 = 0; n0 < q.N; n0 += 65535) {
         tp.n0 = n0;
         const dim3 grid((unsigned)(tp.tiles_x * tiles_y), (unsigned)tp.gblocks, (unsigned)std::min(65535, q.N - n0));
-        bwd_dots<T><<<grid, kThreads, kSmemBytes, stream>>>(tv, to, tm, tgo, tgm, static_cast<const T *>(value),
-                                                            static_cast<const T *>(offset), static_cast<const T *>(mask),
-                                                            static_cast<const T *>(grad_out), static_cast<T *>(grad_mask), q, tp);
+        kern<<<grid, kThreads, kSmemBytes, stream>>>(tv, to, tm, tgo, tgm, static_cast<const T *>(value),
+                                                     static_cast<const T *>(offset), static_cast<const T *>(mask),
+                                                     static_cast<const T *>(grad_out), static_cast<T *>(grad_mask), q, tp);
     }
     *err = cudaGetLastError();
     return true;

@@ -1,5 +1,8 @@
 // dcnv3_forward_gs.cu -- DCNv3 core forward for 16-bit I/O, group_channels == 16, 3x3 / stride 1 /
 // dilation 1, group count a multiple of 8: the "group-slice" kernel (default forward for these).
+// group_channels == 32 (G % 4 == 0) runs the same kernel with a group as TWO 16-channel slices (template
+// parameter GSH = 1): lanes 2j and 2j+1 share the group's offsets / masks; its 72-byte mask runs are not
+// legal TMA boxes, so the mask box starts on the 16-byte boundary below the run (m_shift).
 //
 // Why (profiles/README.md, r1_v3 fwd_tile): the tiled forward was issue-bound at 201 instructions
 // per sampled point, of which only 64 are the FHFMAs and 8 the gather loads; ~40 went into staging
@@ -84,7 +87,7 @@ static bool make_rows_tensor_map(CUtensorMap *map, const void *base, int dtype, 
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename T, bool FAST>
+template <typename T, bool FAST, int GSH>
 __global__ void __launch_bounds__(kThreads, 2)
 fwd_gs(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
        const __grid_constant__ CUtensorMap tmap_m, const T *__restrict__ value, const T *__restrict__ offset,
@@ -100,10 +103,11 @@ fwd_gs(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUten
     const int g = tid & 7, pix = tid >> 3, px = pix & 7, py = pix >> 3;
     const int tile_x = blockIdx.x % tp.tiles_x, tile_y = blockIdx.x / tp.tiles_x;
     const int g0 = blockIdx.y * kGroups;                       // first 16-channel slice of the CTA
-    const int gr = g >> tp.gsh;                                // this lane's group inside the CTA's block
-    const int G0 = blockIdx.y * (kGroups >> tp.gsh);           // first group of the CTA
+    constexpr int kOPitch = (kGroups >> GSH) * kP * 4, kMPitch = GSH ? 80 : (kGroups >> GSH) * kP * 2;
+    const int gr = g >> GSH;                                   // this lane's group inside the CTA's block
+    const int G0 = blockIdx.y * (kGroups >> GSH);              // first group of the CTA
     // the mask box starts on the 16-byte boundary below the block's run (72-byte runs when gc == 32)
-    const int m_shift = (G0 * kP * 2) & 15;
+    const int m_shift = GSH ? (G0 * kP * 2) & 15 : 0;
     const int n = tp.n0 + blockIdx.z;
     const int wo0 = tile_x * kTile, ho0 = tile_y * kTile;
     const int ox = wo0 + tp.ox_rel, oy = ho0 + tp.oy_rel;
@@ -114,7 +118,7 @@ fwd_gs(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUten
     }
     __syncthreads();
     if (tid == 0) {
-        mbar_expect_tx(&bar, kWinBytes + kPix * (tp.o_pitch + tp.m_pitch));
+        mbar_expect_tx(&bar, kWinBytes + kPix * (kOPitch + kMPitch));
         tma_load_4d(smem + kWinBytes, &tmap_o, &bar, G0 * kP * 2, wo0, ho0, n);
         tma_load_4d(smem + kWinBytes + kOffBytes, &tmap_m, &bar, (G0 * kP * 2 - m_shift) >> 1, wo0, ho0, n);
         tma_load_4d(win, &tmap_v, &bar, g0 * kCh, ox, oy, n);
@@ -127,8 +131,8 @@ fwd_gs(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUten
     const float base_h = axis_base(ho, 3, 1, q.ph, 1, q.sigma);
     const float bw = base_w - (float)ox, bh = base_h - (float)oy;     // window-relative anchors
     const uint32_t win_addr = smem_u32(win) + g * 32 + half * 16;
-    const uint32_t my_off = s_off + pix * tp.o_pitch + gr * (kP * 4);
-    const uint32_t my_msk = s_msk + pix * tp.m_pitch + m_shift + gr * (kP * 2);
+    const uint32_t my_off = s_off + pix * kOPitch + gr * (kP * 4);
+    const uint32_t my_msk = s_msk + pix * kMPitch + m_shift + gr * (kP * 2);
 
     float acc_a[E], acc_b[E];   // acc_a: channels of chunk `half`, acc_b: the other chunk
 #pragma unroll
@@ -237,7 +241,7 @@ static bool launch_typed(const void *value, const void *offset, const void *mask
     if (tp.gblocks > 65535) return false;
     const T *v = static_cast<const T *>(value), *o = static_cast<const T *>(offset), *m = static_cast<const T *>(mask);
     T *y = static_cast<T *>(out);
-    auto kern = fast ? fwd_gs<T, true> : fwd_gs<T, false>;
+    auto kern = gsh ? (fast ? fwd_gs<T, true, 1> : fwd_gs<T, false, 1>) : (fast ? fwd_gs<T, true, 0> : fwd_gs<T, false, 0>);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     for (int n0 = 0; n0 < q.N; n0 += 65535) {
         tp.n0 = n0;
