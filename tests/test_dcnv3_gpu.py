@@ -164,6 +164,23 @@ def test_tiled_kernels_vs_oracle(case, spread, bwd, fwd, monkeypatch):
         assert max_abs(a, w) <= 5e-2 * max(rms, float(np.abs(w).max()) * 0.2) or name == "go"
 
 
+@pytest.mark.parametrize("spread", [1.0, 3.0], ids=["near", "far"])
+@pytest.mark.parametrize("case", [c for c in _TILE_CASES if c.name.startswith("gs_")], ids=lambda c: c.name)
+def test_default_kernels_fp16(case, spread):
+    """fp16 is the reference's AMP dtype (train.py:263): the default group-slice forward and split backward
+    (channel sums + tcgen05 value product, gc 16 and 32) in __half, against the fp64 oracle on the rounded inputs."""
+    from oracle import dcnv3_oracle as orc
+    v, o, m, g = cases.make_inputs(case)
+    arrs = rounded((v, o * spread, m, g), torch.float16)
+    got = run_cuda(arrs, case.geom, dtype=torch.float16)
+    out = orc.direct_forward(*arrs[:3], *case.geom)
+    gv, go, gm = orc.direct_backward(*arrs, *case.geom)
+    for name, a, w in zip(WHAT, got, (out, gv, go, gm)):
+        rms = float(np.sqrt(np.mean(w ** 2))) + 1e-30
+        frac = allclose_frac(a, w, rtol=1e-2, atol=1e-2 * rms)
+        assert frac <= (2e-3 if name == "go" else 1e-3), (name, frac, max_abs(a, w), rms)
+
+
 @pytest.mark.parametrize("dt", ["bf16", "f16"])
 def test_split_weights_forward_is_fp32_accurate(dt, monkeypatch):
     """DCNV3_WEIGHTS=split keeps the bilinear*mask coefficients fp32-accurate: the only error left
