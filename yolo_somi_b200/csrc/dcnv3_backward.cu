@@ -31,6 +31,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 #include <type_traits>
 
 namespace dcnv3 {
@@ -434,8 +435,10 @@ static SideStream *side_stream() {
     constexpr int kMaxDev = 64;
     static SideStream tab[kMaxDev];
     static int state[kMaxDev];   // 0 = not tried, 1 = ready, -1 = failed
+    static std::mutex mu;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
     if (state[dev] == 0) {
         SideStream s{};
         const bool ok = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -499,6 +502,10 @@ static cudaError_t backward_typed(const void *value, const void *offset, const v
                 SideStream *ss = side_stream();
                 cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
                 if (ss) {   // fork: memset of the plane || channel sums
+                    // (the events are per device, not per call: record + wait must not interleave with another
+                    // host thread's; the side stream itself is in order, so a later `join` covers an earlier memset)
+                    static std::mutex fork_mu;
+                    std::lock_guard<std::mutex> lock(fork_mu);
                     if ((err = cudaEventRecord(ss->fork, stream)) != cudaSuccess) return err;
                     if ((err = cudaStreamWaitEvent(ss->stream, ss->fork, 0)) != cudaSuccess) return err;
                     if ((err = cudaMemsetAsync(acc, 0, plane * sizeof(float), ss->stream)) != cudaSuccess) return err;
