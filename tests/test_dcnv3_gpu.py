@@ -128,6 +128,11 @@ _TILE_CASES = [
     cases.Case("gs_g8_gc32", N=2, H=27, W=21, G=8, gc=32, seed=211),
     cases.Case("gs_g16_gc32_pad0", N=1, H=19, W=34, G=16, gc=32, ph=0, pw=0, sigma=0.8, seed=212),
     cases.Case("gs_g4_gc32_fwd_only", N=1, H=18, W=20, G=4, gc=32, seed=213),
+    # group_channels == 8 in the same kernels (BASELINE configs[4], group 32 at C = 256): 16-byte slices
+    # (128-byte cells, three CTAs per SM); the tcgen05 product takes the 16-channel run of a group PAIR as its
+    # B operand and keeps the group's own eight accumulator columns
+    cases.Case("gs_g8_gc8", N=2, H=27, W=21, G=8, gc=8, seed=214),
+    cases.Case("gs_g32_gc8_pad0", N=1, H=19, W=34, G=32, gc=8, ph=0, pw=0, sigma=0.8, seed=215),
 ]
 
 
@@ -429,8 +434,8 @@ def test_layer_bf16_autocast_runs_and_is_close():
 
 
 # ----------------------------------------------------------------------------- guard bands
-@pytest.mark.parametrize("shape", [(2, 27, 21, 16, 16), (1, 19, 34, 8, 32), (2, 30, 41, 3, 16)],
-                         ids=["split_g16", "split_g8_gc32", "strip_g3"])
+@pytest.mark.parametrize("shape", [(2, 27, 21, 16, 16), (1, 19, 34, 8, 32), (2, 30, 41, 3, 16), (2, 27, 21, 16, 8)],
+                         ids=["split_g16", "split_g8_gc32", "strip_g3", "split_g16_gc8"])
 def test_outputs_and_workspace_stay_inside_their_buffers(shape):
     """Through the C ABI with every output and the workspace embedded in a larger sentinel-filled allocation
     (the sanitizer is not available on the GPU pool): reductions, TMA stores and bulk copies of the default

@@ -2,7 +2,8 @@
 // (G % 8 == 0) or 32 (G % 4 == 0: a group is two 16-channel slices, template parameter GSH = 1 -- the two lanes
 // of a group share its offsets / masks and add their partial sums with one shuffle; the 72-byte mask runs are
 // not legal TMA boxes, so the mask box starts on the 16-byte boundary below the run and grad_mask leaves by
-// plain 32-bit stores), 3x3 / stride 1 / dilation 1: grad_offset and grad_mask (the per-point channel sums
+// plain 32-bit stores) or 8 (G % 8 == 0: 16-byte slices, template parameter CH = 8 -- a 128-byte cell, three CTAs
+// per SM), 3x3 / stride 1 / dilation 1: grad_offset and grad_mask (the per-point channel sums
 // of dcnv3_im2col_cuda.cuh:106-146, 278-370) with the forward's group-slice layout.
 //
 // Why split (profiles/README.md, r1_v4): the fused strip backward holds a 12 KB coefficient tile
@@ -29,15 +30,15 @@ namespace bdots {
 constexpr int kTile = 8;                       // output pixels per tile side
 constexpr int kWin = 18;                       // value window side
 constexpr int kGroups = 8;                     // groups per CTA
-constexpr int kCh = 16;                        // channels per group (32 bytes of 16-bit data)
-constexpr int kCellBytes = kGroups * 32;       // 256
+constexpr int kCh = 16;                        // channels per slice (32 bytes of 16-bit data); 8 for gc == 8
 constexpr int kPix = kTile * kTile;            // 64
 constexpr int kThreads = kPix * kGroups;       // 512
 constexpr int kP = 9;
-constexpr int kWinBytes = kWin * kWin * kCellBytes;          // 82944
+__host__ __device__ constexpr int cell_bytes(int ch) { return kGroups * ch * 2; }                 // 256 / 128
+__host__ __device__ constexpr int win_bytes(int ch) { return kWin * kWin * cell_bytes(ch); }      // 82944 / 41472
 constexpr int kOffBytes = kPix * kGroups * kP * 4;           // 18432
 constexpr int kMskBytes = kPix * kGroups * kP * 2;           // 9216
-constexpr int kSmemBytes = kWinBytes + kOffBytes + kMskBytes;
+__host__ __device__ constexpr int smem_bytes(int ch) { return win_bytes(ch) + kOffBytes + kMskBytes; }
 
 struct Params {
     int ox_rel, oy_rel;      // window origin relative to the tile origin
@@ -77,14 +78,17 @@ static bool make_rows_tensor_map(CUtensorMap *map, const void *base, int dtype, 
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename T, int GSH>
-__global__ void __launch_bounds__(kThreads, 2)
+template <typename T, int GSH, int CH>
+__global__ void __launch_bounds__(kThreads, CH == 8 ? 3 : 2)
 bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
          const __grid_constant__ CUtensorMap tmap_m, const __grid_constant__ CUtensorMap tmap_go,
          const __grid_constant__ CUtensorMap tmap_gm, const T *__restrict__ value, const T *__restrict__ offset,
          const T *__restrict__ mask, const T *__restrict__ grad_out, T *__restrict__ grad_mask_out, const Geom q,
          const Params tp) {
     constexpr int E = 8;
+    constexpr int kCellBytes = cell_bytes(CH), kWinBytes = win_bytes(CH);
+    constexpr bool TWO = CH == 16;              // a lane owns two 16-byte chunks of a cell (one when gc == 8)
+    static_assert(CH == 16 || (CH == 8 && GSH == 0), "slices of 16 or 8 channels");
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     unsigned char *win = smem;
@@ -115,16 +119,16 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
         mbar_expect_tx(&bar, kWinBytes + kPix * (kOPitch + kMPitch));
         tma_load_4d(off_tile, &tmap_o, &bar, G0 * kP * 2, wo0, ho0, n);
         tma_load_4d(msk_tile, &tmap_m, &bar, (G0 * kP * 2 - m_shift) >> 1, wo0, ho0, n);
-        tma_load_4d(win, &tmap_v, &bar, g0 * kCh, ox, oy, n);
+        tma_load_4d(win, &tmap_v, &bar, g0 * CH, ox, oy, n);
     }
 
     const int wo = wo0 + px, ho = ho0 + py;
     const bool live = wo < q.Wo && ho < q.Ho;
-    const int half = (g >> 2) & 1;                   // 16-byte chunk this lane reads FIRST
+    const int half = TWO ? (g >> 2) & 1 : 0;         // 16-byte chunk this lane reads FIRST
     const float base_w = axis_base(wo, 3, 1, q.pw, 1, q.sigma);
     const float base_h = axis_base(ho, 3, 1, q.ph, 1, q.sigma);
     const float bw = base_w - (float)ox, bh = base_h - (float)oy;     // window-relative anchors
-    const uint32_t win_addr = smem_u32(win) + g * 32 + half * 16;
+    const uint32_t win_addr = smem_u32(win) + g * (CH * 2) + half * 16;
     const uint32_t my_off = s_off + pix * kOPitch + gr * (kP * 4);
     const uint32_t my_msk = s_msk + pix * kMPitch + m_shift + gr * (kP * 2);
 
@@ -132,9 +136,9 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
     // runs of 256 contiguous bytes)
     uint4 gq_a = make_uint4(0u, 0u, 0u, 0u), gq_b = gq_a;
     if (live) {
-        const T *gp = grad_out + (((size_t)n * q.Ho + ho) * q.Wo + wo) * (size_t)C + (g0 + g) * kCh;
+        const T *gp = grad_out + (((size_t)n * q.Ho + ho) * q.Wo + wo) * (size_t)C + (g0 + g) * CH;
         gq_a = __ldg(reinterpret_cast<const uint4 *>(gp + half * E));
-        gq_b = __ldg(reinterpret_cast<const uint4 *>(gp + (half ^ 1) * E));
+        if (TWO) gq_b = __ldg(reinterpret_cast<const uint4 *>(gp + (half ^ 1) * E));
     }
 
     mbar_wait(&bar, 0);
@@ -166,8 +170,8 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
             float dr[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                const uint4 qa = lds128(tl + o[t]), qb = lds128((tl ^ 16u) + o[t]);
-                dr[t] = dot<T>(gq_a, qa, 0.f) + dot<T>(gq_b, qb, 0.f);
+                dr[t] = dot<T>(gq_a, lds128(tl + o[t]), 0.f);
+                if (TWO) dr[t] += dot<T>(gq_b, lds128((tl ^ 16u) + o[t]), 0.f);
             }
             if (GSH) {   // the group's other 16 channels are the neighbouring lane's
                 const unsigned am = __activemask();
@@ -185,7 +189,7 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
         if (miss) {
             // ---- points whose corner block leaves the window: clamped global reads
             const int row_stride = q.W * C;
-            const T *img = value + (size_t)n * q.H * row_stride + (g0 + g) * kCh;
+            const T *img = value + (size_t)n * q.H * row_stride + (g0 + g) * CH;
             // (the staged inputs of a missed point were overwritten above: re-read them from the tensors)
             for (int p = 0; p < kP; ++p) {
                 if (!((miss >> p) & 1u)) continue;
@@ -205,9 +209,8 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
                     float dk[4];
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
-                        const uint4 qa = __ldg(reinterpret_cast<const uint4 *>(img + at[t] + ea));
-                        const uint4 qb = __ldg(reinterpret_cast<const uint4 *>(img + at[t] + eb));
-                        dk[t] = dot<T>(gq_a, qa, 0.f) + dot<T>(gq_b, qb, 0.f);
+                        dk[t] = dot<T>(gq_a, __ldg(reinterpret_cast<const uint4 *>(img + at[t] + ea)), 0.f);
+                        if (TWO) dk[t] += dot<T>(gq_b, __ldg(reinterpret_cast<const uint4 *>(img + at[t] + eb)), 0.f);
                     }
                     if (GSH) {   // (both lanes of a group take the same path: same coordinates)
                         const unsigned am = __activemask();
@@ -253,10 +256,11 @@ template <typename T>
 static bool launch_typed(const void *value, const void *offset, const void *mask, const void *grad_out,
                          void *grad_offset, void *grad_mask, const Geom &q, int dtype, cudaStream_t stream,
                          cudaError_t *err) {
-    if (!((q.gc == kCh && q.G % kGroups == 0) || (q.gc == 2 * kCh && q.G % (kGroups / 2) == 0)) || q.kh != 3 ||
+    if (!(((q.gc == kCh || q.gc == 8) && q.G % kGroups == 0) || (q.gc == 2 * kCh && q.G % (kGroups / 2) == 0)) || q.kh != 3 ||
         q.kw != 3 || q.sh != 1 || q.sw != 1 || q.dh != 1 || q.dw != 1)
         return false;
-    const int gsh = q.gc == kCh ? 0 : 1, grp = kGroups >> gsh;     // groups per CTA
+    const int gsh = q.gc == 2 * kCh ? 1 : 0, grp = kGroups >> gsh;     // groups per CTA
+    const int ch = q.gc == 8 ? 8 : kCh;                                // channels per slice
     if (((uintptr_t)value | (uintptr_t)grad_out | (uintptr_t)offset | (uintptr_t)mask | (uintptr_t)grad_offset |
          (uintptr_t)grad_mask) % 16)
         return false;
@@ -264,7 +268,7 @@ static bool launch_typed(const void *value, const void *offset, const void *mask
     if (!(q.sigma > 0.f) || span + 4 > kWin - 2) return false;
     const int C = q.G * q.gc;
     CUtensorMap tv, to, tm, tgo, tgm;
-    if (!make_nhwc_tensor_map(&tv, value, dtype, q.N, q.H, q.W, C, kGroups * kCh, kWin, kWin)) return false;
+    if (!make_nhwc_tensor_map(&tv, value, dtype, q.N, q.H, q.W, C, kGroups * ch, kWin, kWin)) return false;
     Params tp;
     tp.gsh = gsh;
     tp.o_pitch = grp * kP * 4;                                  // 288 / 144 bytes
@@ -280,7 +284,8 @@ static bool launch_typed(const void *value, const void *offset, const void *mask
     tp.gblocks = q.G / grp;
     const int tiles_y = (q.Ho + kTile - 1) / kTile;
     if (tp.gblocks > 65535) return false;
-    auto kern = gsh ? bwd_dots<T, 1> : bwd_dots<T, 0>;
+    auto kern = ch == 8 ? bwd_dots<T, 0, 8> : gsh ? bwd_dots<T, 1, 16> : bwd_dots<T, 0, 16>;
+    const int kSmemBytes = smem_bytes(ch);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     for (int n0 = 0; n0 < q.N; n0 += 65535) {
         tp.n0 = n0;

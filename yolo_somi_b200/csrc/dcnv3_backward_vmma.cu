@@ -1,5 +1,8 @@
-// dcnv3_backward_vmma.cu -- grad_value of the DCNv3 core backward for 16-bit I/O, group_channels 16 or 32,
+// dcnv3_backward_vmma.cu -- grad_value of the DCNv3 core backward for 16-bit I/O, group_channels 8, 16 or 32,
 // 3x3 / stride 1 / dilation 1, as a tcgen05 product with the accumulators in TENSOR MEMORY.
+// (group_channels == 8: N = 8 is not a legal UMMA shape at M = 128, so the B operand is the 16-channel run of the
+// group PAIR (g & ~1, g | 1) -- the same two TMA boxes as for 16 channels -- and the drain keeps the group's own
+// eight accumulator columns; the product is not what bounds the kernel.)
 // Second half of the split backward (grad_offset / grad_mask: dcnv3_backward_dots.cu).
 //
 // What it computes (reference dcnv3_im2col_cuda.cuh:82-147, col2im bilinear):
@@ -117,12 +120,12 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // ------------------------------------------------------------------------------------------------
 // A point beyond the band: its four coefficient x grad_out rows go straight to the fp32 plane.
-template <typename T>
+template <typename T, int NC = 16>
 __device__ __noinline__ void far_point(float *gv_img, int H, int W, int row_stride, int C, int h0, int w0, float c0,
                                        float c1, float c2, float c3, uint4 ga, uint4 gb) {
     float g[16];
     unpack<T>(ga, g);
-    unpack<T>(gb, g + 8);
+    unpack<T>(gb, g + 8);   // (NC == 8: unused)
     const float cf[4] = {c0, c1, c2, c3};
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
@@ -130,7 +133,7 @@ __device__ __noinline__ void far_point(float *gv_img, int H, int W, int row_stri
         if ((unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W && cf[t] != 0.f) {
             float *dst = gv_img + (ptrdiff_t)hh * row_stride + (ptrdiff_t)ww * C;
 #pragma unroll
-            for (int e = 0; e < 16; e += 4)
+            for (int e = 0; e < NC; e += 4)
                 red_add4(dst + e, make_float4(cf[t] * g[e], cf[t] * g[e + 1], cf[t] * g[e + 2], cf[t] * g[e + 3]));
         }
     }
@@ -159,10 +162,28 @@ __device__ __forceinline__ void drain_cells(const float (&r)[16], int lane, floa
         red_add4(po + 8, odd ? make_float4(r[12], r[13], r[14], r[15]) : make_float4(rv[4], rv[5], rv[6], rv[7]));
     }
 }
+#define VMMA_TMEM_LD_8(taddr, r)                                                                 \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"         \
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]) \
+                 : "r"(taddr))
+// `gsel` (NCH == 8 only): which half of the pair's 16 accumulator columns is this group's
 template <int NCH>
 __device__ __forceinline__ void drain_block(uint32_t tmem_base, int slot, int warp, int lane, float *gv_img, int y0,
-                                            int x0, int H, int W, int row_stride, int C) {
+                                            int x0, int H, int W, int row_stride, int C, int gsel) {
     const int y = y0 + 2 * warp + (lane >> 4);
+    if constexpr (NCH == 8) {
+        // a cell's eight fp32 channels are one 32-byte sector: every lane reduces its own cell
+        const int x = x0 + (lane & 15);
+        float r[8];
+        VMMA_TMEM_LD_8(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(slot * 16 + gsel * 8), r);
+        tmem_ld_wait();
+        if ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W) {
+            float *p = gv_img + (ptrdiff_t)y * row_stride + (ptrdiff_t)x * C;
+            red_add4(p, make_float4(r[0], r[1], r[2], r[3]));
+            red_add4(p + 4, make_float4(r[4], r[5], r[6], r[7]));
+        }
+        return;
+    }
     const int xe = x0 + (lane & 14);            // column of the pair's even cell
     const bool oky = (unsigned)y < (unsigned)H;
     float *p = gv_img + (ptrdiff_t)y * row_stride + (ptrdiff_t)xe * C;
@@ -211,7 +232,8 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
     unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t a_addr0 = smem_u32(base);                                   // A tiles: [strip][256 rows][128 B]
     unsigned char *stages = base + kStrips * kATileBytes;                      // [stage][strip][off | msk | gout]
-    constexpr int kStBytes = st_bytes(NCH), kStStrip = kStBytes, kTmemCols = 2 * NCH;   // (one strip per CTA)
+    constexpr int NB = NCH == 8 ? 16 : NCH;     // channels of the B operand = accumulator columns per block
+    constexpr int kStBytes = st_bytes(NB), kStStrip = kStBytes, kTmemCols = 2 * NB;   // (one strip per CTA)
     const uint32_t st_thr = smem_u32(stages) + strip_id * kStStrip;            // + stage * kStBytes
     const uint32_t a_strip = a_addr0 + strip_id * kATileBytes;
     const uint32_t kc = (uint32_t)k >> 3, kl = ((uint32_t)k & 7u) * 2u;
@@ -240,8 +262,9 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
             tma_load_4d(dst + st * kStStrip + kStMsk, &tmap_msk, bar, (gg * kP * 2 & ~15) >> 1, w0 + st * kStripW, h0, nn);
             // grad_out as two boxes of 8 channels: [half][64 px][16 B] is the MMA's B operand as it lands (MN-major)
 #pragma unroll
-            for (int c8 = 0; c8 < NCH / 8; ++c8)
-                tma_load_4d(dst + st * kStStrip + kStGout + c8 * 1024, &tmap_gout, bar, gg * NCH + c8 * 8, w0 + st * kStripW, h0, nn);
+            for (int c8 = 0; c8 < NB / 8; ++c8)   // (NCH == 8: the 16-channel run of the group pair)
+                tma_load_4d(dst + st * kStStrip + kStGout + c8 * 1024, &tmap_gout, bar,
+                            (NCH == 8 ? (gg >> 1) * 16 : gg * NCH) + c8 * 8, w0 + st * kStripW, h0, nn);
         }
     };
 
@@ -267,7 +290,7 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
         mbar_expect_tx(&zero_bar, kStrips * kATileBytes);
         bulk_fill(a_addr0, g_zero_tile, kStrips * kATileBytes, &zero_bar);
     }
-    const uint32_t idesc = umma_idesc(std::is_same<T, __nv_bfloat16>::value ? 1 : 0, 128, NCH);
+    const uint32_t idesc = umma_idesc(std::is_same<T, __nv_bfloat16>::value ? 1 : 0, 128, NB);
 
     if (tid == 0) request(0, n, g, wo0, ho0);
 
@@ -349,11 +372,17 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                         const float lw_abs = ub + (float)band_x0, lh_abs = vb + (float)band_y0;
                         if (lh_abs > -1.f && lw_abs > -1.f && lh_abs < (float)q.H && lw_abs < (float)q.W) {
                             const float hm = (1.f - lh) * m, lm = lh * m, hwt = 1.f - lw;
+                            if constexpr (NCH == 8) {
+                                const uint4 g8 = lds128(sa + kStGout + (g & 1) * 1024 + k * 16);
+                                far_point<T, 8>(gv_img, q.H, q.W, row_stride, C, (int)fh + band_y0, (int)fw + band_x0,
+                                                hm * hwt, hm * lw, lm * hwt, lm * lw, g8, g8);
+                            } else {
 #pragma unroll 1
-                            for (int h = 0; h < NCH / 16; ++h)
-                                far_point<T>(gv_img + h * 16, q.H, q.W, row_stride, C, (int)fh + band_y0, (int)fw + band_x0,
-                                             hm * hwt, hm * lw, lm * hwt, lm * lw, lds128(sa + kStGout + (2 * h) * 1024 + k * 16),
-                                             lds128(sa + kStGout + (2 * h + 1) * 1024 + k * 16));
+                                for (int h = 0; h < NCH / 16; ++h)
+                                    far_point<T>(gv_img + h * 16, q.H, q.W, row_stride, C, (int)fh + band_y0, (int)fw + band_x0,
+                                                 hm * hwt, hm * lw, lm * hwt, lm * lw, lds128(sa + kStGout + (2 * h) * 1024 + k * 16),
+                                                 lds128(sa + kStGout + (2 * h + 1) * 1024 + k * 16));
+                            }
                         }
                     }
                 }
@@ -369,7 +398,7 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                 for (int st = 0; st < kStrips; ++st)
 #pragma unroll
                     for (int blk = 0; blk < 2; ++blk) {
-                        const uint32_t d = tmem_base + (uint32_t)((st * 2 + ((s + blk) & 1)) * NCH);
+                        const uint32_t d = tmem_base + (uint32_t)((st * 2 + ((s + blk) & 1)) * NB);
                         const uint32_t aa = a_addr0 + st * kATileBytes + blk * kBlockBytes;
                         const uint32_t bb = smem_u32(stages) + stage * kStBytes + st * kStStrip + kStGout;
 #pragma unroll
@@ -388,11 +417,11 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                 bulk_fill(a_addr0, g_zero_tile, kStrips * kATileBytes, &zero_bar);
             }
             // ---- the band's upper block is final: reductions
-            drain_block<NCH>(tmem_base, s & 1, warp, lane, gv_img, band_y0, wo0 + pp.bx_rel, q.H, q.W, row_stride, C);
+            drain_block<NCH>(tmem_base, s & 1, warp, lane, gv_img, band_y0, wo0 + pp.bx_rel, q.H, q.W, row_stride, C, g & 1);
         }
         // ---- the last step's lower block
         drain_block<NCH>(tmem_base, pp.steps & 1, warp, lane, gv_img, ho0 + (pp.steps - 1) * kRows + pp.by_rel + 8,
-                    wo0 + pp.bx_rel, q.H, q.W, row_stride, C);
+                    wo0 + pp.bx_rel, q.H, q.W, row_stride, C, g & 1);
         if (!has_next) break;
         n = n2; g = g2; wo0 = wo2; ho0 = ho2;
         t = t_next;
@@ -436,7 +465,10 @@ static bool launch_typed(const void *offset, const void *mask, const void *grad_
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const int ctas = (int)std::min<long long>(total, (long long)kCtasPerSm * num_sms);
-    if (q.gc == 16) {
+    if (q.gc == 8) {
+        cudaFuncSetAttribute(bwd_vmma<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(16));
+        bwd_vmma<T, 8><<<ctas, kThreadsV, smem_bytes(16), stream>>>(to, tm, tg, gv_acc, q, pp);
+    } else if (q.gc == 16) {
         cudaFuncSetAttribute(bwd_vmma<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(16));
         bwd_vmma<T, 16><<<ctas, kThreadsV, smem_bytes(16), stream>>>(to, tm, tg, gv_acc, q, pp);
     } else {
@@ -451,7 +483,7 @@ static bool launch_typed(const void *offset, const void *mask, const void *grad_
 
 bool backward_vmma_eligible(const void *offset, const void *mask, const void *grad_out, const float *gv_acc, const Geom &q) {
     using namespace strip;
-    if ((q.gc != 16 && q.gc != 32) || q.kh != 3 || q.kw != 3 || q.sh != 1 || q.sw != 1 || q.dh != 1 || q.dw != 1) return false;
+    if ((q.gc != 8 && q.gc != 16 && q.gc != 32) || q.kh != 3 || q.kw != 3 || q.sh != 1 || q.sw != 1 || q.dh != 1 || q.dw != 1) return false;
     if (!(q.sigma >= 0.5f && q.sigma <= 1.25f)) return false;   // band = taps +- 3 px
     // TMA staging: 16-byte aligned bases and row strides (G * 18 B for the masks: G % 8 == 0)
     if (((uintptr_t)grad_out | (uintptr_t)gv_acc | (uintptr_t)offset | (uintptr_t)mask) % 16 || q.G % 8) return false;

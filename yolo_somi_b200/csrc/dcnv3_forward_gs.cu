@@ -3,6 +3,9 @@
 // group_channels == 32 (G % 4 == 0) runs the same kernel with a group as TWO 16-channel slices (template
 // parameter GSH = 1): lanes 2j and 2j+1 share the group's offsets / masks; its 72-byte mask runs are not
 // legal TMA boxes, so the mask box starts on the 16-byte boundary below the run (m_shift).
+// group_channels == 8 (G % 8 == 0; BASELINE configs[4], group 32 at C = 256) runs it with 16-byte slices (template
+// parameter CH = 8): a cell of eight groups is 128 bytes = one full bank row, a quarter-warp's eight 16-byte reads
+// cover it exactly once whatever cell each lane samples, the window shrinks to 41 KB and three CTAs share an SM.
 //
 // Why (profiles/README.md, r1_v3 fwd_tile): the tiled forward was issue-bound at 201 instructions
 // per sampled point, of which only 64 are the FHFMAs and 8 the gather loads; ~40 went into staging
@@ -43,15 +46,15 @@ namespace gs {
 constexpr int kTile = 8;                       // output pixels per tile side
 constexpr int kWin = 18;                       // value window side
 constexpr int kGroups = 8;                     // groups per CTA
-constexpr int kCh = 16;                        // channels per group (32 bytes of 16-bit data)
-constexpr int kCellBytes = kGroups * 32;       // 256
+constexpr int kCh = 16;                        // channels per slice (32 bytes of 16-bit data); 8 for gc == 8
 constexpr int kPix = kTile * kTile;            // 64
 constexpr int kThreads = kPix * kGroups;       // 512
 constexpr int kP = 9;
-constexpr int kWinBytes = kWin * kWin * kCellBytes;          // 82944
+__host__ __device__ constexpr int cell_bytes(int ch) { return kGroups * ch * 2; }                 // 256 / 128
+__host__ __device__ constexpr int win_bytes(int ch) { return kWin * kWin * cell_bytes(ch); }      // 82944 / 41472
 constexpr int kOffBytes = kPix * kGroups * kP * 4;           // 18432
 constexpr int kMskBytes = kPix * kGroups * kP * 2;           // 9216
-constexpr int kSmemBytes = kWinBytes + kOffBytes + kMskBytes;
+__host__ __device__ constexpr int smem_bytes(int ch) { return win_bytes(ch) + kOffBytes + kMskBytes; }
 
 struct Params {
     int ox_rel, oy_rel;      // window origin relative to the tile origin
@@ -87,12 +90,15 @@ static bool make_rows_tensor_map(CUtensorMap *map, const void *base, int dtype, 
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename T, bool FAST, int GSH>
-__global__ void __launch_bounds__(kThreads, 2)
+template <typename T, bool FAST, int GSH, int CH>
+__global__ void __launch_bounds__(kThreads, CH == 8 ? 3 : 2)
 fwd_gs(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
        const __grid_constant__ CUtensorMap tmap_m, const T *__restrict__ value, const T *__restrict__ offset,
        const T *__restrict__ mask, T *__restrict__ out, const Geom q, const Params tp) {
     constexpr int E = 8;
+    constexpr int kCellBytes = cell_bytes(CH), kWinBytes = win_bytes(CH);
+    constexpr bool TWO = CH == 16;              // a lane owns two 16-byte chunks of a cell (one when gc == 8)
+    static_assert(CH == 16 || (CH == 8 && GSH == 0), "slices of 16 or 8 channels");
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     unsigned char *win = smem;
@@ -121,16 +127,16 @@ fwd_gs(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUten
         mbar_expect_tx(&bar, kWinBytes + kPix * (kOPitch + kMPitch));
         tma_load_4d(smem + kWinBytes, &tmap_o, &bar, G0 * kP * 2, wo0, ho0, n);
         tma_load_4d(smem + kWinBytes + kOffBytes, &tmap_m, &bar, (G0 * kP * 2 - m_shift) >> 1, wo0, ho0, n);
-        tma_load_4d(win, &tmap_v, &bar, g0 * kCh, ox, oy, n);
+        tma_load_4d(win, &tmap_v, &bar, g0 * CH, ox, oy, n);
     }
 
     const int wo = wo0 + px, ho = ho0 + py;
     const bool live = wo < q.Wo && ho < q.Ho;
-    const int half = (g >> 2) & 1;                   // 16-byte chunk this lane reads FIRST
+    const int half = TWO ? (g >> 2) & 1 : 0;         // 16-byte chunk this lane reads FIRST
     const float base_w = axis_base(wo, 3, 1, q.pw, 1, q.sigma);
     const float base_h = axis_base(ho, 3, 1, q.ph, 1, q.sigma);
     const float bw = base_w - (float)ox, bh = base_h - (float)oy;     // window-relative anchors
-    const uint32_t win_addr = smem_u32(win) + g * 32 + half * 16;
+    const uint32_t win_addr = smem_u32(win) + g * (CH * 2) + half * 16;
     const uint32_t my_off = s_off + pix * kOPitch + gr * (kP * 4);
     const uint32_t my_msk = s_msk + pix * kMPitch + m_shift + gr * (kP * 2);
 
@@ -168,17 +174,16 @@ fwd_gs(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUten
         const uint32_t o[4] = {0u, (uint32_t)kCellBytes, (uint32_t)(kWin * kCellBytes), (uint32_t)((kWin + 1) * kCellBytes)};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-            const uint4 qa = lds128(tl + o[t]), qb = lds128((tl ^ 16u) + o[t]);
             const Weight<T, FAST> wt(w[t]);
-            axpy<T, FAST>(acc_a, qa, wt);
-            axpy<T, FAST>(acc_b, qb, wt);
+            axpy<T, FAST>(acc_a, lds128(tl + o[t]), wt);
+            if (TWO) axpy<T, FAST>(acc_b, lds128((tl ^ 16u) + o[t]), wt);
         }
     }
 
     if (miss) {
         // ---- points whose corner block leaves the window: clamped global reads
         const int C = q.G * q.gc, row_stride = q.W * C;
-        const T *img = value + (size_t)n * q.H * row_stride + (g0 + g) * kCh;
+        const T *img = value + (size_t)n * q.H * row_stride + (g0 + g) * CH;
         const size_t e0 = ((((size_t)n * q.Ho + ho) * q.Wo + wo) * q.G + (G0 + gr)) * kP;
         for (int p = 0; p < kP; ++p) {
             if (!((miss >> p) & 1u)) continue;
@@ -198,34 +203,33 @@ fwd_gs(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUten
             const float wc[4] = {fy_lo * fx_lo, fy_lo * fx_hi, fy_hi * fx_lo, fy_hi * fx_hi};
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                const uint4 qa = __ldg(reinterpret_cast<const uint4 *>(corner[t] + ea));
-                const uint4 qb = __ldg(reinterpret_cast<const uint4 *>(corner[t] + eb));
                 const Weight<T, FAST> wt(wc[t]);
-                axpy<T, FAST>(acc_a, qa, wt);
-                axpy<T, FAST>(acc_b, qb, wt);
+                axpy<T, FAST>(acc_a, __ldg(reinterpret_cast<const uint4 *>(corner[t] + ea)), wt);
+                if (TWO) axpy<T, FAST>(acc_b, __ldg(reinterpret_cast<const uint4 *>(corner[t] + eb)), wt);
             }
         }
     }
 
-    T *dst = out + (((size_t)n * q.Ho + ho) * q.Wo + wo) * (size_t)(q.G * q.gc) + (g0 + g) * kCh;
+    T *dst = out + (((size_t)n * q.Ho + ho) * q.Wo + wo) * (size_t)(q.G * q.gc) + (g0 + g) * CH;
     *reinterpret_cast<uint4 *>(dst + half * E) = pack<T>(acc_a);
-    *reinterpret_cast<uint4 *>(dst + (half ^ 1) * E) = pack<T>(acc_b);
+    if (TWO) *reinterpret_cast<uint4 *>(dst + (half ^ 1) * E) = pack<T>(acc_b);
 }
 
 template <typename T>
 static bool launch_typed(const void *value, const void *offset, const void *mask, void *out, const Geom &q,
                          int dtype, bool fast, cudaStream_t stream, cudaError_t *err) {
-    if (!((q.gc == kCh && q.G % kGroups == 0) || (q.gc == 2 * kCh && q.G % (kGroups / 2) == 0)) || q.kh != 3 ||
+    if (!(((q.gc == kCh || q.gc == 8) && q.G % kGroups == 0) || (q.gc == 2 * kCh && q.G % (kGroups / 2) == 0)) || q.kh != 3 ||
         q.kw != 3 || q.sh != 1 || q.sw != 1 || q.dh != 1 || q.dw != 1)
         return false;
     if (((uintptr_t)value | (uintptr_t)out | (uintptr_t)offset | (uintptr_t)mask) % 16) return false;
-    const int gsh = q.gc == kCh ? 0 : 1, grp = kGroups >> gsh;     // groups per CTA
+    const int gsh = q.gc == 2 * kCh ? 1 : 0, grp = kGroups >> gsh;     // groups per CTA
+    const int ch = q.gc == 8 ? 8 : kCh;                                // channels per slice
     // the tile's nominal tap span must leave at least 2 pixels of offset slack on each side
     const float span = (kTile - 1) + 2 * q.sigma;
     if (!(q.sigma > 0.f) || span + 4 > kWin - 2) return false;
     const int C = q.G * q.gc;
     CUtensorMap tmap_v, tmap_o, tmap_m;
-    if (!make_nhwc_tensor_map(&tmap_v, value, dtype, q.N, q.H, q.W, C, kGroups * kCh, kWin, kWin)) return false;
+    if (!make_nhwc_tensor_map(&tmap_v, value, dtype, q.N, q.H, q.W, C, kGroups * ch, kWin, kWin)) return false;
     Params tp;
     tp.gsh = gsh;
     tp.o_pitch = grp * kP * 4;                                  // 288 / 144 bytes
@@ -241,7 +245,10 @@ static bool launch_typed(const void *value, const void *offset, const void *mask
     if (tp.gblocks > 65535) return false;
     const T *v = static_cast<const T *>(value), *o = static_cast<const T *>(offset), *m = static_cast<const T *>(mask);
     T *y = static_cast<T *>(out);
-    auto kern = gsh ? (fast ? fwd_gs<T, true, 1> : fwd_gs<T, false, 1>) : (fast ? fwd_gs<T, true, 0> : fwd_gs<T, false, 0>);
+    auto kern = ch == 8 ? (fast ? fwd_gs<T, true, 0, 8> : fwd_gs<T, false, 0, 8>)
+                : gsh   ? (fast ? fwd_gs<T, true, 1, 16> : fwd_gs<T, false, 1, 16>)
+                        : (fast ? fwd_gs<T, true, 0, 16> : fwd_gs<T, false, 0, 16>);
+    const int kSmemBytes = smem_bytes(ch);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     for (int n0 = 0; n0 < q.N; n0 += 65535) {
         tp.n0 = n0;
