@@ -32,13 +32,17 @@ constexpr int kWin = 18;                       // value window side
 constexpr int kGroups = 8;                     // groups per CTA
 constexpr int kCh = 16;                        // channels per slice (32 bytes of 16-bit data); 8 for gc == 8
 constexpr int kPix = kTile * kTile;            // 64
-constexpr int kThreads = kPix * kGroups;       // 512
+constexpr int kThreads = kPix * kGroups;       // 512 (256 when a CTA takes four slices, template parameter KG = 4)
 constexpr int kP = 9;
-__host__ __device__ constexpr int cell_bytes(int ch) { return kGroups * ch * 2; }                 // 256 / 128
-__host__ __device__ constexpr int win_bytes(int ch) { return kWin * kWin * cell_bytes(ch); }      // 82944 / 41472
-constexpr int kOffBytes = kPix * kGroups * kP * 4;           // 18432
-constexpr int kMskBytes = kPix * kGroups * kP * 2;           // 9216
-__host__ __device__ constexpr int smem_bytes(int ch) { return win_bytes(ch) + kOffBytes + kMskBytes; }
+__host__ __device__ constexpr int cell_bytes(int ch, int kg = kGroups) { return kg * ch * 2; }                  // 256 / 128
+__host__ __device__ constexpr int win_bytes(int ch, int kg = kGroups) { return kWin * kWin * cell_bytes(ch, kg); } // 82944 / 41472
+// staged offset / mask bytes per pixel for `groups` groups: 36 / 18 bytes each; a mask run that is not a multiple
+// of 16 bytes (4 groups: 72) is staged from the 16-byte boundary below it (up to 8 bytes of shift): 80-byte pitch
+__host__ __device__ constexpr int off_pitch(int groups) { return groups * kP * 4; }
+__host__ __device__ constexpr int msk_pitch(int groups) { return (groups * kP * 2) % 16 ? 80 : groups * kP * 2; }
+__host__ __device__ constexpr int smem_bytes(int ch, int kg = kGroups, int gsh = 0) {
+    return win_bytes(ch, kg) + kPix * (off_pitch(kg >> gsh) + msk_pitch(kg >> gsh));
+}
 
 struct Params {
     int ox_rel, oy_rel;      // window origin relative to the tile origin
@@ -78,17 +82,21 @@ static bool make_rows_tensor_map(CUtensorMap *map, const void *base, int dtype, 
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename T, int GSH, int CH>
-__global__ void __launch_bounds__(kThreads, CH == 8 ? 3 : 2)
+template <typename T, int GSH, int CH, int KG = kGroups>
+__global__ void __launch_bounds__(kPix * KG, KG == 4 ? 4 : CH == 8 ? 3 : 2)
 bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
          const __grid_constant__ CUtensorMap tmap_m, const __grid_constant__ CUtensorMap tmap_go,
          const __grid_constant__ CUtensorMap tmap_gm, const T *__restrict__ value, const T *__restrict__ offset,
          const T *__restrict__ mask, const T *__restrict__ grad_out, T *__restrict__ grad_mask_out, const Geom q,
          const Params tp) {
     constexpr int E = 8;
-    constexpr int kCellBytes = cell_bytes(CH), kWinBytes = win_bytes(CH);
+    constexpr int kCellBytes = cell_bytes(CH, KG), kWinBytes = win_bytes(CH, KG);
+    constexpr int kOPitch = off_pitch(KG >> GSH), kMPitch = msk_pitch(KG >> GSH), kOffBytes = kPix * kOPitch;
+    constexpr bool PADM = ((KG >> GSH) * kP * 2) % 16 != 0;      // 72-byte mask runs: no legal TMA box
+    constexpr int kThreadsK = kPix * KG;
     constexpr bool TWO = CH == 16;              // a lane owns two 16-byte chunks of a cell (one when gc == 8)
     static_assert(CH == 16 || (CH == 8 && GSH == 0), "slices of 16 or 8 channels");
+    static_assert(KG == 8 || (KG == 4 && GSH == 0 && CH == 16), "eight slices per CTA, or four 16-channel groups");
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     unsigned char *win = smem;
@@ -97,14 +105,13 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
     const uint32_t s_off = smem_u32(off_tile), s_msk = smem_u32(msk_tile);
 
     const int tid = threadIdx.x;
-    const int g = tid & 7, pix = tid >> 3, px = pix & 7, py = pix >> 3;
+    const int g = tid & (KG - 1), pix = tid / KG, px = pix & 7, py = pix >> 3;
     const int tile_x = blockIdx.x % tp.tiles_x, tile_y = blockIdx.x / tp.tiles_x;
-    const int g0 = blockIdx.y * kGroups;                       // first 16-channel slice of the CTA
-    constexpr int kOPitch = (kGroups >> GSH) * kP * 4, kMPitch = GSH ? 80 : (kGroups >> GSH) * kP * 2;
+    const int g0 = blockIdx.y * KG;                            // first 16-channel slice of the CTA
     const int gr = g >> GSH;                                   // this lane's group inside the CTA's block
-    const int G0 = blockIdx.y * (kGroups >> GSH);              // first group of the CTA
+    const int G0 = blockIdx.y * (KG >> GSH);                   // first group of the CTA
     // the mask box starts on the 16-byte boundary below the block's run (72-byte runs when gc == 32)
-    const int m_shift = GSH ? (G0 * kP * 2) & 15 : 0;
+    const int m_shift = PADM ? (G0 * kP * 2) & 15 : 0;
     const int C = q.G * q.gc;
     const int n = tp.n0 + blockIdx.z;
     const int wo0 = tile_x * kTile, ho0 = tile_y * kTile;
@@ -124,7 +131,8 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
 
     const int wo = wo0 + px, ho = ho0 + py;
     const bool live = wo < q.Wo && ho < q.Ho;
-    const int half = TWO ? (g >> 2) & 1 : 0;         // 16-byte chunk this lane reads FIRST
+    // 16-byte chunk this lane reads FIRST (KG == 4: a quarter-warp is two pixels x four groups of 128-byte cells)
+    const int half = TWO ? (KG == 8 ? (g >> 2) & 1 : pix & 1) : 0;
     const float base_w = axis_base(wo, 3, 1, q.pw, 1, q.sigma);
     const float base_h = axis_base(ho, 3, 1, q.ph, 1, q.sigma);
     const float bw = base_w - (float)ox, bh = base_h - (float)oy;     // window-relative anchors
@@ -233,13 +241,13 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
     __syncthreads();
     if (tid == 0) {
         tma_store_4d(&tmap_go, off_tile, G0 * kP * 2, wo0, ho0, n);
-        if (!GSH) tma_store_4d(&tmap_gm, msk_tile, G0 * kP, wo0, ho0, n);
+        if (!PADM) tma_store_4d(&tmap_gm, msk_tile, G0 * kP, wo0, ho0, n);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-    if (GSH) {
-        // gc == 32: the block's mask run is 72 bytes at a 72-byte pitch -- not a legal TMA box; plain 32-bit stores
+    if (PADM) {
+        // four groups per CTA (gc == 32, or KG == 4): the block's mask run is 72 bytes at a 72-byte pitch -- not a legal TMA box; plain 32-bit stores
         uint32_t *gmw = reinterpret_cast<uint32_t *>(grad_mask_out);
-        for (int idx = tid; idx < kPix * 18; idx += kThreads) {
+        for (int idx = tid; idx < kPix * 18; idx += kThreadsK) {
             const int pxl = idx / 18, w = idx - pxl * 18;
             const int xo = wo0 + (pxl & 7), yo = ho0 + (pxl >> 3);
             if (xo < q.Wo && yo < q.Ho) {
@@ -259,8 +267,13 @@ static bool launch_typed(const void *value, const void *offset, const void *mask
     if (!(((q.gc == kCh || q.gc == 8) && q.G % kGroups == 0) || (q.gc == 2 * kCh && q.G % (kGroups / 2) == 0)) || q.kh != 3 ||
         q.kw != 3 || q.sh != 1 || q.sw != 1 || q.dh != 1 || q.dw != 1)
         return false;
-    const int gsh = q.gc == 2 * kCh ? 1 : 0, grp = kGroups >> gsh;     // groups per CTA
+    const int gsh = q.gc == 2 * kCh ? 1 : 0;
     const int ch = q.gc == 8 ? 8 : kCh;                                // channels per slice
+    // DCNV3_GS_KG=4 (gc == 16): four groups per 256-thread CTA, four CTAs per SM -- the forward's default, measured
+    // here at 100.5 us against 99 us for the 512-thread form (grad_mask then leaves by plain stores), so opt-in
+    const char *ekg = std::getenv("DCNV3_GS_KG");
+    const int kg = (q.gc == kCh && ekg && ekg[0] == '4') ? 4 : kGroups;
+    const int grp = kg >> gsh;                                         // groups per CTA
     if (((uintptr_t)value | (uintptr_t)grad_out | (uintptr_t)offset | (uintptr_t)mask | (uintptr_t)grad_offset |
          (uintptr_t)grad_mask) % 16)
         return false;
@@ -268,11 +281,11 @@ static bool launch_typed(const void *value, const void *offset, const void *mask
     if (!(q.sigma > 0.f) || span + 4 > kWin - 2) return false;
     const int C = q.G * q.gc;
     CUtensorMap tv, to, tm, tgo, tgm;
-    if (!make_nhwc_tensor_map(&tv, value, dtype, q.N, q.H, q.W, C, kGroups * ch, kWin, kWin)) return false;
+    if (!make_nhwc_tensor_map(&tv, value, dtype, q.N, q.H, q.W, C, kg * ch, kWin, kWin)) return false;
     Params tp;
     tp.gsh = gsh;
-    tp.o_pitch = grp * kP * 4;                                  // 288 / 144 bytes
-    tp.m_pitch = gsh ? 80 : grp * kP * 2;                       // 144 bytes, or the 72-byte run + up to 8 bytes of shift
+    tp.o_pitch = off_pitch(grp);                                // 288 / 144 bytes
+    tp.m_pitch = msk_pitch(grp);                                // 144 bytes, or the 72-byte run + up to 8 bytes of shift
     if (!make_rows_tensor_map(&to, offset, dtype, q.N, q.Ho, q.Wo, q.G * kP * 2, tp.o_pitch / 2)) return false;
     if (!make_rows_tensor_map(&tm, mask, dtype, q.N, q.Ho, q.Wo, q.G * kP, tp.m_pitch / 2)) return false;
     if (!make_rows_tensor_map(&tgo, grad_offset, dtype, q.N, q.Ho, q.Wo, q.G * kP * 2, tp.o_pitch / 2)) return false;
@@ -284,13 +297,13 @@ static bool launch_typed(const void *value, const void *offset, const void *mask
     tp.gblocks = q.G / grp;
     const int tiles_y = (q.Ho + kTile - 1) / kTile;
     if (tp.gblocks > 65535) return false;
-    auto kern = ch == 8 ? bwd_dots<T, 0, 8> : gsh ? bwd_dots<T, 1, 16> : bwd_dots<T, 0, 16>;
-    const int kSmemBytes = smem_bytes(ch);
+    auto kern = kg == 4 ? bwd_dots<T, 0, 16, 4> : ch == 8 ? bwd_dots<T, 0, 8> : gsh ? bwd_dots<T, 1, 16> : bwd_dots<T, 0, 16>;
+    const int kSmemBytes = smem_bytes(ch, kg, gsh);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     for (int n0 = 0; n0 < q.N; n0 += 65535) {
         tp.n0 = n0;
         const dim3 grid((unsigned)(tp.tiles_x * tiles_y), (unsigned)tp.gblocks, (unsigned)std::min(65535, q.N - n0));
-        kern<<<grid, kThreads, kSmemBytes, stream>>>(tv, to, tm, tgo, tgm, static_cast<const T *>(value),
+        kern<<<grid, kPix * kg, kSmemBytes, stream>>>(tv, to, tm, tgo, tgm, static_cast<const T *>(value),
                                                      static_cast<const T *>(offset), static_cast<const T *>(mask),
                                                      static_cast<const T *>(grad_out), static_cast<T *>(grad_mask), q, tp);
     }

@@ -24,6 +24,11 @@
 //   * their shared-memory layout is conflict-free for the per-point 32-bit / 16-bit reads
 //     ((8 px + 9 g + p) mod 32 is a bijection of the 32 lanes);
 //   * the output of a warp is four runs of 256 contiguous bytes.
+// Default for group_channels == 16 since the end of round 1 (template parameter KG = 4): the same kernel with FOUR
+// groups per 256-thread CTA and four CTAs per SM -- 128-byte cells, a quarter-warp is two pixels x four groups and
+// the odd pixel reads its second 16-byte chunk first (all eight slots once, for any offsets); the 72-byte mask
+// runs are staged like those of gc == 32.  Same occupancy, but while one CTA waits for its window three others
+// compute instead of one: 79 -> 75 us on cfg2 (DCNV3_GS_KG=8 selects the 512-thread form).
 // The loop over the nine points is branch-free: a point whose corner block leaves the window
 // (offsets beyond about +-4 px of the kernel tap) contributes zero there and is redone afterwards
 // from global memory, so the compiler is free to keep several points' loads in flight.
@@ -48,13 +53,17 @@ constexpr int kWin = 18;                       // value window side
 constexpr int kGroups = 8;                     // groups per CTA
 constexpr int kCh = 16;                        // channels per slice (32 bytes of 16-bit data); 8 for gc == 8
 constexpr int kPix = kTile * kTile;            // 64
-constexpr int kThreads = kPix * kGroups;       // 512
+constexpr int kThreads = kPix * kGroups;       // 512 (256 when a CTA takes four slices, template parameter KG = 4)
 constexpr int kP = 9;
-__host__ __device__ constexpr int cell_bytes(int ch) { return kGroups * ch * 2; }                 // 256 / 128
-__host__ __device__ constexpr int win_bytes(int ch) { return kWin * kWin * cell_bytes(ch); }      // 82944 / 41472
-constexpr int kOffBytes = kPix * kGroups * kP * 4;           // 18432
-constexpr int kMskBytes = kPix * kGroups * kP * 2;           // 9216
-__host__ __device__ constexpr int smem_bytes(int ch) { return win_bytes(ch) + kOffBytes + kMskBytes; }
+__host__ __device__ constexpr int cell_bytes(int ch, int kg = kGroups) { return kg * ch * 2; }                  // 256 / 128
+__host__ __device__ constexpr int win_bytes(int ch, int kg = kGroups) { return kWin * kWin * cell_bytes(ch, kg); } // 82944 / 41472
+// staged offset / mask bytes per pixel for `groups` groups: 36 / 18 bytes each; a mask run that is not a multiple
+// of 16 bytes (4 groups: 72) is staged from the 16-byte boundary below it (up to 8 bytes of shift): 80-byte pitch
+__host__ __device__ constexpr int off_pitch(int groups) { return groups * kP * 4; }
+__host__ __device__ constexpr int msk_pitch(int groups) { return (groups * kP * 2) % 16 ? 80 : groups * kP * 2; }
+__host__ __device__ constexpr int smem_bytes(int ch, int kg = kGroups, int gsh = 0) {
+    return win_bytes(ch, kg) + kPix * (off_pitch(kg >> gsh) + msk_pitch(kg >> gsh));
+}
 
 struct Params {
     int ox_rel, oy_rel;      // window origin relative to the tile origin
@@ -90,15 +99,18 @@ static bool make_rows_tensor_map(CUtensorMap *map, const void *base, int dtype, 
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename T, bool FAST, int GSH, int CH>
-__global__ void __launch_bounds__(kThreads, CH == 8 ? 3 : 2)
+template <typename T, bool FAST, int GSH, int CH, int KG = kGroups>
+__global__ void __launch_bounds__(kPix * KG, KG == 4 ? 4 : CH == 8 ? 3 : 2)
 fwd_gs(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
        const __grid_constant__ CUtensorMap tmap_m, const T *__restrict__ value, const T *__restrict__ offset,
        const T *__restrict__ mask, T *__restrict__ out, const Geom q, const Params tp) {
     constexpr int E = 8;
-    constexpr int kCellBytes = cell_bytes(CH), kWinBytes = win_bytes(CH);
+    constexpr int kCellBytes = cell_bytes(CH, KG), kWinBytes = win_bytes(CH, KG);
+    constexpr int kOPitch = off_pitch(KG >> GSH), kMPitch = msk_pitch(KG >> GSH), kOffBytes = kPix * kOPitch;
+    constexpr bool PADM = ((KG >> GSH) * kP * 2) % 16 != 0;
     constexpr bool TWO = CH == 16;              // a lane owns two 16-byte chunks of a cell (one when gc == 8)
     static_assert(CH == 16 || (CH == 8 && GSH == 0), "slices of 16 or 8 channels");
+    static_assert(KG == 8 || (KG == 4 && GSH == 0 && CH == 16), "eight slices per CTA, or four 16-channel groups");
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     unsigned char *win = smem;
@@ -106,14 +118,13 @@ fwd_gs(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUten
     const uint32_t s_msk = smem_u32(smem + kWinBytes + kOffBytes);   // [64 px][8 g][9]
 
     const int tid = threadIdx.x;
-    const int g = tid & 7, pix = tid >> 3, px = pix & 7, py = pix >> 3;
+    const int g = tid & (KG - 1), pix = tid / KG, px = pix & 7, py = pix >> 3;
     const int tile_x = blockIdx.x % tp.tiles_x, tile_y = blockIdx.x / tp.tiles_x;
-    const int g0 = blockIdx.y * kGroups;                       // first 16-channel slice of the CTA
-    constexpr int kOPitch = (kGroups >> GSH) * kP * 4, kMPitch = GSH ? 80 : (kGroups >> GSH) * kP * 2;
+    const int g0 = blockIdx.y * KG;                            // first 16-channel slice of the CTA
     const int gr = g >> GSH;                                   // this lane's group inside the CTA's block
-    const int G0 = blockIdx.y * (kGroups >> GSH);              // first group of the CTA
+    const int G0 = blockIdx.y * (KG >> GSH);                   // first group of the CTA
     // the mask box starts on the 16-byte boundary below the block's run (72-byte runs when gc == 32)
-    const int m_shift = GSH ? (G0 * kP * 2) & 15 : 0;
+    const int m_shift = PADM ? (G0 * kP * 2) & 15 : 0;
     const int n = tp.n0 + blockIdx.z;
     const int wo0 = tile_x * kTile, ho0 = tile_y * kTile;
     const int ox = wo0 + tp.ox_rel, oy = ho0 + tp.oy_rel;
@@ -132,7 +143,8 @@ fwd_gs(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUten
 
     const int wo = wo0 + px, ho = ho0 + py;
     const bool live = wo < q.Wo && ho < q.Ho;
-    const int half = TWO ? (g >> 2) & 1 : 0;         // 16-byte chunk this lane reads FIRST
+    // 16-byte chunk this lane reads FIRST (KG == 4: a quarter-warp is two pixels x four groups of 128-byte cells)
+    const int half = TWO ? (KG == 8 ? (g >> 2) & 1 : pix & 1) : 0;
     const float base_w = axis_base(wo, 3, 1, q.pw, 1, q.sigma);
     const float base_h = axis_base(ho, 3, 1, q.ph, 1, q.sigma);
     const float bw = base_w - (float)ox, bh = base_h - (float)oy;     // window-relative anchors
@@ -222,18 +234,22 @@ static bool launch_typed(const void *value, const void *offset, const void *mask
         q.kw != 3 || q.sh != 1 || q.sw != 1 || q.dh != 1 || q.dw != 1)
         return false;
     if (((uintptr_t)value | (uintptr_t)out | (uintptr_t)offset | (uintptr_t)mask) % 16) return false;
-    const int gsh = q.gc == 2 * kCh ? 1 : 0, grp = kGroups >> gsh;     // groups per CTA
+    const int gsh = q.gc == 2 * kCh ? 1 : 0;
     const int ch = q.gc == 8 ? 8 : kCh;                                // channels per slice
+    // gc == 16: four groups per 256-thread CTA, four CTAs per SM (DCNV3_GS_KG=8 selects the 512-thread form)
+    const char *ekg = std::getenv("DCNV3_GS_KG");
+    const int kg = (q.gc == kCh && !(ekg && ekg[0] == '8')) ? 4 : kGroups;
+    const int grp = kg >> gsh;                                         // groups per CTA
     // the tile's nominal tap span must leave at least 2 pixels of offset slack on each side
     const float span = (kTile - 1) + 2 * q.sigma;
     if (!(q.sigma > 0.f) || span + 4 > kWin - 2) return false;
     const int C = q.G * q.gc;
     CUtensorMap tmap_v, tmap_o, tmap_m;
-    if (!make_nhwc_tensor_map(&tmap_v, value, dtype, q.N, q.H, q.W, C, kGroups * ch, kWin, kWin)) return false;
+    if (!make_nhwc_tensor_map(&tmap_v, value, dtype, q.N, q.H, q.W, C, kg * ch, kWin, kWin)) return false;
     Params tp;
     tp.gsh = gsh;
-    tp.o_pitch = grp * kP * 4;                                  // 288 / 144 bytes
-    tp.m_pitch = gsh ? 80 : grp * kP * 2;                       // 144 bytes, or the 72-byte run + up to 8 bytes of shift
+    tp.o_pitch = off_pitch(grp);                                // 288 / 144 bytes
+    tp.m_pitch = msk_pitch(grp);                                // 144 bytes, or the 72-byte run + up to 8 bytes of shift
     if (!make_rows_tensor_map(&tmap_o, offset, dtype, q.N, q.Ho, q.Wo, q.G * kP * 2, tp.o_pitch / 2)) return false;
     if (!make_rows_tensor_map(&tmap_m, mask, dtype, q.N, q.Ho, q.Wo, q.G * kP, tp.m_pitch / 2)) return false;
     const float a_w = (float)(1 - q.pw) - q.sigma, a_h = (float)(1 - q.ph) - q.sigma;
@@ -245,15 +261,16 @@ static bool launch_typed(const void *value, const void *offset, const void *mask
     if (tp.gblocks > 65535) return false;
     const T *v = static_cast<const T *>(value), *o = static_cast<const T *>(offset), *m = static_cast<const T *>(mask);
     T *y = static_cast<T *>(out);
-    auto kern = ch == 8 ? (fast ? fwd_gs<T, true, 0, 8> : fwd_gs<T, false, 0, 8>)
+    auto kern = kg == 4 ? (fast ? fwd_gs<T, true, 0, 16, 4> : fwd_gs<T, false, 0, 16, 4>)
+                : ch == 8 ? (fast ? fwd_gs<T, true, 0, 8> : fwd_gs<T, false, 0, 8>)
                 : gsh   ? (fast ? fwd_gs<T, true, 1, 16> : fwd_gs<T, false, 1, 16>)
                         : (fast ? fwd_gs<T, true, 0, 16> : fwd_gs<T, false, 0, 16>);
-    const int kSmemBytes = smem_bytes(ch);
+    const int kSmemBytes = smem_bytes(ch, kg, gsh);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     for (int n0 = 0; n0 < q.N; n0 += 65535) {
         tp.n0 = n0;
         const dim3 grid((unsigned)(tp.tiles_x * tiles_y), (unsigned)tp.gblocks, (unsigned)std::min(65535, q.N - n0));
-        kern<<<grid, kThreads, kSmemBytes, stream>>>(tmap_v, tmap_o, tmap_m, v, o, m, y, q, tp);
+        kern<<<grid, kPix * kg, kSmemBytes, stream>>>(tmap_v, tmap_o, tmap_m, v, o, m, y, q, tp);
     }
     *err = cudaGetLastError();
     return true;
