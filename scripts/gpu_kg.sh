@@ -2,7 +2,7 @@
 # Four groups per 256-thread CTA (default for gc == 16) against eight per 512-thread CTA (DCNV3_GS_KG=8).
 set -u
 mkdir -p gpurun_out
-DCNV3_GS_KG=4 python -m pytest tests -m gpu -x -q -k "tiled and default and gs_ or cfg2 or fp16 or inside_their" 2>&1 | tail -3
+python -m pytest tests -m gpu -x -q -k "cta_forms or gc32 or inside_their" 2>&1 | tail -3
 for kg in 8 4 8 4; do
   DCNV3_GS_KG=$kg python bench.py --steps 30 --warmup 5 --no-cpu 2>/dev/null | python -c "
 import json,sys

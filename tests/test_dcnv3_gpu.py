@@ -186,6 +186,26 @@ def test_default_kernels_fp16(case, spread):
         assert frac <= (2e-3 if name == "go" else 1e-3), (name, frac, max_abs(a, w), rms)
 
 
+@pytest.mark.parametrize("kg", ["4", "8"])
+@pytest.mark.parametrize("spread", [1.0, 3.0], ids=["near", "far"])
+@pytest.mark.parametrize("case", [c for c in _TILE_CASES if c.name.startswith("gs_") and c.gc == 16], ids=lambda c: c.name)
+def test_group_slice_cta_forms(case, spread, kg, monkeypatch):
+    """gc == 16 has two CTA forms of the group-slice kernels: four groups per 256-thread CTA (the forward's default;
+    72-byte mask runs staged from the 16-byte boundary below, grad_mask copied out by plain stores) and eight groups
+    per 512-thread CTA (the channel sums' default).  DCNV3_GS_KG forces one form for both kernels."""
+    from oracle import dcnv3_oracle as orc
+    monkeypatch.setenv("DCNV3_GS_KG", kg)
+    v, o, m, g = cases.make_inputs(case)
+    arrs = rounded((v, o * spread, m, g), torch.bfloat16)
+    got = run_cuda(arrs, case.geom, dtype=torch.bfloat16)
+    out = orc.direct_forward(*arrs[:3], *case.geom)
+    gv, go, gm = orc.direct_backward(*arrs, *case.geom)
+    for name, a, w in zip(WHAT, got, (out, gv, go, gm)):
+        rms = float(np.sqrt(np.mean(w ** 2))) + 1e-30
+        frac = allclose_frac(a, w, rtol=1e-2, atol=1e-2 * rms)
+        assert frac <= (2e-3 if name == "go" else 1e-3), (name, frac, max_abs(a, w), rms)
+
+
 @pytest.mark.parametrize("dt", ["bf16", "f16"])
 def test_split_weights_forward_is_fp32_accurate(dt, monkeypatch):
     """DCNV3_WEIGHTS=split keeps the bilinear*mask coefficients fp32-accurate: the only error left

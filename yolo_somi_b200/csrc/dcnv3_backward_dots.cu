@@ -245,15 +245,18 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     if (PADM) {
-        // four groups per CTA (gc == 32, or KG == 4): the block's mask run is 72 bytes at a 72-byte pitch -- not a legal TMA box; plain 32-bit stores
-        uint32_t *gmw = reinterpret_cast<uint32_t *>(grad_mask_out);
-        for (int idx = tid; idx < kPix * 18; idx += kThreadsK) {
-            const int pxl = idx / 18, w = idx - pxl * 18;
+        // four groups per CTA (gc == 32, or KG == 4): the block's mask run is 72 bytes at a 72-byte pitch -- not a
+        // legal TMA box; plain 64-bit stores (a run starts on an 8-byte boundary: 72 G0 bytes into a row of 18 G)
+        uint2 *gmw = reinterpret_cast<uint2 *>(grad_mask_out);
+#pragma unroll
+        for (int it = 0; it < (kPix * 9 + kThreadsK - 1) / kThreadsK; ++it) {
+            const int idx = tid + it * kThreadsK;
+            const int pxl = idx / 9, w = idx - pxl * 9;
             const int xo = wo0 + (pxl & 7), yo = ho0 + (pxl >> 3);
-            if (xo < q.Wo && yo < q.Ho) {
-                uint32_t vword;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(vword) : "r"(s_msk + pxl * kMPitch + m_shift + w * 4));
-                gmw[(((((size_t)n * q.Ho + yo) * q.Wo + xo) * q.G + G0) * kP) / 2 + w] = vword;
+            if (idx < kPix * 9 && xo < q.Wo && yo < q.Ho) {
+                uint2 vword;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(vword.x), "=r"(vword.y) : "r"(s_msk + pxl * kMPitch + m_shift + w * 8));
+                gmw[(((((size_t)n * q.Ho + yo) * q.Wo + xo) * q.G + G0) * kP) / 4 + w] = vword;
             }
         }
     }
@@ -269,10 +272,10 @@ static bool launch_typed(const void *value, const void *offset, const void *mask
         return false;
     const int gsh = q.gc == 2 * kCh ? 1 : 0;
     const int ch = q.gc == 8 ? 8 : kCh;                                // channels per slice
-    // DCNV3_GS_KG=4 (gc == 16): four groups per 256-thread CTA, four CTAs per SM -- the forward's default, measured
-    // here at 100.5 us against 99 us for the 512-thread form (grad_mask then leaves by plain stores), so opt-in
+    // gc == 16: four groups per 256-thread CTA, four CTAs per SM, as in the forward (DCNV3_GS_KG=8 selects the
+    // 512-thread form): 99 -> 95 us on cfg2 once the grad_mask copy-out became an unrolled loop of 64-bit stores
     const char *ekg = std::getenv("DCNV3_GS_KG");
-    const int kg = (q.gc == kCh && ekg && ekg[0] == '4') ? 4 : kGroups;
+    const int kg = (q.gc == kCh && !(ekg && ekg[0] == '8')) ? 4 : kGroups;
     const int grp = kg >> gsh;                                         // groups per CTA
     if (((uintptr_t)value | (uintptr_t)grad_out | (uintptr_t)offset | (uintptr_t)mask | (uintptr_t)grad_offset |
          (uintptr_t)grad_mask) % 16)
