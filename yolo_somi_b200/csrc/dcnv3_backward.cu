@@ -491,7 +491,7 @@ static cudaError_t backward_typed(const void *value, const void *offset, const v
         // Default for eligible shapes (gc == 16, G % 8 == 0, 3x3 / stride 1 / dilation 1): the SPLIT backward --
         // channel sums (grad_offset / grad_mask) in the forward's group-slice layout (dcnv3_backward_dots.cu),
         // grad_value as a tcgen05 product with TMEM accumulators (dcnv3_backward_vmma.cu).  The channel-sum
-        // kernel does not touch the fp32 plane, so the plane's memset runs beside it on a side stream.
+        // kernel also zeroes the value kernel's fp32 plane (a slice per CTA while the CTA waits for its window).
         // DCNV3_BWD=strip selects the fused register-accumulator kernel, DCNV3_VALUE=hmma the HMMA value kernel.
         {
             const char *e = std::getenv("DCNV3_BWD");
@@ -499,7 +499,11 @@ static cudaError_t backward_typed(const void *value, const void *offset, const v
             const char *ev = std::getenv("DCNV3_VALUE");
             const bool hmma = ev && ev[0] == 'h';
             if (split && vec_ok && q.G % 8 == 0 && (hmma || backward_vmma_eligible(offset, mask, grad_out, acc, q))) {
-                SideStream *ss = side_stream();
+                // The plane is zeroed by the channel-sum kernel itself (a slice per CTA, while the CTA waits for its
+                // window): no memset launch, no side stream.  DCNV3_ZERO=side keeps the earlier form (memset on a
+                // side stream beside the channel sums, fork / join with events).
+                const char *ez = std::getenv("DCNV3_ZERO");
+                SideStream *ss = (ez && ez[0] == 's') ? side_stream() : nullptr;
                 cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
                 if (ss) {   // fork: memset of the plane || channel sums
                     // (the events are per device, not per call: record + wait must not interleave with another
@@ -511,11 +515,12 @@ static cudaError_t backward_typed(const void *value, const void *offset, const v
                     if ((err = cudaMemsetAsync(acc, 0, plane * sizeof(float), ss->stream)) != cudaSuccess) return err;
                     if ((err = cudaEventRecord(ss->join, ss->stream)) != cudaSuccess) return err;
                 }
-                const bool dots = try_launch_backward_dots(value, offset, mask, grad_out, grad_offset, grad_mask, q, dtype_tag, stream, &e1);
+                const bool dots = try_launch_backward_dots(value, offset, mask, grad_out, grad_offset, grad_mask, q, dtype_tag, stream, &e1,
+                                                           ss ? nullptr : acc, ss ? 0 : plane * sizeof(float));
                 if (ss) {   // join (also when the channel-sum kernel declined: the plane is needed either way)
                     if ((err = cudaStreamWaitEvent(stream, ss->join, 0)) != cudaSuccess) return err;
-                } else if ((err = cudaMemsetAsync(acc, 0, plane * sizeof(float), stream)) != cudaSuccess) {
-                    return err;
+                } else if (!dots && (err = cudaMemsetAsync(acc, 0, plane * sizeof(float), stream)) != cudaSuccess) {
+                    return err;   // (the channel-sum kernel declined: nobody has zeroed the plane yet)
                 }
                 if (dots) {
                     if (e1 != cudaSuccess) return e1;

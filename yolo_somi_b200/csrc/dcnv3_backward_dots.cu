@@ -53,6 +53,10 @@ struct Params {
     // and add their partial channel sums); a CTA's 8 slices are then 4 groups
     int gsh;                 // log2(slices per group): 0 or 1
     int o_pitch, m_pitch;    // staged offset / mask bytes per pixel
+    // the fp32 plane the value kernel reduces into is zeroed HERE, a slice per CTA, while the CTA waits for its
+    // window (no separate memset, no side stream): 16-byte units per CTA / in all
+    unsigned zero_per_cta;
+    unsigned long long zero_total;
 };
 
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
@@ -87,8 +91,8 @@ __global__ void __launch_bounds__(kPix * KG, KG == 4 ? 4 : CH == 8 ? 3 : 2)
 bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
          const __grid_constant__ CUtensorMap tmap_m, const __grid_constant__ CUtensorMap tmap_go,
          const __grid_constant__ CUtensorMap tmap_gm, const T *__restrict__ value, const T *__restrict__ offset,
-         const T *__restrict__ mask, const T *__restrict__ grad_out, T *__restrict__ grad_mask_out, const Geom q,
-         const Params tp) {
+         const T *__restrict__ mask, const T *__restrict__ grad_out, T *__restrict__ grad_mask_out,
+         float4 *__restrict__ zero_dst, const Geom q, const Params tp) {
     constexpr int E = 8;
     constexpr int kCellBytes = cell_bytes(CH, KG), kWinBytes = win_bytes(CH, KG);
     constexpr int kOPitch = off_pitch(KG >> GSH), kMPitch = msk_pitch(KG >> GSH), kOffBytes = kPix * kOPitch;
@@ -147,6 +151,13 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
         const T *gp = grad_out + (((size_t)n * q.Ho + ho) * q.Wo + wo) * (size_t)C + (g0 + g) * CH;
         gq_a = __ldg(reinterpret_cast<const uint4 *>(gp + half * E));
         if (TWO) gq_b = __ldg(reinterpret_cast<const uint4 *>(gp + (half ^ 1) * E));
+    }
+
+    if (zero_dst) {   // this CTA's slice of the fp32 plane (independent of everything else the kernel does)
+        const unsigned long long cta = blockIdx.x + (unsigned long long)gridDim.x * (blockIdx.y + (unsigned long long)gridDim.y * blockIdx.z);
+        const unsigned long long b = cta * tp.zero_per_cta;
+        const unsigned long long e = b + tp.zero_per_cta < tp.zero_total ? b + tp.zero_per_cta : tp.zero_total;
+        for (unsigned long long i = b + tid; i < e; i += kThreadsK) zero_dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 
     mbar_wait(&bar, 0);
@@ -266,7 +277,7 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
 template <typename T>
 static bool launch_typed(const void *value, const void *offset, const void *mask, const void *grad_out,
                          void *grad_offset, void *grad_mask, const Geom &q, int dtype, cudaStream_t stream,
-                         cudaError_t *err) {
+                         cudaError_t *err, float *zero_plane, size_t zero_bytes) {
     if (!(((q.gc == kCh || q.gc == 8) && q.G % kGroups == 0) || (q.gc == 2 * kCh && q.G % (kGroups / 2) == 0)) || q.kh != 3 ||
         q.kw != 3 || q.sh != 1 || q.sw != 1 || q.dh != 1 || q.dw != 1)
         return false;
@@ -306,9 +317,15 @@ static bool launch_typed(const void *value, const void *offset, const void *mask
     for (int n0 = 0; n0 < q.N; n0 += 65535) {
         tp.n0 = n0;
         const dim3 grid((unsigned)(tp.tiles_x * tiles_y), (unsigned)tp.gblocks, (unsigned)std::min(65535, q.N - n0));
+        // the first launch zeroes the whole plane, a slice per CTA
+        const bool zero = n0 == 0 && zero_plane && zero_bytes;
+        const unsigned long long ctas = (unsigned long long)grid.x * grid.y * grid.z;
+        tp.zero_total = zero ? zero_bytes / 16 : 0;
+        tp.zero_per_cta = zero ? (unsigned)((tp.zero_total + ctas - 1) / ctas) : 0;
         kern<<<grid, kPix * kg, kSmemBytes, stream>>>(tv, to, tm, tgo, tgm, static_cast<const T *>(value),
                                                      static_cast<const T *>(offset), static_cast<const T *>(mask),
-                                                     static_cast<const T *>(grad_out), static_cast<T *>(grad_mask), q, tp);
+                                                     static_cast<const T *>(grad_out), static_cast<T *>(grad_mask),
+                                                     zero ? reinterpret_cast<float4 *>(zero_plane) : nullptr, q, tp);
     }
     *err = cudaGetLastError();
     return true;
@@ -319,10 +336,11 @@ static bool launch_typed(const void *value, const void *offset, const void *mask
 // grad_offset / grad_mask only.  Returns false if the shape is not eligible.
 bool try_launch_backward_dots(const void *value, const void *offset, const void *mask, const void *grad_out,
                               void *grad_offset, void *grad_mask, const Geom &q, int dtype, cudaStream_t stream,
-                              cudaError_t *err) {
+                              cudaError_t *err, float *zero_plane, size_t zero_bytes) {
     if ((long long)q.N * q.Ho * q.Wo == 0) return false;
-    if (dtype == 1) return bdots::launch_typed<__half>(value, offset, mask, grad_out, grad_offset, grad_mask, q, dtype, stream, err);
-    if (dtype == 2) return bdots::launch_typed<__nv_bfloat16>(value, offset, mask, grad_out, grad_offset, grad_mask, q, dtype, stream, err);
+    if (zero_bytes % 16 || (uintptr_t)zero_plane % 16) return false;
+    if (dtype == 1) return bdots::launch_typed<__half>(value, offset, mask, grad_out, grad_offset, grad_mask, q, dtype, stream, err, zero_plane, zero_bytes);
+    if (dtype == 2) return bdots::launch_typed<__nv_bfloat16>(value, offset, mask, grad_out, grad_offset, grad_mask, q, dtype, stream, err, zero_plane, zero_bytes);
     return false;
 }
 

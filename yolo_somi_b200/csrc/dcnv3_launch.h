@@ -41,9 +41,11 @@ bool try_launch_backward_strip(const void *value, const void *offset, const void
                                const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err);
 
 // split backward: grad_offset / grad_mask (dcnv3_backward_dots.cu) + grad_value (value-only strip kernel)
+// (`zero_plane` / `zero_bytes`: if given, the kernel also zeroes that buffer -- the value kernel's fp32 plane --
+// a slice per CTA while the CTA waits for its inputs)
 bool try_launch_backward_dots(const void *value, const void *offset, const void *mask, const void *grad_out,
                               void *grad_offset, void *grad_mask, const Geom &q, int dtype, cudaStream_t stream,
-                              cudaError_t *err);
+                              cudaError_t *err, float *zero_plane = nullptr, size_t zero_bytes = 0);
 bool try_launch_backward_vstrip(const void *offset, const void *mask, const void *grad_out, float *gv_acc,
                                 const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err);
 // grad_value as a tcgen05 product with TMEM accumulators (dcnv3_backward_vmma.cu)
