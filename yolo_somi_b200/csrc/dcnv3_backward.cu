@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(256)
 narrow_f32_kernel(const float *__restrict__ src, T *__restrict__ dst, size_t n) {
     // 8 elements per thread per step: two 128-bit loads, one 128-bit store (src/dst 16-byte aligned)
     // back to front: the accumulating kernels work image-major, so the END of the plane is what is still in L2
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // (a no-op unless launched as a programmatic dependent)
     const size_t n8 = n / 8;
     for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n8; j += (size_t)gridDim.x * blockDim.x) {
         const size_t i = n8 - 1 - j;
@@ -527,7 +528,8 @@ static cudaError_t backward_typed(const void *value, const void *offset, const v
                     if ((!hmma && try_launch_backward_vmma(offset, mask, grad_out, acc, q, dtype_tag, stream, &e2)) ||
                         try_launch_backward_vstrip(offset, mask, grad_out, acc, q, dtype_tag, stream, &e2)) {
                         if (e2 != cudaSuccess) return e2;
-                        narrow_f32_kernel<T><<<aux_blocks, 256, 0, stream>>>(acc, gv, plane);
+                        if ((err = pdl_launch(narrow_f32_kernel<T>, dim3(aux_blocks), dim3(256), 0, stream,
+                                              static_cast<const float *>(acc), gv, plane)) != cudaSuccess) return err;
                         return cudaGetLastError();
                     }
                 }

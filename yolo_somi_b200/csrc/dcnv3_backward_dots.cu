@@ -153,6 +153,9 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
         if (TWO) gq_b = __ldg(reinterpret_cast<const uint4 *>(gp + (half ^ 1) * E));
     }
 
+    // the value kernel (launched with programmatic stream serialisation) may start its prologue and input loads as
+    // soon as every CTA of this grid has started; it waits for this grid's completion before it touches the plane
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (zero_dst) {   // this CTA's slice of the fp32 plane (independent of everything else the kernel does)
         const unsigned long long cta = blockIdx.x + (unsigned long long)gridDim.x * (blockIdx.y + (unsigned long long)gridDim.y * blockIdx.z);
         const unsigned long long b = cta * tp.zero_per_cta;

@@ -295,6 +295,8 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
     if (tid == 0) request(0, n, g, wo0, ho0);
 
     unsigned commits = 0;
+    bool dep_waited = false;   // programmatic dependent launch: the plane (zeroed by the channel-sum kernel) is first
+                               // touched by this CTA's first A build (far points) / drain -- wait for that grid there
     for (;;) {
         const int t_next = t + gridDim.x;
         const bool has_next = t_next < pp.total_tiles;
@@ -343,6 +345,10 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
             // ---- A build: the pixel's 36 coefficients into its column of the strip's tile
             mbar_wait(&zero_bar, fills & 1u);
             ++fills;
+            if (!dep_waited) {
+                asm volatile("griddepcontrol.wait;" ::: "memory");
+                dep_waited = true;
+            }
             if (live && par == 0) {
                 const float bw = axis_base(wo, 3, 1, q.pw, 1, q.sigma) - (float)band_x0;
                 const float bh = axis_base(ho, 3, 1, q.ph, 1, q.sigma) - (float)band_y0;
@@ -427,6 +433,7 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
         t = t_next;
     }
 
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the narrowing pass may be scheduled
     mbar_wait(&zero_bar, fills & 1u);   // the last refill must land before the CTA's memory is released
     tc_fence_before();
     __syncthreads();
@@ -467,15 +474,15 @@ static bool launch_typed(const void *offset, const void *mask, const void *grad_
     const int ctas = (int)std::min<long long>(total, (long long)kCtasPerSm * num_sms);
     if (q.gc == 8) {
         cudaFuncSetAttribute(bwd_vmma<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(16));
-        bwd_vmma<T, 8><<<ctas, kThreadsV, smem_bytes(16), stream>>>(to, tm, tg, gv_acc, q, pp);
+        *err = pdl_launch(bwd_vmma<T, 8>, dim3(ctas), dim3(kThreadsV), smem_bytes(16), stream, to, tm, tg, gv_acc, q, pp);
     } else if (q.gc == 16) {
         cudaFuncSetAttribute(bwd_vmma<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(16));
-        bwd_vmma<T, 16><<<ctas, kThreadsV, smem_bytes(16), stream>>>(to, tm, tg, gv_acc, q, pp);
+        *err = pdl_launch(bwd_vmma<T, 16>, dim3(ctas), dim3(kThreadsV), smem_bytes(16), stream, to, tm, tg, gv_acc, q, pp);
     } else {
         cudaFuncSetAttribute(bwd_vmma<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(32));
-        bwd_vmma<T, 32><<<ctas, kThreadsV, smem_bytes(32), stream>>>(to, tm, tg, gv_acc, q, pp);
+        *err = pdl_launch(bwd_vmma<T, 32>, dim3(ctas), dim3(kThreadsV), smem_bytes(32), stream, to, tm, tg, gv_acc, q, pp);
     }
-    *err = cudaGetLastError();
+    if (*err == cudaSuccess) *err = cudaGetLastError();
     return true;
 }
 

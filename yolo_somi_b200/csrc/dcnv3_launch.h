@@ -1,6 +1,7 @@
 // dcnv3_launch.h -- internal host-side entry points shared by the C ABI (dcnv3_capi.cu).
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stddef.h>
 
 #include "dcnv3_common.cuh"
@@ -56,6 +57,25 @@ bool try_launch_backward_vmma(const void *offset, const void *mask, const void *
 bool try_launch_backward_mma2(const void *value, const void *offset, const void *mask,
                               const void *grad_out, float *gv_acc, void *grad_offset, void *grad_mask,
                               const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err);
+
+// Programmatic dependent launch (PDL) between the kernels of the split backward: a kernel launched with
+// `pdl_launch` may start (prologue, loads of tensors no earlier kernel of the call writes) while the previous
+// kernel of the stream drains; it executes griddepcontrol.wait before it touches what that kernel produced.
+// DCNV3_PDL=0 launches everything fully serialised.
+inline bool pdl_enabled() {
+    static const bool on = [] { const char *e = std::getenv("DCNV3_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t pdl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 
 size_t backward_workspace_bytes(const Geom &q, int dtype, unsigned flags);
 
