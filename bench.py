@@ -434,7 +434,7 @@ def run_ours(args, rank, world, local_rank):
                 "api": "dcnv3_host_pipeline_run (C ABI, pinned host buffers, 8-image chunks, H2D | kernels | D2H on three streams)",
                 "timing": "host clock around enqueue + drain of all steps (the pipeline owns its streams)"},
         "gpu_launches": 4 * args.steps,   # fwd_gs, bwd_dots, bwd_vmma, narrow_f32 (the memset is the driver's)
-        "roofline": {"bound": "hbm", "kernel": "backward pass: bdots::bwd_dots + vmma::bwd_vmma (tcgen05 / TMEM) + narrow_f32 (the fp32 plane's memset runs beside bwd_dots)",
+        "roofline": {"bound": "hbm", "kernel": "backward pass: bdots::bwd_dots (also zeroes the fp32 plane) + vmma::bwd_vmma (tcgen05 / TMEM) + narrow_f32, chained by programmatic dependent launch",
                      "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes": ab["bwd"], "avg_ms": bwd_t * 1e3},
