@@ -49,6 +49,12 @@
 #include <cstdlib>
 #include <type_traits>
 
+// Diagnostic builds only (scripts/gpu_vdiag.sh; results are WRONG, the timing shows what a phase costs):
+// -DVMMA_DIAG=1 no scatter into the A tile, 2 no zero refill, 3 no reductions in the drain, 4 no tcgen05.mma
+#ifndef VMMA_DIAG
+#define VMMA_DIAG 0
+#endif
+
 namespace dcnv3 {
 namespace vmma {
 
@@ -153,6 +159,7 @@ __device__ __forceinline__ void drain_cells(const float (&r)[16], int lane, floa
     }
     // even lane: E[0:4] own, O[0:4] recv, E[8:12] own, O[8:12] recv; odd lane: E[4:8] recv, O[4:8] own, E[12:16] recv, O[12:16] own
     float *pe = p_even + (odd ? 4 : 0), *po = p_even + C + (odd ? 4 : 0);
+    if (VMMA_DIAG == 3) { ok_even = ok_even && rv[0] == 12345.678f; ok_odd = ok_odd && rv[1] == 12345.678f; }
     if (ok_even) {
         red_add4(pe, odd ? make_float4(rv[0], rv[1], rv[2], rv[3]) : make_float4(r[0], r[1], r[2], r[3]));
         red_add4(pe + 8, odd ? make_float4(rv[4], rv[5], rv[6], rv[7]) : make_float4(r[8], r[9], r[10], r[11]));
@@ -219,7 +226,7 @@ __global__ void __launch_bounds__(kThreadsV, kCtasPerSm)
 bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ CUtensorMap tmap_msk,
          const __grid_constant__ CUtensorMap tmap_gout, float *__restrict__ gv_acc, const Geom q, const VParams pp) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t mma_bar, zero_bar, full_bar[kStages];
+    __shared__ __align__(8) uint64_t mma_bar, mma_bar1, zero_bar, full_bar[kStages];
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -270,6 +277,7 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
 
     if (tid == 0) {
         mbar_init(&mma_bar, 1);
+        mbar_init(&mma_bar1, 1);
         mbar_init(&zero_bar, 1);
         for (int i = 0; i < kStages; ++i) mbar_init(&full_bar[i], 1);
         fence_barrier_init();
@@ -363,6 +371,7 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                     // 0 <= x < limit on the float's bit pattern: negative values and NaN compare as large unsigned
                     if (__float_as_uint(ub) < __float_as_uint((float)(kBandW - 1)) &&
                         __float_as_uint(vb) < __float_as_uint((float)(kBandH - 1))) {
+                        if (VMMA_DIAG == 1) continue;
                         const uint32_t cx = (uint32_t)(int)fw, ry = (uint32_t)(int)fh;
                         const float hm = (1.f - lh) * m, lm = lh * m, hwt = 1.f - lw;
                         const uint32_t e0 = a_thr + (ry * kBandW + cx) * 128u + ((kc ^ (cx & 7u)) << 4);
@@ -408,24 +417,33 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                         const uint32_t aa = a_addr0 + st * kATileBytes + blk * kBlockBytes;
                         const uint32_t bb = smem_u32(stages) + stage * kStBytes + st * kStStrip + kStGout;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)   // K step = 16 pixels: 32 B of an A row, 256 B of the pixel-major B
+                        for (int j = 0; j < (VMMA_DIAG == 4 ? 0 : 4); ++j)   // K step = 16 pixels: 32 B of an A row, 256 B of the pixel-major B
                             tc_mma(d, umma_desc_k_sw128(aa + j * 32), umma_desc_mn_plain(bb + j * 256, 128, 1024), idesc,
                                    (uint32_t)(j > 0 || (blk == 0 && s > 0)));
+                        // the UPPER block (the one drained below) completes first: its own commit, so that the drain
+                        // starts while the lower block's products still run
+                        tc_commit(blk == 0 ? &mma_bar : &mma_bar1);
                     }
-                tc_commit(&mma_bar);
             }
             mbar_wait(&mma_bar, commits & 1u);
-            ++commits;
             tc_fence_after();
 
-            if (tid == 0) {   // the tensor core is done with the tiles: refill them with zeros
-                mbar_expect_tx(&zero_bar, kStrips * kATileBytes);
-                bulk_fill(a_addr0, g_zero_tile, kStrips * kATileBytes, &zero_bar);
+            if (tid == 0) {   // the tensor core is done with the tiles (both blocks): refill them with zeros
+                mbar_wait(&mma_bar1, commits & 1u);
+                if (VMMA_DIAG == 2) {
+                    mbar_expect_tx(&zero_bar, 0);
+                } else {
+                    mbar_expect_tx(&zero_bar, kStrips * kATileBytes);
+                    bulk_fill(a_addr0, g_zero_tile, kStrips * kATileBytes, &zero_bar);
+                }
             }
+            ++commits;
             // ---- the band's upper block is final: reductions
             drain_block<NCH>(tmem_base, s & 1, warp, lane, gv_img, band_y0, wo0 + pp.bx_rel, q.H, q.W, row_stride, C, g & 1);
         }
-        // ---- the last step's lower block
+        // ---- the last step's lower block (its products have their own barrier, which only thread 0 has waited on)
+        mbar_wait(&mma_bar1, (commits - 1u) & 1u);
+        tc_fence_after();
         drain_block<NCH>(tmem_base, pp.steps & 1, warp, lane, gv_img, ho0 + (pp.steps - 1) * kRows + pp.by_rel + 8,
                     wo0 + pp.bx_rel, q.H, q.W, row_stride, C, g & 1);
         if (!has_next) break;
