@@ -528,7 +528,7 @@ static cudaError_t backward_typed(const void *value, const void *offset, const v
                     if ((!hmma && try_launch_backward_vmma(offset, mask, grad_out, acc, q, dtype_tag, stream, &e2)) ||
                         try_launch_backward_vstrip(offset, mask, grad_out, acc, q, dtype_tag, stream, &e2)) {
                         if (e2 != cudaSuccess) return e2;
-                        if ((err = pdl_launch(narrow_f32_kernel<T>, dim3(aux_blocks), dim3(256), 0, stream,
+                        if ((err = pdl_launch(pdl_for(q), narrow_f32_kernel<T>, dim3(aux_blocks), dim3(256), 0, stream,
                                               static_cast<const float *>(acc), gv, plane)) != cudaSuccess) return err;
                         return cudaGetLastError();
                     }

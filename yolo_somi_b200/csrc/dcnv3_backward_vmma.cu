@@ -492,13 +492,13 @@ static bool launch_typed(const void *offset, const void *mask, const void *grad_
     const int ctas = (int)std::min<long long>(total, (long long)kCtasPerSm * num_sms);
     if (q.gc == 8) {
         cudaFuncSetAttribute(bwd_vmma<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(16));
-        *err = pdl_launch(bwd_vmma<T, 8>, dim3(ctas), dim3(kThreadsV), smem_bytes(16), stream, to, tm, tg, gv_acc, q, pp);
+        *err = pdl_launch(pdl_for(q), bwd_vmma<T, 8>, dim3(ctas), dim3(kThreadsV), smem_bytes(16), stream, to, tm, tg, gv_acc, q, pp);
     } else if (q.gc == 16) {
         cudaFuncSetAttribute(bwd_vmma<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(16));
-        *err = pdl_launch(bwd_vmma<T, 16>, dim3(ctas), dim3(kThreadsV), smem_bytes(16), stream, to, tm, tg, gv_acc, q, pp);
+        *err = pdl_launch(pdl_for(q), bwd_vmma<T, 16>, dim3(ctas), dim3(kThreadsV), smem_bytes(16), stream, to, tm, tg, gv_acc, q, pp);
     } else {
         cudaFuncSetAttribute(bwd_vmma<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(32));
-        *err = pdl_launch(bwd_vmma<T, 32>, dim3(ctas), dim3(kThreadsV), smem_bytes(32), stream, to, tm, tg, gv_acc, q, pp);
+        *err = pdl_launch(pdl_for(q), bwd_vmma<T, 32>, dim3(ctas), dim3(kThreadsV), smem_bytes(32), stream, to, tm, tg, gv_acc, q, pp);
     }
     if (*err == cudaSuccess) *err = cudaGetLastError();
     return true;

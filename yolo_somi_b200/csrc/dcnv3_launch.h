@@ -61,19 +61,21 @@ bool try_launch_backward_mma2(const void *value, const void *offset, const void 
 // Programmatic dependent launch (PDL) between the kernels of the split backward: a kernel launched with
 // `pdl_launch` may start (prologue, loads of tensors no earlier kernel of the call writes) while the previous
 // kernel of the stream drains; it executes griddepcontrol.wait before it touches what that kernel produced.
-// DCNV3_PDL=0 launches everything fully serialised.
+// DCNV3_PDL=0 launches everything fully serialised.  Measured (profiles/README.md): -3 us per backward pass for
+// group_channels 16 / 32, but +25 us for group_channels == 8 (cfg5, G = 32), where it therefore stays off.
+inline bool pdl_for(const Geom &q) { return q.gc != 8; }
 inline bool pdl_enabled() {
     static const bool on = [] { const char *e = std::getenv("DCNV3_PDL"); return !(e && e[0] == '0'); }();
     return on;
 }
 template <typename... KArgs, typename... Args>
-inline cudaError_t pdl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+inline cudaError_t pdl_launch(bool allow, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = allow && pdl_enabled() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
