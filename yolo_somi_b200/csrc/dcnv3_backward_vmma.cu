@@ -151,6 +151,14 @@ __device__ __noinline__ void far_point(float *gv_img, int H, int W, int row_stri
 // lanes of a pair write the two halves of ONE sector in the same instruction (whole-sector reductions).
 __device__ __forceinline__ void drain_cells(const float (&r)[16], int lane, float *p_even, bool ok_even, bool ok_odd, int C) {
     const bool odd = lane & 1;
+    // a cell nobody sampled (the band's outer columns / rows mostly) holds exact zeros: nothing to reduce.
+    // (0 x Inf / NaN in grad_out gives NaN != 0, so a poisoned neighbourhood is still written.)
+    bool nz = false;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) nz |= r[j] != 0.f;
+    const bool nz_other = __shfl_xor_sync(0xffffffffu, (int)nz, 1) != 0;
+    ok_even = ok_even && (odd ? nz_other : nz);
+    ok_odd = ok_odd && (odd ? nz : nz_other);
     float rv[8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -184,7 +192,10 @@ __device__ __forceinline__ void drain_block(uint32_t tmem_base, int slot, int wa
         float r[8];
         VMMA_TMEM_LD_8(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(slot * 16 + gsel * 8), r);
         tmem_ld_wait();
-        if ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W) {
+        bool nz = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) nz |= r[j] != 0.f;
+        if (nz && (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W) {
             float *p = gv_img + (ptrdiff_t)y * row_stride + (ptrdiff_t)x * C;
             red_add4(p, make_float4(r[0], r[1], r[2], r[3]));
             red_add4(p + 4, make_float4(r[4], r[5], r[6], r[7]));
