@@ -14,12 +14,12 @@ Unit of work: one sampled point (n,ho,wo,g,p); a step processes N*Ho*Wo*G*9 = 14
   e2e        same metric through the public API with HOST (pinned) buffers: H2D of the four inputs
              and D2H of the four results inside the timed region
   roofline   backward pass (the dominant launches), algorithmic bytes / event time vs measured HBM
-  cpu_baseline  the oracle's grid_sample port of dcnv3_core_pytorch on this box's host cores,
-             bounded sample (rank 0, N=1 only)
+  cpu_baseline  the reference's dcnv3_core_pytorch (baseline/_ref, else the oracle's port) on this box's host cores,
+             the full workload, a few passes (rank 0, N=1 only)
 
 Multi-GPU: the batch shards over ranks with no data-path collective -> weak scaling.
-`--impl reference` times the reference's CPU path (oracle port; the Python reference cannot travel
-to the GPU box) on the host cores, rank 0 only.
+`--impl reference` times the reference's own CPU path -- the unmodified dcnv3_core_pytorch from the verbatim copy
+staged under git-ignored baseline/_ref/ (scripts/stage_reference.py) -- on all 16 images, host cores, rank 0 only.
 """
 from __future__ import annotations
 
@@ -184,44 +184,57 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_run(sample_n, repeats):
-    """The reference's CPU path (oracle port of dcnv3_core_pytorch, fp32) on `sample_n` images of
-    the workload; returns best seconds per fwd+bwd and the thread count."""
+def cpu_reference_fn():
+    """The reference's own CPU path: UNMODIFIED dcnv3_core_pytorch (functions/dcnv3_func.py:147-188) from the verbatim
+    copy staged under git-ignored baseline/_ref/ (scripts/stage_reference.py; it travels with the snapshot).  Only if
+    that copy is absent: the oracle's restatement of the same function (kind "port")."""
+    from baseline import ref_loader
+    if ref_loader.available():
+        core = ref_loader.core_pytorch()
+
+        def fwd_bwd(v, o, m, g, *geo):
+            v = v.clone().requires_grad_(True); o = o.clone().requires_grad_(True); m = m.clone().requires_grad_(True)
+            out = core(v, o, m, *geo)
+            out.backward(g)
+            return out, v.grad, o.grad, m.grad
+        return fwd_bwd, "reference", "unmodified dcnv3_core_pytorch from baseline/_ref (grid_sample + autograd)"
     from oracle import dcnv3_oracle as orc
+    return orc.gridsample_fwd_bwd, "port", "oracle port of dcnv3_core_pytorch (grid_sample + autograd)"
+
+
+def cpu_reference_run(sample_n, repeats, warm=1):
+    """fwd+bwd of the CPU reference (fp32 arithmetic on the bf16-rounded inputs of the workload) on `sample_n` images;
+    returns (list of seconds per pass, threads, kind, description)."""
+    fn, kind, desc = cpu_reference_fn()
     torch.set_num_threads(os.cpu_count() or 1)
     v, o, m, g = make_inputs(sample_n, "cpu", torch.bfloat16, seed=1234)
     v, o, m, g = (t.float() for t in (v, o, m, g))     # bf16-rounded values, fp32 arithmetic
-    best = float("inf")
-    for i in range(repeats + 1):                       # first pass is warm-up
+    times = []
+    for i in range(warm + repeats):
         t0 = time.perf_counter()
-        orc.gridsample_fwd_bwd(v, o, m, g, *geom())
+        fn(v, o, m, g, *geom())
         dt = time.perf_counter() - t0
-        if i:
-            best = min(best, dt)
-    return best, torch.get_num_threads()
+        if i >= warm:
+            times.append(dt)
+    return times, torch.get_num_threads(), kind, desc
 
 
 def run_reference_arm(args, rank, world):
+    """`--impl reference`: the reference's CPU implementation of the path on ALL images of the workload
+    (N = 16, same shape: same_config), every host thread, rank 0 only."""
     if rank != 0:
         return
-    sample_n = 2
-    times = []
-    threads = 1
-    for i in range(args.warmup + args.steps):
-        t, threads = cpu_reference_run(sample_n, 1)
-        if i >= args.warmup:
-            times.append(t)
+    n = CFG["N"]
+    times, threads, kind, desc = cpu_reference_run(n, args.steps, warm=args.warmup)
     total = sum(times)
-    val = points_per_step(sample_n) * len(times) / total
-    sample = (f"{sample_n} of {CFG['N']} images per step (same shape, fp32 arithmetic on bf16-rounded "
-              f"inputs), oracle port of dcnv3_core_pytorch (grid_sample + autograd)")
+    val = points_per_step(n) * len(times) / total
+    sample = f"all {n} images per step (the full workload, fp32 arithmetic on bf16-rounded inputs), {desc}"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": sample},
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample, "same_config": True},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -446,11 +459,12 @@ def run_ours(args, rank, world, local_rank):
     if proj is not None:
         line["next_rows"] = {"offset_mask_proj": proj, "layer": layer}
     if world == 1 and not args.no_cpu:
-        t, threads = cpu_reference_run(2, 3)
+        # the CPU reference beside the GPU number, same run, same box: the full workload (all 16 images), 5 passes
+        times, threads, kind, desc = cpu_reference_run(CFG["N"], 5)
         line["cpu_baseline"] = {
-            "value": points_per_step(2) / t, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "2 of 16 images (same shape), fp32 on bf16-rounded inputs, best of 3, oracle "
-                      "port of dcnv3_core_pytorch (grid_sample fwd + autograd bwd)"}
+            "value": points_per_step() / min(times), "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"all {CFG['N']} images (the full workload), fp32 on bf16-rounded inputs, best of 5 after 1 warm-up "
+                      f"({sum(times):.1f} s of CPU work), {desc}"}
     print(json.dumps(line))
 
 

@@ -171,3 +171,28 @@ def test_two_rank_gloo_aggregation():
     assert res[0][:2] == (0, 9) and res[1][:2] == (9, 17)
     for r in range(world):
         assert res[r][2] == pytest.approx(17 / 2.0) and res[r][3] == 2.0
+
+
+# ----------------------------------------------------------------------------- ONNX symbolic
+def test_symbolic_emits_the_reference_node():
+    """DCNv3Function.symbolic (reference dcnv3_func.py:63-89): node `mmdeploy::TRTDCNv3`, three tensor inputs, eleven
+    integer attributes (`_i`) and `offset_scale_f`, exactly the reference's names."""
+    from yolo_somi_b200.ops_dcnv3.functions import DCNv3Function
+
+    class G:
+        def op(self, name, *inputs, **attrs):
+            self.call = (name, inputs, attrs)
+            return "node"
+    g = G()
+    out = DCNv3Function.symbolic(g, "x", "off", "msk", 3, 3, 1, 1, 1, 1, 1, 1, 4, 16, 2.0, 256)
+    name, inputs, attrs = g.call
+    assert out == "node" and name == "mmdeploy::TRTDCNv3" and inputs == ("x", "off", "msk")
+    assert attrs == dict(kernel_h_i=3, kernel_w_i=3, stride_h_i=1, stride_w_i=1, pad_h_i=1, pad_w_i=1,
+                         dilation_h_i=1, dilation_w_i=1, group_i=4, group_channels_i=16, offset_scale_f=2.0,
+                         im2col_step_i=256)
+    from baseline import ref_loader
+    if ref_loader.available():          # the reference's own symbolic, fed the same arguments
+        RefFn, _, _ = ref_loader.dropin()
+        g2 = G()
+        RefFn.symbolic(g2, "x", "off", "msk", 3, 3, 1, 1, 1, 1, 1, 1, 4, 16, 2.0, 256)
+        assert g2.call == g.call

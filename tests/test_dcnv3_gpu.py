@@ -136,8 +136,10 @@ _TILE_CASES = [
 ]
 
 
-@pytest.mark.parametrize("fwd", ["default", "tile", "mma"])
-@pytest.mark.parametrize("bwd", ["default", "strip", "mma", "tile", "scatter", "mma2"])
+# (kernels under csrc/experiments/ -- forward "mma", backward "tile" / "mma2" / value kernel "band" -- are not in the
+# default build; with DCNV3_BUILD_EXPERIMENTS=1 they are selected by the same knobs and covered by scripts/vband_check.py)
+@pytest.mark.parametrize("fwd", ["default", "tile"])
+@pytest.mark.parametrize("bwd", ["default", "strip", "mma", "scatter"])
 @pytest.mark.parametrize("spread", [1.0, 4.0], ids=["near", "far"])
 @pytest.mark.parametrize("case", _TILE_CASES, ids=lambda c: c.name)
 def test_tiled_kernels_vs_oracle(case, spread, bwd, fwd, monkeypatch):

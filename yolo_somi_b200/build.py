@@ -20,7 +20,13 @@ INCLUDE = PKG.parent / "include"
 LIB = PKG / "libdcnv3_sm100.so"
 OBJ_DIR = PKG / "csrc" / "_obj"
 
-SOURCES = ["dcnv3_forward.cu", "dcnv3_forward_tile.cu", "dcnv3_forward_gs.cu", "dcnv3_forward_mma.cu", "dcnv3_backward.cu", "dcnv3_backward_tile.cu", "dcnv3_backward_mma.cu", "dcnv3_backward_mma2.cu", "dcnv3_backward_strip.cu", "dcnv3_backward_dots.cu", "dcnv3_backward_vmma.cu", "dcnv3_host_pipeline.cu", "dcnv3_proj.cu", "dcnv3_dwconv.cu", "dcnv3_capi.cu"]
+SOURCES = ["dcnv3_forward.cu", "dcnv3_forward_tile.cu", "dcnv3_forward_gs.cu", "dcnv3_backward.cu", "dcnv3_backward_mma.cu",
+           "dcnv3_backward_strip.cu", "dcnv3_backward_dots.cu", "dcnv3_backward_vmma.cu", "dcnv3_host_pipeline.cu",
+           "dcnv3_proj.cu", "dcnv3_dwconv.cu", "dcnv3_capi.cu"]
+# measured alternatives that lost to the defaults (profiles/README.md): built only on request
+EXPERIMENTS = ["experiments/dcnv3_forward_mma.cu", "experiments/dcnv3_backward_mma2.cu", "experiments/dcnv3_backward_tile.cu",
+               "experiments/dcnv3_backward_vband.cu"]
+WITH_EXPERIMENTS = os.environ.get("DCNV3_BUILD_EXPERIMENTS", "0") not in ("", "0")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",   # no --use_fast_math: IEEE div/sqrt, denormals kept
@@ -35,7 +41,7 @@ def _nvcc() -> str:
 
 
 def _deps() -> list[Path]:
-    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + \
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("experiments/*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + \
         sorted(INCLUDE.glob("*.h"))
 
 
@@ -52,9 +58,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     nvcc = _nvcc()
     OBJ_DIR.mkdir(exist_ok=True)
 
+    sources = SOURCES + (EXPERIMENTS if WITH_EXPERIMENTS else [])
+    flags = NVCC_FLAGS + (["-DDCNV3_EXPERIMENTS"] if WITH_EXPERIMENTS else [])
+
     def compile_one(src: str) -> Path:
         obj = OBJ_DIR / (Path(src).stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-Xcompiler", "-fPIC,-fvisibility=hidden", f"-I{INCLUDE}", f"-I{CSRC}",
+        cmd = [nvcc, *flags, "-Xcompiler", "-fPIC,-fvisibility=hidden", f"-I{INCLUDE}", f"-I{CSRC}",
                "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -65,8 +74,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             sys.stderr.write(r.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
-        objs = list(ex.map(compile_one, SOURCES))
+    with ThreadPoolExecutor(max_workers=len(sources)) as ex:
+        objs = list(ex.map(compile_one, sources))
     tmp = LIB.with_suffix(".so.tmp")
     r = subprocess.run([nvcc, "-shared", "-o", str(tmp), *map(str, objs)],
                        capture_output=True, text=True)

@@ -525,7 +525,10 @@ static cudaError_t backward_typed(const void *value, const void *offset, const v
                 }
                 if (dots) {
                     if (e1 != cudaSuccess) return e1;
-                    if ((!hmma && try_launch_backward_vmma(offset, mask, grad_out, acc, q, dtype_tag, stream, &e2)) ||
+                    // DCNV3_VALUE=band: the dense-band value kernel (experiments/dcnv3_backward_vband.cu, opt-in)
+                    const bool band = ev && ev[0] == 'b';
+                    if ((band && try_launch_backward_vband(offset, mask, grad_out, acc, q, dtype_tag, stream, &e2)) ||
+                        (!hmma && try_launch_backward_vmma(offset, mask, grad_out, acc, q, dtype_tag, stream, &e2)) ||
                         try_launch_backward_vstrip(offset, mask, grad_out, acc, q, dtype_tag, stream, &e2)) {
                         if (e2 != cudaSuccess) return e2;
                         if ((err = pdl_launch(pdl_for(q), narrow_f32_kernel<T>, dim3(aux_blocks), dim3(256), 0, stream,

@@ -140,6 +140,10 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
     const float base_w = axis_base(wo, 3, 1, q.pw, 1, q.sigma);
     const float base_h = axis_base(ho, 3, 1, q.ph, 1, q.sigma);
     const float bw = base_w - (float)ox, bh = base_h - (float)oy;     // window-relative anchors
+    // The reference's range test (dcnv3_im2col_cuda.cuh:334: loc > -1 && loc < extent) is implied by the window's zero
+    // fill everywhere EXCEPT at loc == -1 exactly (row / column -1 reads zeros, so grad_mask is 0, but the derivative
+    // across that row / column is not): window-relative -1 on either axis zeroes the point's offset gradient.
+    const float u_m1 = -1.f - (float)ox, v_m1 = -1.f - (float)oy;
     const uint32_t win_addr = smem_u32(win) + g * (CH * 2) + half * 16;
     const uint32_t my_off = s_off + pix * kOPitch + gr * (kP * 4);
     const uint32_t my_msk = s_msk + pix * kMPitch + m_shift + gr * (kP * 2);
@@ -201,8 +205,9 @@ bwd_dots(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUt
                 for (int t = 0; t < 4; ++t) dr[t] += __shfl_xor_sync(am, dr[t], 1);
             }
             const float gm = hh * (hw * dr[0] + lw * dr[1]) + lh * (hw * dr[2] + lw * dr[3]);
-            const float gx = m * (hh * (dr[1] - dr[0]) + lh * (dr[3] - dr[2]));
-            const float gy = m * (hw * (dr[2] - dr[0]) + lw * (dr[3] - dr[1]));
+            const float mg = (u == u_m1 || v == v_m1) ? 0.f : m;
+            const float gx = mg * (hh * (dr[1] - dr[0]) + lh * (dr[3] - dr[2]));
+            const float gy = mg * (hw * (dr[2] - dr[0]) + lw * (dr[3] - dr[1]));
             // results overwrite the staged inputs of this point (a miss is redone below)
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(my_off + p * 4), "r"(pack2(q.sigma * gx, q.sigma * gy, T())) : "memory");
             asm volatile("st.shared.u16 [%0], %1;" ::"r"(my_msk + p * 2), "h"(bits16(gm, T())) : "memory");

@@ -341,8 +341,11 @@ __device__ __forceinline__ bool points_fast(const StepCtx<T> &c, int i) {
         rotate4(dr, (4 - rho[q]) & 3);   // back to corner order TL, TR, BL, BR
         const float hh = 1.f - lh[q], hw = 1.f - lw[q];
         const float gm = hh * (hw * dr[0] + lw[q] * dr[1]) + lh[q] * (hw * dr[2] + lw[q] * dr[3]);
-        const float gx = m[q] * (hh * (dr[1] - dr[0]) + lh[q] * (dr[3] - dr[2]));
-        const float gy = m[q] * (hw * (dr[2] - dr[0]) + lw[q] * (dr[3] - dr[1]));
+        // the reference's range test (dcnv3_im2col_cuda.cuh:334) is implied by the window's zero fill except at
+        // loc == -1 exactly (row / column -1 reads zeros: grad_mask is 0, the derivative across it is not)
+        const float mg = (uw[q] == -1.f - (float)c.ox || vw[q] == -1.f - (float)c.oy) ? 0.f : m[q];
+        const float gx = mg * (hh * (dr[1] - dr[0]) + lh[q] * (dr[3] - dr[2]));
+        const float gy = mg * (hw * (dr[2] - dr[0]) + lw[q] * (dr[3] - dr[1]));
         sts32(c.s_off_lane + (p0 + q) * 4, pack2(c.sigma * gx, c.sigma * gy, T()));
         sts16(c.s_msk_lane + (p0 + q) * 2, bits16(gm, T()));
     }

@@ -20,15 +20,29 @@ bool fast_weights_requested();
 // group-slice forward (dcnv3_forward_gs.cu): 16-bit I/O, group_channels == 16, G % 8 == 0, 3x3 / stride 1
 bool try_launch_forward_gs(const void *value, const void *offset, const void *mask, void *out,
                            const Geom &q, int dtype, bool fast, cudaStream_t stream, cudaError_t *err);
-// tensor-core forward for 16-bit I/O, group_channels == 16 (dcnv3_forward_mma.cu)
+// Kernels under csrc/experiments/ are measured alternatives that lost to the defaults (profiles/README.md); they are
+// compiled only with DCNV3_BUILD_EXPERIMENTS=1 (-DDCNV3_EXPERIMENTS) and otherwise decline every shape.
+// tensor-core forward for 16-bit I/O, group_channels == 16 (experiments/dcnv3_forward_mma.cu)
+#ifdef DCNV3_EXPERIMENTS
 bool try_launch_forward_mma(const void *value, const void *offset, const void *mask, void *out,
                             const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err);
+#else
+inline bool try_launch_forward_mma(const void *value, const void *offset, const void *mask, void *out,
+                            const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err) { return false; }
+#endif
 
 // shared-memory tiled backward (dcnv3_backward_tile.cu); gv_acc = zeroed fp32 accumulator
+#ifdef DCNV3_EXPERIMENTS
 bool try_launch_backward_tile(const void *value, const void *offset, const void *mask,
                               const void *grad_out, float *gv_acc, void *grad_offset,
                               void *grad_mask, const Geom &q, int dtype, cudaStream_t stream,
                               cudaError_t *err);
+#else
+inline bool try_launch_backward_tile(const void *value, const void *offset, const void *mask,
+                              const void *grad_out, float *gv_acc, void *grad_offset,
+                              void *grad_mask, const Geom &q, int dtype, cudaStream_t stream,
+                              cudaError_t *err) { return false; }
+#endif
 
 // tensor-core backward for 16-bit I/O, group_channels == 16 (dcnv3_backward_mma.cu)
 bool try_launch_backward_mma(const void *value, const void *offset, const void *mask,
@@ -54,9 +68,24 @@ bool backward_vmma_eligible(const void *offset, const void *mask, const void *gr
 bool try_launch_backward_vmma(const void *offset, const void *mask, const void *grad_out, float *gv_acc,
                               const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err);
 
+// grad_value with the coefficient columns built dense in registers and a circular TMEM band (dcnv3_backward_vband.cu)
+#ifdef DCNV3_EXPERIMENTS
+bool try_launch_backward_vband(const void *offset, const void *mask, const void *grad_out, float *gv_acc,
+                               const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err);
+#else
+inline bool try_launch_backward_vband(const void *offset, const void *mask, const void *grad_out, float *gv_acc,
+                               const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err) { return false; }
+#endif
+
+#ifdef DCNV3_EXPERIMENTS
 bool try_launch_backward_mma2(const void *value, const void *offset, const void *mask,
                               const void *grad_out, float *gv_acc, void *grad_offset, void *grad_mask,
                               const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err);
+#else
+inline bool try_launch_backward_mma2(const void *value, const void *offset, const void *mask,
+                              const void *grad_out, float *gv_acc, void *grad_offset, void *grad_mask,
+                              const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err) { return false; }
+#endif
 
 // Programmatic dependent launch (PDL) between the kernels of the split backward: a kernel launched with
 // `pdl_launch` may start (prologue, loads of tensors no earlier kernel of the call writes) while the previous

@@ -10,10 +10,10 @@
 //                   (32 x 16 ch) on the tensor cores (HMMA m16n8k16, fp32 accumulate), bands summed
 //                   and flushed with 128-bit reductions.  81 KB per CTA (the four 17 KB A tiles).
 // See dcnv3_backward_mma.cu for the derivation and the precision note (A is stored in the I/O dtype).
-#include "dcnv3_common.cuh"
-#include "dcnv3_launch.h"
-#include "dcnv3_stage.cuh"
-#include "dcnv3_tma.cuh"
+#include "../dcnv3_common.cuh"
+#include "../dcnv3_launch.h"
+#include "../dcnv3_stage.cuh"
+#include "../dcnv3_tma.cuh"
 
 #include <algorithm>
 #include <cmath>

@@ -24,9 +24,9 @@
 // Points whose 2x2 corner block leaves the window (or the warp's band) fall back to direct global
 // reductions.  Finally the bands are summed and added to the fp32 grad_value accumulator in
 // global memory with 128-bit reductions (cells outside the map and all-zero pieces are skipped).
-#include "dcnv3_common.cuh"
-#include "dcnv3_launch.h"
-#include "dcnv3_tma.cuh"
+#include "../dcnv3_common.cuh"
+#include "../dcnv3_launch.h"
+#include "../dcnv3_tma.cuh"
 
 #include <algorithm>
 #include <cmath>

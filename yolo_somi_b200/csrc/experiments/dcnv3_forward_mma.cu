@@ -20,10 +20,10 @@
 // A CTA (4 warps) owns an 8x16 (w x h) tile of output pixels of one (image, group).  Points whose
 // corner block leaves the window or the warp's band fall back to clamped global reads with fp32
 // FMAs; their partial sums join the MMA result through a small shared-memory patch.
-#include "dcnv3_common.cuh"
-#include "dcnv3_launch.h"
-#include "dcnv3_stage.cuh"
-#include "dcnv3_tma.cuh"
+#include "../dcnv3_common.cuh"
+#include "../dcnv3_launch.h"
+#include "../dcnv3_stage.cuh"
+#include "../dcnv3_tma.cuh"
 
 #include <algorithm>
 #include <cmath>
