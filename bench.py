@@ -335,6 +335,138 @@ def layer_row(dev, dtype):
 
 
 # ------------------------------------------------------------------------------- our arm
+# ------------------------------------------------------------------------------- BASELINE configs[2] / [3]
+def _kernel_split(prof):
+    """CUDA time of one profiled window by kernel family (torch.profiler / kineto, rank 0)."""
+    fam = {"nccl": 0.0, "dcnv3_sm100": 0.0, "conv_gemm": 0.0, "batchnorm_layernorm": 0.0, "elementwise_act_loss": 0.0,
+           "copy_cat_permute": 0.0, "optimizer_ema": 0.0, "other": 0.0}
+    names = {"nccl": set(), "dcnv3_sm100": set(), "other": set()}
+    ours = ("dcnv3", "fwd_gs", "bwd_dots", "bwd_vmma", "bwd_strip", "bwd_scatter", "bwd_mma", "fwd_tile", "fwd_gather",
+            "narrow_f32", "offset_mask_proj", "dwconv_ln_gelu", "absmax", "narrow_fixed")
+    for ev in prof.events():
+        if getattr(ev, "device_type", None) is None or "cuda" not in str(ev.device_type).lower():
+            continue
+        t = float(getattr(ev, "device_time", 0.0) or getattr(ev, "cuda_time", 0.0) or 0.0)
+        n = ev.name
+        low = n.lower()
+        if "nccl" in low:
+            fam["nccl"] += t; names["nccl"].add(n.split("(")[0][:60])
+        elif any(k in n for k in ours):
+            fam["dcnv3_sm100"] += t; names["dcnv3_sm100"].add(n.split("<")[0].split("(")[0][-40:])
+        elif any(k in low for k in ("gemm", "conv", "cudnn", "cutlass", "xmma", "sm90", "sm100", "nvjet", "wgrad", "dgrad")):
+            fam["conv_gemm"] += t
+        elif any(k in low for k in ("batch_norm", "batchnorm", "layer_norm", "layernorm", "bn_fw", "bn_bw")):
+            fam["batchnorm_layernorm"] += t
+        elif any(k in low for k in ("multi_tensor", "foreach", "lpnorm")):
+            fam["optimizer_ema"] += t
+        elif any(k in low for k in ("copy", "cat", "permute", "transpose", "memcpy", "memset", "index", "scatter", "gather", "upsample")):
+            fam["copy_cat_permute"] += t
+        elif any(k in low for k in ("elementwise", "silu", "sigmoid", "gelu", "reduce", "softmax", "binary_cross", "pool")):
+            fam["elementwise_act_loss"] += t
+        else:
+            fam["other"] += t; names["other"].add(n.split("<")[0].split("(")[0][-50:])
+    return fam, {k: sorted(v)[:8] for k, v in names.items()}
+
+
+def train_row(args, rank, world, local_rank, dev):
+    """BASELINE configs[3]: the YOLOv5l-DCNv3 training step on synthetic VisDrone-shaped 640 x 640 batches, GLOBAL batch
+    128 split over the ranks (strong scaling: 128 / 64 / 32 / 16 images per GPU at 1 / 2 / 4 / 8), bf16 autocast,
+    DistributedDataParallel over NCCL with one gradient all-reduce per optimizer step, SGD + fused EMA.  Every rank
+    takes part; returns the row on rank 0.  configs[2] (inference, batch 32, one GPU) is measured at N = 1."""
+    from yolo_somi_b200.train_step import FusedModelEMA, TrainStep, make_optimizer, synthetic_batch, wrap_ddp
+    from yolo_somi_b200.yolov5l_dcnv3 import YOLOv5lDCNv3, layers
+    gb = int(os.environ.get("BENCH_TRAIN_BATCH", 128))
+    if gb % world:
+        return None
+    per = gb // world
+    torch.manual_seed(0)
+    torch.backends.cudnn.benchmark = True
+    model = YOLOv5lDCNv3(nc=10).to(dev).to(memory_format=torch.channels_last)
+    n_params = sum(p.numel() for p in model.parameters())
+    ema = FusedModelEMA(model) if rank == 0 else None
+    ddp = wrap_ddp(model, local_rank)
+    ts = TrainStep(ddp, nc=10, optimizer=make_optimizer(model), ema=ema)
+    # the reference's loader hands uint8 images on the host; the step copies them (train.py:249-250)
+    imgs, targets = synthetic_batch(per, 640, device="cpu", seed=rank)
+    host_u8 = (imgs * 255).to(torch.uint8).pin_memory()
+    host_t = targets.pin_memory()
+
+    def one():
+        x = host_u8.to(dev, non_blocking=True).to(memory_format=torch.channels_last).float().div_(255)
+        t = host_t.to(dev, non_blocking=True)
+        return ts.step(x, t)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    steps = int(os.environ.get("BENCH_TRAIN_STEPS", 6))
+    for _ in range(3):
+        one()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = one()
+    e1.record()
+    barrier()
+    from yolo_somi_b200.sharding import max_over_ranks
+    ms = max_over_ranks(e0.elapsed_time(e1), dev) / steps
+    loss_val = float(loss)
+    # where the step's GPU time goes (rank 0): NCCL all-reduce vs this library's kernels vs cuDNN / cuBLAS
+    split = kernels = None
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(2):
+                one()
+            torch.cuda.synchronize()
+        if rank == 0:
+            fam, kernels = _kernel_split(prof)
+            tot = sum(fam.values()) or 1.0
+            split = {k: {"ms_per_step": v / 2e3, "share": v / tot} for k, v in fam.items()}
+    except Exception as exc:  # profiling is evidence, not the measurement
+        split = {"error": str(exc)[:200]}
+    barrier()
+    infer = None
+    if world == 1:
+        m = ema.ema
+        x = torch.rand(32, 3, 640, 640, device=dev).to(memory_format=torch.channels_last)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            for _ in range(3):
+                m(x)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(10):
+                m(x)
+            b.record(); torch.cuda.synchronize()
+        infer = {"img_per_s": 32 * 10 / (a.elapsed_time(b) * 1e-3), "batch": 32, "ms_per_batch": a.elapsed_time(b) / 10,
+                 "config": "BASELINE configs[2]: YOLOv5l-DCNv3 inference, synthetic 640x640 batch 32, bf16 autocast, EMA weights"}
+    mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    del ts, ddp, model, ema
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    grad_bytes = n_params * 4
+    limiter = None
+    if split and "error" not in split:
+        limiter = max(split, key=lambda k: split[k]["share"])
+    return {
+        "img_per_s": gb / (ms * 1e-3), "ms_per_step": ms, "global_batch": gb, "per_gpu_batch": per, "n_gpus": world,
+        "scaling": "strong", "steps": steps, "warmup": 3, "loss_last": loss_val, "peak_mem_gib": mem,
+        "model": "YOLOv5l-DCNv3 (stock YOLOv5l layout, the four head C3 stages are C3_DCNv3: 12 DCNv3 layers)",
+        "params": n_params, "layers": layers(),
+        "step": "uint8 host batch -> H2D -> bf16 autocast forward -> YOLO-shaped surrogate loss -> backward -> "
+                "clip -> SGD(nesterov, foreach) -> fused EMA (rank 0); no host sync inside the step",
+        "ddp": {"backend": "nccl" if world > 1 else None, "gradient_as_bucket_view": True, "static_graph": True,
+                "broadcast_buffers": False, "bucket_cap_mb": 64, "allreduce_bytes_per_step": grad_bytes if world > 1 else 0},
+        "gpu_time_split_rank0": split, "kernels_seen": kernels, "limiter": limiter, "inference": infer,
+        "config": "BASELINE configs[3]: YOLO-SOMI training step, synthetic VisDrone-shaped 640x640, global batch 128",
+    }
+
+
 def run_ours(args, rank, world, local_rank):
     import DCNv3  # the drop-in shim (repo root) over libdcnv3_sm100.so; raises if the .so is absent
     from yolo_somi_b200 import _native
@@ -422,6 +554,10 @@ def run_ours(args, rank, world, local_rank):
     # (tcgen05 GEMM + bias + softmax epilogue) against the layer's two linears + softmax, same shape
     proj = proj_row(dev, dtype) if rank == 0 else None
     layer = layer_row(dev, dtype) if rank == 0 else None
+    # ---- BASELINE configs[2] / [3]: the model-level step, every rank takes part (NCCL gradient all-reduce)
+    del sets, host_in, host_out
+    torch.cuda.empty_cache()
+    train = None if args.no_train else train_row(args, rank, world, local_rank, dev)
 
     if rank != 0:
         return
@@ -458,6 +594,9 @@ def run_ours(args, rank, world, local_rank):
     }
     if proj is not None:
         line["next_rows"] = {"offset_mask_proj": proj, "layer": layer}
+    if train is not None:
+        line["train_step"] = train
+        line["img_per_s"] = train["img_per_s"]
     if world == 1 and not args.no_cpu:
         # the CPU reference beside the GPU number, same run, same box: the full workload (all 16 images), 5 passes
         times, threads, kind, desc = cpu_reference_run(CFG["N"], 5)
@@ -475,6 +614,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-train", action="store_true", help="skip the YOLOv5l-DCNv3 training-step row")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

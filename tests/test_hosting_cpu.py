@@ -1,0 +1,73 @@
+"""Host-side logic of the NCHW hosting modules and the parse_model patch (no GPU: constructors and text only)."""
+import ast
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_groups_for_always_divides_and_prefers_fast_shapes():
+    from yolo_somi_b200.hosting import groups_for
+    for c in list(range(1, 300)) + [512, 640, 768, 1024]:
+        g = groups_for(c)
+        assert g >= 1 and c % g == 0, c
+    assert groups_for(256) == 16 and groups_for(128) == 8 and groups_for(512) == 32     # 16 channels per group, G % 8 == 0
+    assert groups_for(64) == 8                                                            # 8 per group rather than G = 4
+    assert groups_for(100) == 4                                                           # 25 per group: the largest divisor <= 32
+
+
+def test_stride_two_is_rejected_and_blocks_build():
+    from yolo_somi_b200 import hosting
+    with pytest.raises(ValueError, match="stride must be 1"):
+        hosting.DCNv3_YOLO(64, 64, 3, 2)
+    m = hosting.C3_DCNv3(64, 128, n=2)
+    keys = set(m.state_dict())
+    assert {"cv1.conv.weight", "cv3.bn.weight", "m.1.cv2.dcn.offset.weight", "m.0.cv1.bn.running_mean"} <= keys
+    m = hosting.C2f_DCNv3(64, 100, n=1)          # c = 50: 25 channels per group, constructor must not raise
+    assert m.m[0].cv2.dcn.group == 2
+    assert isinstance(hosting.C3_DCNv3(32, 32), hosting.C3) and isinstance(hosting.C2f_DCNv3(32, 32), hosting.C2f)
+
+
+_SNIPPET = '''
+from models.common import *
+from models.common import ASFF
+def parse_model(d, ch):
+    for i, (f, n, m, args) in enumerate(d['backbone'] + d['head']):
+        m = eval(m) if isinstance(m, str) else m
+        if m in [Conv, GhostConv, Bottleneck,
+                 C3, C2f]:
+            c1, c2 = ch[f], args[0]
+            args = [c1, c2, *args[1:]]
+            if m in [BottleneckCSP, C3,
+                     C2f]:
+                args.insert(2, n)
+                n = 1
+'''
+
+
+def _lists(text):
+    tree = ast.parse(text)
+    out = []
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Compare) and isinstance(node.comparators[0], ast.List):
+            out.append([e.id for e in node.comparators[0].elts if isinstance(e, ast.Name)])
+    return out
+
+
+def test_parse_model_patch_on_the_builder_shape():
+    import sys
+    sys.path.insert(0, str(ROOT / "integration"))
+    from apply_parse_model_patch import patch
+    out = patch(_SNIPPET)
+    assert patch(out) == out                                             # idempotent
+    assert "from yolo_somi_b200.hosting import DCNv3_YOLO" in out
+    channel, repeat = _lists(out)
+    assert {"DCNv3_YOLO", "Bottleneck_DCNv3", "C3_DCNv3", "C2f_DCNv3"} <= set(channel)
+    assert {"C3_DCNv3", "C2f_DCNv3"} <= set(repeat) and "DCNv3_YOLO" not in repeat
+    ref = Path("/root/reference/models/yolo.py")
+    if ref.exists():                                                     # the real builder, in memory only
+        text = patch(ref.read_text())
+        ast.parse(text)
+        lists = _lists(text)
+        assert any("C3_DCNv3" in l and "Conv" in l for l in lists) and any("C3_DCNv3" in l and "BottleneckCSP" in l for l in lists)

@@ -1,17 +1,19 @@
 """Hosting the DCNv3 layer in the reference's NCHW module zoo.
 
 The reference bundles ``ops_dcnv3`` but never wires it into ``models/common.py`` / ``parse_model``
-(SURVEY F1).  These modules follow the way the zoo hosts DCNv2 -- a Conv-like wrapper
-(models/common.py:3768-3831), a bottleneck using it as ``cv2`` (:3849-3859) and the ``C3`` / ``C2f``
-containers built from it (:3862-3882) -- for the channels-last DCNv3 layer:
+(SURVEY F1).  The zoo hosts its other deformable layer this way: a Conv-like wrapper (models/common.py:3768-3831),
+a bottleneck that uses it as ``cv2`` (:3849-3859) and ``C3`` / ``C2f`` subclasses that swap their inner blocks
+(:3862-3882).  This module does the same for the channels-last DCNv3 layer and REUSES the zoo's own building blocks:
 
     DCNv3_YOLO         NCHW in -> NHWC -> DCNv3 (this library) -> NCHW -> BatchNorm -> SiLU
-    Bottleneck_DCNv3   cv1 = 1x1 Conv, cv2 = DCNv3_YOLO, optional shortcut
-    C3_DCNv3, C2f_DCNv3   the zoo's CSP containers with that bottleneck
+    Bottleneck_DCNv3   cv1 = the zoo's 1x1 Conv, cv2 = DCNv3_YOLO, optional shortcut
+    C3_DCNv3, C2f_DCNv3   subclasses of the zoo's C3 / C2f whose ``m`` holds Bottleneck_DCNv3 blocks
 
-To use them from a model yaml, import the names into ``models/yolo.py`` and add them to the
-channel-handling lists of ``parse_model`` (models/yolo.py:1472-1492), see INTEGRATION.md.  The
-permutes are views when the surrounding model runs in ``torch.channels_last`` memory format.
+Inside the host tree ``Conv`` / ``C3`` / ``C2f`` are imported from ``models.common`` (so ``fuse()``, checkpoints and
+``parse_model`` see the classes they know).  Outside it (this repo's own step harness, the GPU box) a minimal stand-in
+with the same attribute names (``conv``/``bn``/``act``, ``cv1``/``cv2``/``cv3``/``m``) is used.  The patch that lists
+these names in ``parse_model`` is ``integration/parse_model_dcnv3.patch``.
+The permutes are views when the surrounding model runs in ``torch.channels_last`` memory format.
 """
 from __future__ import annotations
 
@@ -21,43 +23,88 @@ from torch import nn
 from .ops_dcnv3.modules import DCNv3
 
 
-def autopad(k, p=None, d=1):
-    if d > 1:
-        k = d * (k - 1) + 1 if isinstance(k, int) else [d * (x - 1) + 1 for x in k]
-    if p is None:
-        p = k // 2 if isinstance(k, int) else [x // 2 for x in k]
-    return p
+def _host_zoo():
+    """(Conv, C3, C2f) of the host model zoo if this file is used inside it, else None."""
+    try:
+        from models import common as zoo           # the reference tree: models/common.py:55-66 (Conv), C3, C2f
+        return zoo.Conv, zoo.C3, zoo.C2f
+    except Exception:
+        return None
 
 
-class Conv(nn.Module):
-    """The zoo's standard convolution block: Conv2d + BatchNorm2d + SiLU."""
-    default_act = nn.SiLU()
+def _standin_zoo():
+    """Stand-ins for use outside the host tree: same constructor arguments and attribute names as the zoo's blocks."""
 
-    def __init__(self, c1, c2, k=1, s=1, p=None, g=1, d=1, act=True):
-        super().__init__()
-        self.conv = nn.Conv2d(c1, c2, k, s, autopad(k, p, d), groups=g, dilation=d, bias=False)
-        self.bn = nn.BatchNorm2d(c2)
-        self.act = self.default_act if act is True else act if isinstance(act, nn.Module) else nn.Identity()
+    class Conv(nn.Module):
+        def __init__(self, c1, c2, k=1, s=1, p=None, g=1, d=1, act=True):
+            super().__init__()
+            pad = (d * (k - 1)) // 2 if p is None else p
+            self.conv = nn.Conv2d(c1, c2, k, s, pad, dilation=d, groups=g, bias=False)
+            self.bn = nn.BatchNorm2d(c2)
+            self.act = nn.SiLU() if act is True else (act if isinstance(act, nn.Module) else nn.Identity())
 
-    def forward(self, x):
-        return self.act(self.bn(self.conv(x)))
+        def forward(self, x):
+            return self.act(self.bn(self.conv(x)))
+
+    class C3(nn.Module):
+        def __init__(self, c1, c2, n=1, shortcut=True, g=1, e=0.5):
+            super().__init__()
+            hidden = int(c2 * e)
+            self.cv1, self.cv2, self.cv3 = Conv(c1, hidden), Conv(c1, hidden), Conv(2 * hidden, c2)
+            self.m = nn.Sequential()
+
+        def forward(self, x):
+            return self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), 1))
+
+    class C2f(nn.Module):
+        def __init__(self, c1, c2, n=1, shortcut=False, g=1, e=0.5):
+            super().__init__()
+            self.c = int(c2 * e)
+            self.cv1, self.cv2 = Conv(c1, 2 * self.c), Conv((2 + n) * self.c, c2)
+            self.m = nn.ModuleList()
+
+        def forward(self, x):
+            parts = list(self.cv1(x).split((self.c, self.c), 1))
+            for block in self.m:
+                parts.append(block(parts[-1]))
+            return self.cv2(torch.cat(parts, 1))
+
+    return Conv, C3, C2f
 
 
-def _groups_for(channels: int) -> int:
-    """16 channels per group (the fast kernels' shape), at least one group."""
-    return max(1, channels // 16)
+Conv, C3, C2f = _host_zoo() or _standin_zoo()
+
+
+def groups_for(channels: int) -> int:
+    """Group count for a DCNv3 layer of `channels`: group_channels 16 (else 32, else 8) -- the shapes the fastest
+    kernels take -- preferring a multiple of 8 groups; otherwise the largest divisor that leaves <= 32 channels per
+    group.  Always divides `channels` (the layer's constructor requires it, modules/dcnv3.py:252-254)."""
+    for want_mult8 in (True, False):
+        for gc in (16, 32, 8):
+            if channels % gc == 0 and (not want_mult8 or (channels // gc) % 8 == 0):
+                return channels // gc
+    for gc in range(min(32, channels), 0, -1):
+        if channels % gc == 0:
+            return channels // gc
+    return 1
 
 
 class DCNv3_YOLO(nn.Module):
-    """Conv-like wrapper of the DCNv3 layer for NCHW feature maps (c1 -> c2, stride 1 or 2)."""
+    """Conv-like wrapper of the DCNv3 layer for NCHW feature maps (c1 -> c2, stride 1).
+
+    Stride 2 is rejected: the layer computes offsets / masks on the INPUT grid (its depthwise conv has stride 1,
+    modules/dcnv3.py:276-289) while the core expects them on the OUTPUT grid, so the reference layer itself cannot run
+    with stride != 1; downsample with the zoo's strided Conv in front instead."""
 
     def __init__(self, c1, c2, k=3, s=1, p=None, g=None, d=1, act=True):
         super().__init__()
+        if s != 1:
+            raise ValueError("DCNv3_YOLO: stride must be 1 (put a strided Conv in front); got %r" % (s,))
         self.pre = Conv(c1, c2, 1, 1) if c1 != c2 else nn.Identity()
-        self.dcn = DCNv3(channels=c2, kernel_size=k, stride=s, pad=autopad(k, p, d), dilation=d,
-                         group=g or _groups_for(c2))
+        self.dcn = DCNv3(channels=c2, kernel_size=k, stride=1, pad=(d * (k - 1)) // 2 if p is None else p, dilation=d,
+                         group=g or groups_for(c2))
         self.bn = nn.BatchNorm2d(c2)
-        self.act = Conv.default_act if act is True else act if isinstance(act, nn.Module) else nn.Identity()
+        self.act = nn.SiLU() if act is True else (act if isinstance(act, nn.Module) else nn.Identity())
 
     def forward(self, x):
         x = self.pre(x).permute(0, 2, 3, 1)          # NCHW -> NHWC (a view under channels_last)
@@ -66,41 +113,32 @@ class DCNv3_YOLO(nn.Module):
 
 
 class Bottleneck_DCNv3(nn.Module):
+    """The zoo's bottleneck (1x1 reduce, 3x3, optional residual) with the DCNv3 wrapper as the 3x3."""
+
     def __init__(self, c1, c2, shortcut=True, g=None, e=0.5):
         super().__init__()
-        c_ = int(c2 * e)
-        self.cv1 = Conv(c1, c_, 1, 1)
-        self.cv2 = DCNv3_YOLO(c_, c2, 3, 1, g=g)
+        hidden = int(c2 * e)
+        self.cv1 = Conv(c1, hidden, 1, 1)
+        self.cv2 = DCNv3_YOLO(hidden, c2, 3, 1, g=g)
         self.add = shortcut and c1 == c2
 
     def forward(self, x):
-        return x + self.cv2(self.cv1(x)) if self.add else self.cv2(self.cv1(x))
+        y = self.cv2(self.cv1(x))
+        return x + y if self.add else y
 
 
-class C3_DCNv3(nn.Module):
-    """CSP bottleneck with 3 convolutions (the zoo's C3) whose inner blocks are Bottleneck_DCNv3."""
+class C3_DCNv3(C3):
+    """The zoo's C3 with Bottleneck_DCNv3 inner blocks (the way C3_DCN swaps them, models/common.py:3862-3867)."""
 
     def __init__(self, c1, c2, n=1, shortcut=True, g=None, e=0.5):
-        super().__init__()
-        c_ = int(c2 * e)
-        self.cv1 = Conv(c1, c_, 1, 1)
-        self.cv2 = Conv(c1, c_, 1, 1)
-        self.cv3 = Conv(2 * c_, c2, 1)
-        self.m = nn.Sequential(*(Bottleneck_DCNv3(c_, c_, shortcut, g, e=1.0) for _ in range(n)))
-
-    def forward(self, x):
-        return self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), 1))
+        super().__init__(c1, c2, n, shortcut, 1, e)
+        hidden = int(c2 * e)
+        self.m = nn.Sequential(*(Bottleneck_DCNv3(hidden, hidden, shortcut, g, e=1.0) for _ in range(n)))
 
 
-class C2f_DCNv3(nn.Module):
+class C2f_DCNv3(C2f):
+    """The zoo's C2f with Bottleneck_DCNv3 inner blocks (models/common.py:3870-3882)."""
+
     def __init__(self, c1, c2, n=1, shortcut=False, g=None, e=0.5):
-        super().__init__()
-        self.c = int(c2 * e)
-        self.cv1 = Conv(c1, 2 * self.c, 1, 1)
-        self.cv2 = Conv((2 + n) * self.c, c2, 1)
+        super().__init__(c1, c2, n, shortcut, 1, e)
         self.m = nn.ModuleList(Bottleneck_DCNv3(self.c, self.c, shortcut, g, e=1.0) for _ in range(n))
-
-    def forward(self, x):
-        y = list(self.cv1(x).split((self.c, self.c), 1))
-        y.extend(m(y[-1]) for m in self.m)
-        return self.cv2(torch.cat(y, 1))

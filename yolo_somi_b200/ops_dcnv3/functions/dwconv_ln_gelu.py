@@ -41,9 +41,13 @@ def _pack(w, b, gamma, beta, dtype):
     """Kernel-layout copies of the parameters ([k*k][C] taps in the I/O dtype, fp32 vectors),
     rebuilt only when one of the four tensors is another object or was modified in place."""
     tensors = (w, b, gamma, beta)
-    ver = tuple(t._version for t in tensors)
+    # fingerprint: object identity, in-place version, storage pointer and device of all four tensors (`p.data = t`
+    # and module.to(device) keep the Parameter object and its version).  `p.data.add_()` changes none of these, so
+    # parameters that are being TRAINED are repacked on every call -- the cache only serves frozen weights.
+    ver = tuple((t._version, t.data_ptr(), t.device) for t in tensors)
+    training = torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
     hit = _PACKED.get(id(w))
-    if hit is not None and hit[1] == ver and hit[2] == dtype and all(r() is t for r, t in zip(hit[0], tensors)):
+    if not training and hit is not None and hit[1] == ver and hit[2] == dtype and all(r() is t for r, t in zip(hit[0], tensors)):
         return hit[3]
     c, k = w.shape[0], w.shape[-1]
     packed = (w.detach().reshape(c, k * k).t().to(dtype).contiguous(),

@@ -36,9 +36,13 @@ def _pack(lib, w_off, b_off, w_msk, b_msk, group, points, dtype):
     """Concatenated, zero-padded weights / biases in the kernel's layout; repacked only when one of
     the four tensors is another object or has been modified in place (optimizer step)."""
     tensors = (w_off, b_off, w_msk, b_msk)
-    ver = tuple(t._version for t in tensors)
+    # fingerprint: object identity, in-place version, storage pointer and device of all four tensors (`p.data = t`
+    # and module.to(device) keep the Parameter object and its version).  `p.data.add_()` changes none of these, so
+    # parameters that are being TRAINED are repacked on every call -- the cache only serves frozen weights.
+    ver = tuple((t._version, t.data_ptr(), t.device) for t in tensors)
+    training = torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
     hit = _PACKED.get(id(w_off))
-    if hit is not None and hit[1] == ver and hit[2] == dtype and all(r() is t for r, t in zip(hit[0], tensors)):
+    if not training and hit is not None and hit[1] == ver and hit[2] == dtype and all(r() is t for r, t in zip(hit[0], tensors)):
         return hit[3], hit[4]
     n = 3 * group * points
     npad = lib.dcnv3_offset_mask_proj_padded_cols(group, points)

@@ -156,3 +156,161 @@ def install_reference_aliases(force: bool = False) -> list[str]:
         pkg.__path__ = []                         # a namespace stub: only the aliases above live in it
         sys.modules["models"] = pkg
     return done
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The DDP wiring of the training step (reference train.py:165-208 wrap / SyncBN / sampler shard, :263-283 autocast
+# forward - backward - optimizer - EMA - logging, :422-434 process-group set-up), restated for one process per GPU.
+#
+# What changes against the reference, and why:
+#   * the device is bound by LOCAL_RANK only (train.py:55 pins GPU 0 through CUDA_VISIBLE_DEVICES and --device '0' is
+#     the default, train.py:374: under torchrun every rank would land on the same GPU);
+#   * bf16 autocast without a GradScaler (train.py:263 uses fp16 + scaler; the scaler's inf check is a host sync per step);
+#   * DDP with gradient_as_bucket_view (the all-reduce runs on the gradients' own storage, no bucket copy-out),
+#     static_graph (no per-iteration graph search) and broadcast_buffers=False (BatchNorm statistics are per rank in
+#     the reference as well unless --sync-bn; no per-step broadcast of the buffers);
+#   * accumulation micro-steps run under no_sync(): one all-reduce per OPTIMIZER step, not per micro-step (train.py:270
+#     reduces on every backward);
+#   * the running loss stays on the device; the host reads it every `log_every` steps through a pinned buffer and an
+#     event instead of formatting it into tqdm every step (train.py:279-282 synchronises on every iteration);
+#   * the EMA is FusedModelEMA (above), on every rank-0 optimizer step.
+import contextlib
+import os
+
+import torch.distributed as dist
+
+
+def setup_process_group(backend: str | None = None) -> tuple[int, int, int]:
+    """(rank, local_rank, world) from the torchrun environment; initialises the default group if world > 1.
+    NCCL on GPUs (over NVLink 5 / NVSwitch), gloo on CPU (tests)."""
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    use_cuda = torch.cuda.is_available()
+    if use_cuda:
+        torch.cuda.set_device(local_rank)
+    if world > 1 and not dist.is_initialized():
+        kw = {}
+        if use_cuda and (backend or "nccl") == "nccl":
+            kw["device_id"] = torch.device("cuda", local_rank)
+        dist.init_process_group(backend or ("nccl" if use_cuda else "gloo"), rank=rank, world_size=world, **kw)
+    return rank, local_rank, world
+
+
+def wrap_ddp(model: nn.Module, local_rank: int | None = None, sync_bn: bool = False) -> nn.Module:
+    """train.py:165-208: optional SyncBatchNorm conversion, then DistributedDataParallel -- with the settings above.
+    Returns the model unchanged when there is one rank.  (static_graph: the FIRST backward must be a synchronised one --
+    DDP records the graph there -- so accumulation starts with a closing micro-step, as the reference's warm-up does.)"""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return model
+    on_gpu = next(model.parameters()).is_cuda
+    if sync_bn and on_gpu:
+        model = nn.SyncBatchNorm.convert_sync_batchnorm(model)
+    kw = dict(device_ids=[local_rank], output_device=local_rank) if on_gpu else {}
+    return nn.parallel.DistributedDataParallel(model, gradient_as_bucket_view=True, static_graph=True,
+                                               broadcast_buffers=False, bucket_cap_mb=64, **kw)
+
+
+def make_optimizer(model: nn.Module, lr: float = 0.01, momentum: float = 0.937, weight_decay: float = 5e-4):
+    """The reference's three parameter groups (utils/torch_utils.py smart_optimizer: weights with decay, BatchNorm /
+    LayerNorm weights and all biases without), SGD with Nesterov momentum (data/hyps/hyp.VisDrone.yaml), multi-tensor."""
+    decay, no_decay = [], []
+    norms = tuple(v for k, v in nn.__dict__.items() if "Norm" in k and isinstance(v, type))
+    for mod in model.modules():
+        for name, p in mod.named_parameters(recurse=False):
+            if not p.requires_grad:
+                continue
+            (no_decay if name == "bias" or isinstance(mod, norms) else decay).append(p)
+    return torch.optim.SGD([{"params": decay, "weight_decay": weight_decay}, {"params": no_decay, "weight_decay": 0.0}],
+                           lr=lr, momentum=momentum, nesterov=True, foreach=True)
+
+
+def yolo_surrogate_loss(preds, targets, nc: int):
+    """A YOLO-shaped loss for the step harness: objectness BCE over every anchor of every level, class BCE and box L1 at
+    the cells the targets fall into.  (The reference's ComputeLoss -- build_targets' anchor matching + CIoU,
+    utils/loss.py -- is outside the hot path; this has the same inputs, touches every output element
+    and back-propagates through every layer, without a host synchronisation.)
+    preds: list of [B, na, H, W, nc + 5]; targets: [T, 6] = (image, class, x, y, w, h) normalised."""
+    img, cls = targets[:, 0].long(), targets[:, 1].long()
+    total = preds[0].new_zeros((), dtype=torch.float32)
+    for p in preds:
+        b, na, h, w, no = p.shape
+        p = p.float()
+        gx = (targets[:, 2] * w).long().clamp_(0, w - 1)
+        gy = (targets[:, 3] * h).long().clamp_(0, h - 1)
+        obj = torch.zeros(b, na, h, w, device=p.device)
+        obj[img, :, gy, gx] = 1.0
+        total = total + nn.functional.binary_cross_entropy_with_logits(p[..., 4], obj)
+        sel = p[img, :, gy, gx]                                         # [T, na, no]
+        want_cls = nn.functional.one_hot(cls, nc).float()[:, None].expand(-1, na, -1)
+        total = total + 0.5 * nn.functional.binary_cross_entropy_with_logits(sel[..., 5:], want_cls)
+        total = total + 0.05 * (sel[..., :4].sigmoid() - targets[:, None, 2:6]).abs().mean()
+    return total
+
+
+class TrainStep:
+    """One optimizer step of the reference's loop (train.py:249-283) without its per-iteration host synchronisations.
+
+    step(imgs, targets, last_micro=True): autocast forward, loss, backward (under no_sync() unless `last_micro`), and on
+    the last micro-step optimizer step + zero_grad + EMA.  The running mean loss lives on the device; `loss_for_log()`
+    returns the value recorded at the last `log_every` boundary (read through a pinned buffer guarded by an event)."""
+
+    def __init__(self, model: nn.Module, nc: int, optimizer=None, ema: FusedModelEMA | None = None,
+                 autocast_dtype: torch.dtype | None = torch.bfloat16, log_every: int = 50, max_norm: float = 10.0):
+        self.model, self.nc = model, nc
+        self.optimizer = optimizer or make_optimizer(model)
+        self.ema, self.dtype, self.log_every, self.max_norm = ema, autocast_dtype, log_every, max_norm
+        dev = next(model.parameters()).device
+        self.device = dev
+        self._mloss = torch.zeros((), device=dev)
+        self._steps = 0
+        self._host = torch.zeros((), pin_memory=True) if dev.type == "cuda" else torch.zeros(())
+        self._event = torch.cuda.Event() if dev.type == "cuda" else None
+        self._logged = None
+
+    def step(self, imgs: torch.Tensor, targets: torch.Tensor, last_micro: bool = True) -> torch.Tensor:
+        ddp = isinstance(self.model, nn.parallel.DistributedDataParallel)
+        sync_ctx = self.model.no_sync() if (ddp and not last_micro) else contextlib.nullcontext()
+        amp = torch.autocast(self.device.type, dtype=self.dtype) if self.dtype is not None else contextlib.nullcontext()
+        with sync_ctx:
+            with amp:
+                preds = self.model(imgs)
+            loss = yolo_surrogate_loss(preds, targets, self.nc)
+            if ddp:
+                loss = loss * dist.get_world_size()          # DDP averages the gradients (train.py:266-267)
+            loss.backward()
+        if last_micro:
+            if self.max_norm:
+                torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.max_norm, foreach=True)   # train.py:272
+            self.optimizer.step()
+            self.optimizer.zero_grad(set_to_none=True)
+            if self.ema is not None:
+                self.ema.update(self.model)
+            self._steps += 1
+            self._mloss.mul_(1.0 - 1.0 / self._steps).add_(loss.detach() / self._steps)
+            if self._steps % self.log_every == 0:
+                self._host.copy_(self._mloss, non_blocking=True)
+                if self._event is not None:
+                    self._event.record()
+                self._logged = self._steps
+        return loss.detach()
+
+    def loss_for_log(self):
+        """(step, mean loss) of the last logging boundary, or None; waits only for that boundary's copy."""
+        if self._logged is None:
+            return None
+        if self._event is not None:
+            self._event.synchronize()
+        return self._logged, float(self._host)
+
+
+def synthetic_batch(batch: int, size: int = 640, nc: int = 10, boxes_per_image: int = 64, device="cuda", seed: int = 0):
+    """VisDrone-shaped synthetic batch: imgs ~ U[0, 1) [B, 3, S, S]; targets [B * 64, 6] = (image, class,
+    x, y, w, h) with tiny boxes (w, h ~ logU(0.005, 0.08))."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    imgs = torch.rand(batch, 3, size, size, generator=g)
+    t = batch * boxes_per_image
+    wh = torch.exp(torch.empty(t, 2).uniform_(math.log(0.005), math.log(0.08), generator=g))
+    targets = torch.cat([torch.arange(batch).repeat_interleave(boxes_per_image)[:, None].float(),
+                         torch.randint(0, nc, (t, 1), generator=g).float(), torch.rand(t, 2, generator=g), wh], 1)
+    return imgs.to(device), targets.to(device)
