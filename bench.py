@@ -368,7 +368,7 @@ def _kernel_split(prof):
     return fam, {k: sorted(v)[:8] for k, v in names.items()}
 
 
-def train_row(args, rank, world, local_rank, dev):
+def train_row(args, rank, world, local_rank, dev, amp_dtype=torch.float16):
     """BASELINE configs[3]: the YOLOv5l-DCNv3 training step on synthetic VisDrone-shaped 640 x 640 batches, GLOBAL batch
     128 split over the ranks (strong scaling: 128 / 64 / 32 / 16 images per GPU at 1 / 2 / 4 / 8), bf16 autocast,
     DistributedDataParallel over NCCL with one gradient all-reduce per optimizer step, SGD + fused EMA.  Every rank
@@ -385,7 +385,7 @@ def train_row(args, rank, world, local_rank, dev):
     n_params = sum(p.numel() for p in model.parameters())
     ema = FusedModelEMA(model) if rank == 0 else None
     ddp = wrap_ddp(model, local_rank)
-    ts = TrainStep(ddp, nc=10, optimizer=make_optimizer(model), ema=ema)
+    ts = TrainStep(ddp, nc=10, optimizer=make_optimizer(model), ema=ema, autocast_dtype=amp_dtype)
     # the reference's loader hands uint8 images on the host; the step copies them (train.py:249-250)
     imgs, targets = synthetic_batch(per, 640, device="cpu", seed=rank)
     host_u8 = (imgs * 255).to(torch.uint8).pin_memory()
@@ -433,7 +433,7 @@ def train_row(args, rank, world, local_rank, dev):
     if world == 1:
         m = ema.ema
         x = torch.rand(32, 3, 640, 640, device=dev).to(memory_format=torch.channels_last)
-        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        with torch.no_grad(), torch.autocast("cuda", dtype=amp_dtype):
             for _ in range(3):
                 m(x)
             torch.cuda.synchronize()
@@ -443,7 +443,7 @@ def train_row(args, rank, world, local_rank, dev):
                 m(x)
             b.record(); torch.cuda.synchronize()
         infer = {"img_per_s": 32 * 10 / (a.elapsed_time(b) * 1e-3), "batch": 32, "ms_per_batch": a.elapsed_time(b) / 10,
-                 "config": "BASELINE configs[2]: YOLOv5l-DCNv3 inference, synthetic 640x640 batch 32, bf16 autocast, EMA weights"}
+                 "config": f"BASELINE configs[2]: YOLOv5l-DCNv3 inference, synthetic 640x640 batch 32, {str(amp_dtype)[6:]} autocast, EMA weights"}
     mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
     del ts, ddp, model, ema
     torch.cuda.empty_cache()
@@ -458,8 +458,10 @@ def train_row(args, rank, world, local_rank, dev):
         "scaling": "strong", "steps": steps, "warmup": 3, "loss_last": loss_val, "peak_mem_gib": mem,
         "model": "YOLOv5l-DCNv3 (stock YOLOv5l layout, the four head C3 stages are C3_DCNv3: 12 DCNv3 layers)",
         "params": n_params, "layers": layers(),
-        "step": "uint8 host batch -> H2D -> bf16 autocast forward -> YOLO-shaped surrogate loss -> backward -> "
-                "clip -> SGD(nesterov, foreach) -> fused EMA (rank 0); no host sync inside the step",
+        "amp_dtype": str(amp_dtype)[6:],
+        "step": f"uint8 host batch -> H2D -> {str(amp_dtype)[6:]} autocast forward -> YOLO-shaped surrogate loss -> "
+                "(GradScaler for fp16, as train.py:263-274) backward -> unscale -> clip -> fused SGD(nesterov), which "
+                "skips an overflowed step on the device -> fused EMA (rank 0); no host sync inside the step",
         "ddp": {"backend": "nccl" if world > 1 else None, "gradient_as_bucket_view": True, "static_graph": True,
                 "broadcast_buffers": False, "bucket_cap_mb": 64, "allreduce_bytes_per_step": grad_bytes if world > 1 else 0},
         "gpu_time_split_rank0": split, "kernels_seen": kernels, "limiter": limiter, "inference": infer,
@@ -522,6 +524,19 @@ def run_ours(args, rank, world, local_rank):
     # host-buffer entry point of the C ABI (dcnv3_host_pipeline_*): every step copies its four
     # inputs H2D and its four results D2H; chunks of 8 images overlap copy-in, kernels and copy-out
     from yolo_somi_b200.host_pipeline import DCNv3HostPipeline
+    cpu_bind = None
+    if world > 1 and hasattr(os, "sched_setaffinity"):
+        # one slice of the host cores per rank BEFORE the pinned buffers are allocated and first touched (the copies'
+        # staging threads and the pages then stay with the rank; every GPU of this pool reports NUMA node 0, so this
+        # cannot fix a shared root complex -- the bare-copy baseline below says what the box can do)
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+            os.sched_setaffinity(0, mine)
+            cpu_bind = [mine[0], mine[-1]]
+        except OSError:
+            cpu_bind = None
     host_in = [t.cpu().pin_memory() for t in sets[0]]
     pipe = DCNv3HostPipeline(CFG["H"], CFG["W"], CFG["G"], CFG["C"] // CFG["G"], kernel=CFG["K"],
                              stride=CFG["stride"], pad=CFG["pad"], dilation=CFG["dil"],
@@ -549,15 +564,74 @@ def run_ours(args, rank, world, local_rank):
     if not torch.equal(ref_out.cpu(), host_out[0]):
         raise SystemExit("bench.py: host pipeline output differs from the device-resident forward")
     pipe.close()
+    # the box's ceiling for this traffic: the same bytes as bare cudaMemcpyAsync calls (one per tensor), H2D on one
+    # stream and D2H on another at the same time, no kernels -- every rank at once, max over ranks
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    dev_in = [torch.empty_like(t, device=dev) for t in host_in]
+    dev_out = [torch.empty_like(t, device=dev) for t in host_out]
+    def bare_copy():
+        with torch.cuda.stream(s_in):
+            for h, d in zip(host_in, dev_in):
+                d.copy_(h, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            for h, d in zip(host_out, dev_out):
+                h.copy_(d, non_blocking=True)
+    bare_copy(); torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        bare_copy()
+    torch.cuda.synchronize()
+    bare_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    bare_ms = max_over_ranks(bare_ms, dev)
+    del dev_in, dev_out
 
     # ---- SURVEY 8(f) rank 1, measured beside the sampler: the fused offset/mask projection
     # (tcgen05 GEMM + bias + softmax epilogue) against the layer's two linears + softmax, same shape
+    def timed_mode(env, iters=5):
+        for k, val in env.items():
+            os.environ[k] = val
+        try:
+            v, o, m, go = sets[0]
+            for _ in range(2):
+                DCNv3.dcnv3_forward(v, o, m, *g, 256); DCNv3.dcnv3_backward(v, o, m, *g, go, 256)
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            a.record()
+            for i in range(iters):
+                DCNv3.dcnv3_forward(*sets[i % ROTATE][:3], *g, 256)
+            b.record()
+            for i in range(iters):
+                vv, oo, mm, gg = sets[i % ROTATE]
+                DCNv3.dcnv3_backward(vv, oo, mm, *g, gg, 256)
+            c.record(); torch.cuda.synchronize()
+            return {"fwd_ms": a.elapsed_time(b) / iters, "bwd_ms": b.elapsed_time(c) / iters}
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+    modes = None
+    if rank == 0:
+        modes = {
+            "default": "forward: bilinear x mask coefficients rounded to bf16 (one FHFMA per element); backward: exact "
+                       "grad_out x value products, grad_value through the tcgen05 product with bf16 coefficient sums; "
+                       "fp32 accumulation everywhere (errors: profiles/parity_r2.json)",
+            "strict_fp32_coefficients": dict(timed_mode({"DCNV3_WEIGHTS": "split", "DCNV3_BWD": "scatter"}),
+                                             env="DCNV3_WEIGHTS=split DCNV3_BWD=scatter",
+                                             note="every coefficient fp32 as the reference's opmath_t; errors = output rounding only"),
+            "deterministic": dict(timed_mode({"DCNV3_DETERMINISTIC": "1"}), env="DCNV3_DETERMINISTIC=1",
+                                  note="bit-reproducible backward: 64-bit fixed-point accumulation of grad_value"),
+        }
     proj = proj_row(dev, dtype) if rank == 0 else None
     layer = layer_row(dev, dtype) if rank == 0 else None
     # ---- BASELINE configs[2] / [3]: the model-level step, every rank takes part (NCCL gradient all-reduce)
     del sets, host_in, host_out
     torch.cuda.empty_cache()
     train = None if args.no_train else train_row(args, rank, world, local_rank, dev)
+    if train is not None and world == 1 and os.environ.get("BENCH_TRAIN_BF16", "1") != "0":
+        # the same step in bf16: PyTorch 2.11 has no cuDNN BatchNorm for bf16 (native kernel: 2.9x slower,
+        # scripts/bn_probe.py), which is why the headline row uses the reference's own AMP dtype
+        alt = train_row(args, rank, world, local_rank, dev, amp_dtype=torch.bfloat16)
+        train["bf16_autocast"] = {k: alt[k] for k in ("img_per_s", "ms_per_step", "limiter", "gpu_time_split_rank0")}
 
     if rank != 0:
         return
@@ -581,7 +655,13 @@ def run_ours(args, rank, world, local_rank):
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / e2e_steps,
                 "api": "dcnv3_host_pipeline_run (C ABI, pinned host buffers, 8-image chunks, H2D | kernels | D2H on three streams)",
-                "timing": "host clock around enqueue + drain of all steps (the pipeline owns its streams)"},
+                "timing": "host clock around enqueue + drain of all steps (the pipeline owns its streams)",
+                "bare_copy_ms_per_step": bare_ms / e2e_steps,
+                "bare_copy": "the same H2D + D2H bytes as plain cudaMemcpyAsync per tensor on two streams, no kernels, all ranks at once",
+                "pcie_gbs_each_way_per_gpu_bare": h2d / (bare_ms / e2e_steps * 1e-3) / 1e9,
+                "host_link_gbs_aggregate_bare": world * (h2d + d2h) / (bare_ms / e2e_steps * 1e-3) / 1e9,
+                "pipeline_over_bare_copy": (e2e_ms / e2e_steps) / (bare_ms / e2e_steps),
+                "cpu_cores_bound": cpu_bind},
         "gpu_launches": 4 * args.steps,   # fwd_gs, bwd_dots, bwd_vmma, narrow_f32 (the memset is the driver's)
         "roofline": {"bound": "hbm", "kernel": "backward pass: bdots::bwd_dots (also zeroes the fp32 plane) + vmma::bwd_vmma (tcgen05 / TMEM) + narrow_f32, chained by programmatic dependent launch",
                      "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
@@ -594,6 +674,8 @@ def run_ours(args, rank, world, local_rank):
     }
     if proj is not None:
         line["next_rows"] = {"offset_mask_proj": proj, "layer": layer}
+    if modes is not None:
+        line["precision_modes"] = modes
     if train is not None:
         line["train_step"] = train
         line["img_per_s"] = train["img_per_s"]

@@ -9,11 +9,11 @@ tail -25 gpurun_out/pytest.log
 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke.log
 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 if [ "${NCU:-1}" = "1" ]; then
-  python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/plain.log 2>&1 &&
+  python bench.py --steps 2 --warmup 1 --no-cpu --no-train > gpurun_out/plain.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv \
-      --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu_list.log 2>&1
+      --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-train > gpurun_out/ncu_list.log 2>&1
   echo "ncu list rc=$?"
   ncu --set full --clock-control none --import-source on -k regex:"fwd_|bwd_" -s 6 -c 4 \
-      -o gpurun_out/prof_r1 -f python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu_full.log 2>&1
+      -o gpurun_out/prof_r2 -f python bench.py --steps 2 --warmup 1 --no-cpu --no-train > gpurun_out/ncu_full.log 2>&1
   echo "ncu full rc=$?"
 fi

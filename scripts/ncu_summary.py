@@ -24,7 +24,13 @@ WANT = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
         'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
-        'smsp__sass_average_data_bytes_per_sector_mem_global_op_ld.pct']
+        'smsp__sass_average_data_bytes_per_sector_mem_global_op_ld.pct',
+        # tensor pipe (tcgen05): instruction share and the tensor-memory / operand paths
+        'sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active',
+        'sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active']
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, units = rows[0], rows[1]
 idx = {h: i for i, h in enumerate(hdr)}

@@ -14,10 +14,7 @@ import DCNv3
 
 
 def run(which, dv, do_, dm, dg, geom):
-    if which == 'vmma':
-        os.environ['DCNV3_VALUE'] = 'vmma'
-    else:
-        os.environ.pop('DCNV3_VALUE', None)
+    os.environ['DCNV3_VALUE'] = 'band' if which == 'vband' else 'vmma'
     grads = DCNv3.dcnv3_backward(dv, do_, dm, *geom, dg, 256)
     torch.cuda.synchronize()
     return grads

@@ -105,7 +105,9 @@ def test_half_precision_vs_oracle(case, dt):
     for name, a, w in zip(WHAT, got, (out, gv, go, gm)):
         rms = float(np.sqrt(np.mean(w ** 2))) + 1e-30
         frac = allclose_frac(a, w, rtol=1e-2, atol=1e-2 * rms)
-        assert frac <= (2e-3 if name == "go" else 1e-4), (name, frac, max_abs(a, w), rms)
+        # allowances from profiles/parity_r2.json (measured: 0 for out / grad_mask, <= 1e-4 for grad_value with the
+        # default bf16 coefficients, <= 2e-6 for grad_offset, whose outliers are floor() flips)
+        assert frac <= (5e-4 if name == "go" else 1e-4), (name, frac, max_abs(a, w), rms)
 
 
 # ----------------------------------------------------------------------------- tiled kernels
@@ -166,7 +168,9 @@ def test_tiled_kernels_vs_oracle(case, spread, bwd, fwd, monkeypatch):
         # grad_value of the tensor-core backward carries the bf16 rounding of the per-pixel
         # coefficient sums (up to 25 taps x 4 corners at K=5): allow 1e-3 of the elements to sit
         # between 1x and 5x the bound
-        lim = 2e-3 if name == "go" else (1e-3 if name in ("out", "gv") and dt != torch.float32 else 1e-4)
+        # (grad_offset: floor() flips -- these maps are small, 2e-3 is some 40 elements; sigma != 1 and the offsets
+        # scaled x4 put more coordinates next to an integer)
+        lim = 2e-3 if name == "go" else (5e-4 if name in ("out", "gv") and dt != torch.float32 else 1e-4)
         assert frac <= lim, (name, frac, max_abs(a, w), rms)
         assert max_abs(a, w) <= 5e-2 * max(rms, float(np.abs(w).max()) * 0.2) or name == "go"
 
@@ -185,7 +189,7 @@ def test_default_kernels_fp16(case, spread):
     for name, a, w in zip(WHAT, got, (out, gv, go, gm)):
         rms = float(np.sqrt(np.mean(w ** 2))) + 1e-30
         frac = allclose_frac(a, w, rtol=1e-2, atol=1e-2 * rms)
-        assert frac <= (2e-3 if name == "go" else 1e-3), (name, frac, max_abs(a, w), rms)
+        assert frac <= (5e-4 if name == "go" else 1e-4), (name, frac, max_abs(a, w), rms)
 
 
 @pytest.mark.parametrize("kg", ["4", "8"])
@@ -384,8 +388,18 @@ def test_cfg2_full_size_against_direct_oracle(dt):
         frac = allclose_frac(a, w, rtol=rtol, atol=(1e-4 if dt == "f32" else 1e-2) * rms)
         # 16-bit default kernels are the tensor-core ones: out and grad_value carry the rounding of
         # the per-pixel coefficient sums to the I/O dtype
-        lim = 1e-4 if name == "go" else (1e-3 if (name in ("out", "gv") and dt != "f32") else 1e-6)
+        # allowances from profiles/parity_r2.json: measured 0 (out, grad_mask), 5.6e-5 (grad_value), 0 (grad_offset)
+        lim = 2e-5 if name == "go" else (2e-4 if (name == "gv" and dt != "f32") else (1e-5 if dt != "f32" else 1e-6))
         assert frac <= lim, (name, frac, max_abs(a, w), rms)
+        if dt == "f32":
+            # SURVEY section 7's protocol: at the north star's literal 1e-5 / 1e-6 ANY fp32 evaluation of the reference's
+            # formulas violates a few per cent on N(0, 1) data at 80 px; the kernel must not violate more than the same
+            # formulas evaluated in fp32 on the CPU do (profiles/parity_r2.json: 2.58 % vs 2.58 % for `out`)
+            strict = allclose_frac(a, w, rtol=1e-5, atol=1e-6 * max(1.0, rms))
+            if name == "out":
+                f32 = [x.astype(np.float32) for x in arrs[:3]]
+                cpu = np.asarray(orc.direct_forward(*f32, *geom, dtype=np.float32), dtype=np.float64)
+                assert strict <= 1.05 * allclose_frac(cpu, w, rtol=1e-5, atol=1e-6 * max(1.0, rms)) + 1e-6, (name, strict)
 
 
 @pytest.mark.parametrize("dt", ["f32", "bf16"])

@@ -23,7 +23,7 @@ def _oracle(arrs, geom):
     return (orc.direct_forward(*arrs[:3], *geom), *orc.direct_backward(*arrs, *geom))
 
 
-def _check_16bit(got, want, dt, go_frac=2e-3, frac=1e-3, cap=8e-2):
+def _check_16bit(got, want, dt, go_frac=5e-4, frac=3e-4, cap=8e-2):
     """1e-2 relative (north_star) with a floor of 1e-2 x RMS; at most `frac` of the elements outside (grad_offset:
     `go_frac`, floor() flips at pixel boundaries); and NO element further off than cap x max(RMS, |w|) -- except
     grad_offset, whose flipped elements are legitimately a different branch of a discontinuous function."""
@@ -70,7 +70,7 @@ def test_backward_lattice_offsets_all_kernel_families(dt, mode, bwd, monkeypatch
         for name, a, w in zip(WHAT, got, want):
             assert allclose_frac(a, w, rtol=1e-5, atol=2e-6 * (1.0 + float(np.abs(w).max()))) == 0.0, (name, max_abs(a, w))
     else:
-        _check_16bit(got, want, dt, go_frac=0.0, frac=1e-3)
+        _check_16bit(got, want, dt, go_frac=0.0, frac=3e-4)
     # the points the reference's range test rejects have exactly zero gradients
     go, gm = got[2], got[3]
     o = arrs[1].reshape(c.N, c.Ho, c.Wo, c.G, c.P, 2)

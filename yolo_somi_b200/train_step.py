@@ -221,8 +221,11 @@ def make_optimizer(model: nn.Module, lr: float = 0.01, momentum: float = 0.937, 
             if not p.requires_grad:
                 continue
             (no_decay if name == "bias" or isinstance(mod, norms) else decay).append(p)
-    return torch.optim.SGD([{"params": decay, "weight_decay": weight_decay}, {"params": no_decay, "weight_decay": 0.0}],
-                           lr=lr, momentum=momentum, nesterov=True, foreach=True)
+    groups = [{"params": decay, "weight_decay": weight_decay}, {"params": no_decay, "weight_decay": 0.0}]
+    on_gpu = any(p.is_cuda for p in decay + no_decay)
+    # fused on the GPU: one multi-tensor kernel, and it takes GradScaler's found_inf tensor, so an fp16 step that
+    # overflowed is skipped ON THE DEVICE (the unfused path reads found_inf with .item(): a host sync per step)
+    return torch.optim.SGD(groups, lr=lr, momentum=momentum, nesterov=True, **({"fused": True} if on_gpu else {"foreach": True}))
 
 
 def yolo_surrogate_loss(preds, targets, nc: int):
@@ -267,6 +270,8 @@ class TrainStep:
         self._host = torch.zeros((), pin_memory=True) if dev.type == "cuda" else torch.zeros(())
         self._event = torch.cuda.Event() if dev.type == "cuda" else None
         self._logged = None
+        # fp16 autocast (the reference's AMP dtype, train.py:263) needs the reference's GradScaler (train.py:217,268-274)
+        self.scaler = torch.amp.GradScaler(dev.type) if (autocast_dtype == torch.float16 and dev.type == "cuda") else None
 
     def step(self, imgs: torch.Tensor, targets: torch.Tensor, last_micro: bool = True) -> torch.Tensor:
         ddp = isinstance(self.model, nn.parallel.DistributedDataParallel)
@@ -278,11 +283,17 @@ class TrainStep:
             loss = yolo_surrogate_loss(preds, targets, self.nc)
             if ddp:
                 loss = loss * dist.get_world_size()          # DDP averages the gradients (train.py:266-267)
-            loss.backward()
+            (self.scaler.scale(loss) if self.scaler is not None else loss).backward()
         if last_micro:
+            if self.scaler is not None:
+                self.scaler.unscale_(self.optimizer)                                                   # train.py:271
             if self.max_norm:
                 torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.max_norm, foreach=True)   # train.py:272
-            self.optimizer.step()
+            if self.scaler is not None:
+                self.scaler.step(self.optimizer)      # fused optimizer: found_inf stays on the device
+                self.scaler.update()
+            else:
+                self.optimizer.step()
             self.optimizer.zero_grad(set_to_none=True)
             if self.ema is not None:
                 self.ema.update(self.model)
