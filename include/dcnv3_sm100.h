@@ -164,6 +164,23 @@ DCNV3_API int dcnv3_dwconv_ln_gelu_sm100(const void *x, const void *w_dw, const 
                         int N, int H, int W, int C, int k, float eps, int dtype,
                         void *stream /* cudaStream_t */);
 
+/* Backward of that producer (k == 3), two passes over the activation tensor instead of the reference's autograd chain
+ * (permute / conv backward / permute / LayerNorm backward / GELU backward, modules/dcnv3.py:276-289,328-329):
+ *   x, conv_out (as written by the forward), grad_out [N,H,W,C] 16-bit; w_dw [9][C] as above; gamma, beta [C] fp32;
+ *   du_scratch [N,H,W,C] 16-bit (the LayerNorm's input gradient, consumed by the second pass); grad_x [N,H,W,C];
+ *   grad_params: 12 C floats, written as [grad_w_dw [9][C] | grad_b_dw [C] | grad_gamma [C] | grad_beta [C]] (fp32,
+ *   zeroed here, summed with reductions: not bit-reproducible across runs, as the reference's cuDNN wgrad).
+ */
+DCNV3_API int dcnv3_dwconv_ln_gelu_backward_sm100(const void *x, const void *conv_out, const void *grad_out,
+                        const void *w_dw, const float *gamma, const float *beta, void *du_scratch, void *grad_x,
+                        float *grad_params, int N, int H, int W, int C, int k, float eps, int dtype,
+                        void *stream /* cudaStream_t */);
+
+/* Gradient of the mask logits from the gradient of the soft-maxed masks (modules/dcnv3.py:331-334):
+ * grad_logit[r, p] = mask[r, p] * (grad_mask[r, p] - sum_q grad_mask[r, q] mask[r, q]),  r = (pixel, group), fp32 math. */
+DCNV3_API int dcnv3_mask_softmax_backward_sm100(const void *grad_mask, const void *mask, void *grad_logit,
+                        long long rows, int points, int dtype, void *stream /* cudaStream_t */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -217,3 +217,54 @@ def test_reference_default_shapes(name, kw, dt):
             assert allclose_frac(a, w, rtol=1e-5, atol=1e-5 * (1.0 + float(np.sqrt(np.mean(w ** 2))))) <= lim, (nm, max_abs(a, w))
     else:
         _check_16bit(got, want, dt)
+
+
+# ----------------------------------------------------------------------------- fused producer backward kernels
+@pytest.mark.parametrize("dt", ["bf16", "f16"])
+@pytest.mark.parametrize("N,H,W,C", [(2, 16, 24, 256), (1, 13, 19, 128), (3, 9, 8, 64)])
+def test_fused_dwconv_ln_gelu_backward_matches_fp64_autograd(N, H, W, C, dt):
+    """csrc/dcnv3_dwconv_bwd.cu (LayerNorm + GELU backward with the channel sums, depthwise dgrad + wgrad on TMA windows)
+    against autograd of conv2d(groups=C) -> layer_norm -> gelu in fp64 on the rounded inputs (modules/dcnv3.py:276-289):
+    all five gradients, 1e-2 relative with a floor of 1e-2 x RMS; ragged tiles included."""
+    from yolo_somi_b200.ops_dcnv3.functions import dwconv_ln_gelu as dlg
+    dtype = TDT[dt]
+    g = torch.Generator(device="cpu").manual_seed(N * H + C)
+    x = torch.randn(N, H, W, C, generator=g).to(dtype)
+    w = (torch.randn(C, 1, 3, 3, generator=g) / 3).to(dtype)
+    b, gamma, beta = torch.randn(C, generator=g), 1 + 0.3 * torch.randn(C, generator=g), torch.randn(C, generator=g)
+    go = torch.randn(N, H, W, C, generator=g).to(dtype)
+    args = [t.cuda().requires_grad_(True) for t in (x, w.float(), b, gamma, beta)]
+    out = dlg.DwConvLnGelu.apply(*args, 1e-6, dtype)
+    out.backward(go.cuda())
+    torch.cuda.synchronize()
+    ref_in = [t.double().requires_grad_(True) for t in (x, w, b, gamma, beta)]
+    # the kernel's backward starts from the convolution output as the forward stored it (rounded to the I/O dtype)
+    want = torch.autograd.grad(dlg._unfused(*ref_in, 1e-6), ref_in, go.double())
+    for name, a, wv in zip(("grad_x", "grad_w", "grad_b", "grad_gamma", "grad_beta"), args, want):
+        a, wv = a.grad.double().cpu().numpy(), wv.numpy()
+        rms = float(np.sqrt(np.mean(wv ** 2)))
+        # reductions over N H W pixels of 16-bit-rounded du: relative L2 for the parameter gradients
+        if name == "grad_x":
+            assert allclose_frac(a, wv, rtol=2e-2, atol=2e-2 * rms) <= 1e-3, (name, max_abs(a, wv), rms)
+        else:
+            assert float(np.linalg.norm(a - wv) / (np.linalg.norm(wv) + 1e-30)) <= 1e-2, name
+
+
+@pytest.mark.parametrize("dt", ["bf16", "f16"])
+def test_mask_softmax_backward_kernel(dt):
+    from yolo_somi_b200 import _native
+    lib = _native.load()
+    dtype = TDT[dt]
+    rows, P = 4321, 9
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    mask = torch.softmax(torch.randn(rows, P, generator=gen), -1).to(dtype)
+    gm = torch.randn(rows, P, generator=gen).to(dtype)
+    dm, dg = mask.cuda(), gm.cuda()
+    out = torch.empty_like(dm)
+    rc = lib.dcnv3_mask_softmax_backward_sm100(dg.data_ptr(), dm.data_ptr(), out.data_ptr(), rows, P,
+                                               _native.BF16 if dt == "bf16" else _native.F16,
+                                               torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    want = torch._softmax_backward_data(gm.double(), mask.double(), -1, torch.float64)
+    eps = 2.0 ** -8 if dt == "bf16" else 2.0 ** -11
+    assert float((out.double().cpu() - want).abs().max()) <= 1.01 * eps * float(want.abs().max()) + 1e-9

@@ -84,7 +84,27 @@ class DwConvLnGelu(torch.autograd.Function):
     def backward(ctx, g):
         x16, w, b, gamma, beta, conv_out = ctx.saved_tensors
         c, k = x16.shape[-1], w.shape[-1]
-        # LayerNorm + GELU re-derived from the saved convolution output (two cheap passes) ...
+        if k == 3 and os.environ.get("DCNV3_FUSED_DWCONV_BWD", "1") not in ("0", ""):
+            # two passes (csrc/dcnv3_dwconv_bwd.cu): LayerNorm + GELU backward with the channel sums, then the depthwise
+            # convolution's dgrad + wgrad on TMA-staged windows
+            lib = _native.load()
+            n, h, wd, _ = x16.shape
+            wk, _, gf, tf = _pack(w, b, gamma, beta, ctx.dtype)
+            g16 = g.to(ctx.dtype).contiguous()
+            du = torch.empty_like(x16)
+            g_x = torch.empty_like(x16)
+            params = torch.empty(12 * c, dtype=torch.float32, device=x16.device)
+            with torch.cuda.device(x16.device):
+                rc = lib.dcnv3_dwconv_ln_gelu_backward_sm100(
+                    x16.data_ptr(), conv_out.data_ptr(), g16.data_ptr(), wk.data_ptr(), gf.data_ptr(), tf.data_ptr(),
+                    du.data_ptr(), g_x.data_ptr(), params.data_ptr(), n, h, wd, c, k, float(ctx.eps), _DT[ctx.dtype],
+                    torch.cuda.current_stream().cuda_stream)
+            _native.check(rc, "dcnv3_dwconv_ln_gelu_backward_sm100")
+            g_w = params[:9 * c].reshape(9, c).t().reshape(c, 1, 3, 3)
+            g_b, g_gamma, g_beta = params[9 * c:10 * c], params[10 * c:11 * c], params[11 * c:]
+            return (g_x.to(ctx.in_dtype), g_w.to(w.dtype), g_b.to(b.dtype), g_gamma.to(gamma.dtype),
+                    g_beta.to(beta.dtype), None, None)
+        # (other kernel sizes) LayerNorm + GELU re-derived from the saved convolution output under autograd ...
         with torch.enable_grad():
             y = conv_out.detach().requires_grad_(True)
             gl, bl = gamma.detach().to(ctx.dtype).requires_grad_(True), beta.detach().to(ctx.dtype).requires_grad_(True)

@@ -84,10 +84,17 @@ class OffsetMaskProj(torch.autograd.Function):
         g, p = ctx.group, ctx.points
         m = x2.shape[0]
         g_off = g_off.reshape(m, -1)
-        # softmax Jacobian in fp32 (as autograd would for the fp32 softmax of the unfused form), one kernel
-        g_logit = torch._softmax_backward_data(g_msk.reshape(m, g, p).float(), mask.reshape(m, g, p).float(), -1,
-                                               torch.float32).reshape(m, g * p).to(x2.dtype)
-        gx = g_off @ w_off.to(x2.dtype) + g_logit @ w_msk.to(x2.dtype)
+        # softmax Jacobian in fp32, one pass over 16-bit tensors (csrc/dcnv3_dwconv_bwd.cu: mask_softmax_bwd); the
+        # unfused form up-casts both operands, runs the fp32 soft-max backward and casts back: four passes
+        lib = _native.load()
+        g_msk16 = g_msk.reshape(m, g * p).to(x2.dtype).contiguous()
+        g_logit = torch.empty_like(g_msk16)
+        with torch.cuda.device(x2.device):
+            rc = lib.dcnv3_mask_softmax_backward_sm100(g_msk16.data_ptr(), mask.data_ptr(), g_logit.data_ptr(), m * g, p,
+                                                       _DT[x2.dtype], torch.cuda.current_stream().cuda_stream)
+        _native.check(rc, "dcnv3_mask_softmax_backward_sm100")
+        g_off = g_off.to(x2.dtype)
+        gx = torch.addmm(g_off @ w_off.to(x2.dtype), g_logit, w_msk.to(x2.dtype))     # second product accumulates: no add pass
         gw_off = (g_off.t() @ x2).to(w_off.dtype)
         gw_msk = (g_logit.t() @ x2).to(w_msk.dtype)
         # column sums of tall [M, n] matrices as a ones-row GEMM (fp32 accumulation inside cuBLAS):
