@@ -4,7 +4,7 @@ set -u
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q -k "${K:-tiled or half or cfg2}" > gpurun_out/pytest_quick.log 2>&1; echo "pytest rc=$?"
 tail -${TAIL:-15} gpurun_out/pytest_quick.log
-python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "bench rc=$?"
+python bench.py --steps 20 --warmup 5 --no-cpu --no-train > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "bench rc=$?"
 python - <<'PY'
 import json
 try:

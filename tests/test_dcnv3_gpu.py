@@ -510,8 +510,8 @@ def test_outputs_and_workspace_stay_inside_their_buffers(shape):
 
 # ----------------------------------------------------------------------------- stream capture
 def test_forward_backward_under_cuda_graph_capture():
-    """The default 16-bit backward forks a side stream inside the call (the fp32 plane's memset runs beside
-    the channel-sum kernel) and joins it with events: that must be legal under stream capture, and a replayed
+    """The default 16-bit backward chains its kernels by programmatic dependent launch (and, with DCNV3_ZERO=side, forks a
+    side stream inside the call): that must be legal under stream capture, and a replayed
     graph must give the eager results (out / grad_offset / grad_mask bit-identical, grad_value to its
     accumulation-order noise).  Static-shape training loops capture exactly this."""
     import DCNv3
@@ -532,7 +532,10 @@ def test_forward_backward_under_cuda_graph_capture():
         assert torch.equal(out, want[0])
         assert torch.equal(grads[1], want[2]) and torch.equal(grads[2], want[3])
         a, w = grads[0].double().cpu().numpy(), want[1].double().cpu().numpy()
-        assert max_abs(a, w) <= 2e-2 * float(np.sqrt(np.mean(w ** 2)))
+        # grad_value is not bit-reproducible: points that leave their patch's band are added to the stored 16-bit result
+        # with vector reductions (csrc/dcnv3_backward_vres.cu), and the order of two such additions to one cell can flip
+        # its last bit (bf16: 2^-7 of the value; measured by scripts/graph_stress.py: 10-30 cells of 350 k, one ulp)
+        assert (np.abs(a - w) <= 2e-2 * float(np.sqrt(np.mean(w ** 2))) + 2.0 ** -7 * np.abs(w)).all()
 
 
 # ----------------------------------------------------------------------------- host-buffer pipeline

@@ -93,10 +93,16 @@ absmax_kernel(const T *__restrict__ x, size_t n, unsigned *__restrict__ out_bits
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-narrow_f32_kernel(const float *__restrict__ src, T *__restrict__ dst, size_t n) {
+narrow_f32_kernel(const float *__restrict__ src, T *__restrict__ dst, size_t n, const unsigned long long *cond = nullptr,
+                  unsigned long long thr = 0) {
     // 8 elements per thread per step: two 128-bit loads, one 128-bit store (src/dst 16-byte aligned)
     // back to front: the accumulating kernels work image-major, so the END of the plane is what is still in L2
     asm volatile("griddepcontrol.wait;" ::: "memory");   // (a no-op unless launched as a programmatic dependent)
+    if (cond) {                                          // (conditional fall-back of dcnv3_backward_vres.cu)
+        unsigned long long count;                        // a volatile load: must not move above the wait
+        asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(count) : "l"(cond) : "memory");
+        if (count <= thr) return;
+    }
     const size_t n8 = n / 8;
     for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n8; j += (size_t)gridDim.x * blockDim.x) {
         const size_t i = n8 - 1 - j;
@@ -499,6 +505,35 @@ static cudaError_t backward_typed(const void *value, const void *offset, const v
             const bool split = !(e && e[0]) || (e[0] == 's' && e[1] == 'p');
             const char *ev = std::getenv("DCNV3_VALUE");
             const bool hmma = ev && ev[0] == 'h';
+            // group_channels == 16, maps up to 156 wide: grad_value with the accumulator resident in tensor memory
+            // (dcnv3_backward_vres.cu) -- written once in the I/O dtype: no fp32 plane, nothing to zero or to narrow.
+            // DCNV3_VALUE=mma keeps the plane form (dcnv3_backward_vmma.cu).
+            if (split && vec_ok && !(ev && ev[0]) && backward_vres_eligible(offset, mask, grad_out, grad_value, q) &&
+                backward_vmma_eligible(offset, mask, grad_out, acc, q)) {
+                cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
+                // (the channel-sum kernel zeroes the scratch header: the far-point counter lives there)
+                auto *counter = static_cast<unsigned long long *>(workspace);
+                if (try_launch_backward_dots(value, offset, mask, grad_out, grad_offset, grad_mask, q, dtype_tag, stream, &e1,
+                                             static_cast<float *>(workspace), kWorkspaceHeader)) {
+                    if (e1 != cudaSuccess) return e1;
+                    unsigned long long thr = 0;
+                    if (try_launch_backward_vres(offset, mask, grad_out, grad_value, acc, plane * sizeof(float), counter, &thr, q,
+                                                 dtype_tag, stream, &e2)) {
+                        if (e2 != cudaSuccess) return e2;
+                        // More than `thr` points beyond their patch's band (offsets of many pixels): the 16-bit atomics of
+                        // the far path would round too often.  The plane form then runs on top and overwrites grad_value;
+                        // both kernels read the count on the device and exit at once in the common case.
+                        static const bool no_fb = [] { const char *e = std::getenv("DCNV3_VRES_NOFALLBACK"); return e && e[0] == '1'; }();
+                        if (no_fb) return cudaSuccess;   // development only: far-heavy inputs then lose accuracy
+                        if (!try_launch_backward_vmma(offset, mask, grad_out, acc, q, dtype_tag, stream, &e2, counter, thr))
+                            return cudaErrorInvalidConfiguration;
+                        if (e2 != cudaSuccess) return e2;
+                        if ((err = pdl_launch(true, narrow_f32_kernel<T>, dim3(aux_blocks / 8), dim3(256), 0, stream,
+                                              static_cast<const float *>(acc), gv, plane, static_cast<const unsigned long long *>(counter), thr)) != cudaSuccess) return err;
+                        return cudaGetLastError();
+                    }
+                }
+            }
             if (split && vec_ok && q.G % 8 == 0 && (hmma || backward_vmma_eligible(offset, mask, grad_out, acc, q))) {
                 // The plane is zeroed by the channel-sum kernel itself (a slice per CTA, while the CTA waits for its
                 // window): no memset launch, no side stream.  DCNV3_ZERO=side keeps the earlier form (memset on a
@@ -532,7 +567,7 @@ static cudaError_t backward_typed(const void *value, const void *offset, const v
                         try_launch_backward_vstrip(offset, mask, grad_out, acc, q, dtype_tag, stream, &e2)) {
                         if (e2 != cudaSuccess) return e2;
                         if ((err = pdl_launch(pdl_for(q), narrow_f32_kernel<T>, dim3(aux_blocks), dim3(256), 0, stream,
-                                              static_cast<const float *>(acc), gv, plane)) != cudaSuccess) return err;
+                                              static_cast<const float *>(acc), gv, plane, static_cast<const unsigned long long *>(nullptr), 0ull)) != cudaSuccess) return err;
                         return cudaGetLastError();
                     }
                 }

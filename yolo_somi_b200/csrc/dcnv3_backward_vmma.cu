@@ -84,7 +84,20 @@ __device__ __forceinline__ void bulk_fill(uint32_t dst, const void *src, uint32_
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// re-zeroing of the A tile without the L2 round trip: st.bulk (sm_100: UMEMSETS) by the issuing thread, then a plain
+// arrive on the refill barrier (DCNV3_VMMA_REFILL=st)
+__device__ __forceinline__ void st_bulk_zero(uint32_t dst, uint32_t bytes) {
+    asm volatile("st.bulk.weak.shared::cta [%0], %1, 0;" ::"r"(dst), "l"((uint64_t)bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 struct VParams {
+    // run only if *cond > thr (the far-point count of dcnv3_backward_vres.cu; nullptr = always)
+    const unsigned long long *cond;
+    unsigned long long thr;
+    int refill_st;
     int bx_rel, by_rel;      // band origin relative to the first pixel of a strip's 8 x 8 patch
     int tiles_x, tiles_xy, total_tiles;
     int steps;               // 8-row steps per work item
@@ -127,25 +140,12 @@ __device__ __forceinline__ void drain_block(uint32_t tmem_base, int slot, int wa
     }
 }
 
-// 4-D tensor map over a [N, Ho, Wo, row_elems] tensor of 16-bit elements, box (box_elems, 8, 8, 1).  The box
-// may start at any element (a group's run) and run past the row / the map: the hardware zero-fills.
-static bool make_run_tensor_map(CUtensorMap *map, const void *base, int dtype, int N, int Ho, int Wo, int row_elems,
-                                int box_elems) {
-    EncodeTiledFn fn = encode_tiled_fn();
-    if (!fn) return false;
-    const cuuint64_t es = 2;
-    const CUtensorMapDataType dt = dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-    const cuuint64_t dims[4] = {(cuuint64_t)row_elems, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
-    const cuuint64_t strides[3] = {(cuuint64_t)row_elems * es, (cuuint64_t)Wo * row_elems * es,
-                                   (cuuint64_t)Ho * Wo * row_elems * es};
-    const cuuint32_t box[4] = {(cuuint32_t)box_elems, (cuuint32_t)kStripW, (cuuint32_t)kRows, 1u};
-    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
-    return fn(map, dt, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-template <typename T, int NCH>
+// AMN: layout of the coefficient tile.  false = K-major rows of 64 pixels with the 128-byte swizzle, 16-bit
+// read-modify-writes (r1); true = MN-major core matrices [8 cells of one band row][8 pixels] -- a pixel's eight cells
+// are 16 contiguous bytes whose bank group is fixed by the PIXEL (k & 7), a horizontal corner pair that starts on an
+// even column is one 32-bit word: three word read-modify-writes per point on average instead of four 16-bit ones, and
+// only the word inside the lane's own bank group depends on the data.
+template <typename T, int NCH, bool AMN>
 __global__ void __launch_bounds__(kThreadsV, kCtasPerSm)
 bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ CUtensorMap tmap_msk,
          const __grid_constant__ CUtensorMap tmap_gout, float *__restrict__ gv_acc, const Geom q, const VParams pp) {
@@ -153,6 +153,12 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
     __shared__ __align__(8) uint64_t mma_bar, mma_bar1, zero_bar, full_bar[kStages];
     __shared__ uint32_t tmem_base_s;
 
+    if (pp.cond) {   // the fall-back of the resident-accumulator kernel: only when it left too many points to the far path
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        unsigned long long count;                        // a volatile load: must not move above the wait
+        asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(count) : "l"(pp.cond) : "memory");
+        if (count <= pp.thr) return;
+    }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // warps 0-1 (par == 0): builders, thread <-> pixel of the 8 x 8 patch; warps 2-3 join for the drain
     // (a tcgen05.ld reaches the 32 TMEM lanes of the warp's quarter, so 128 cells need four warps)
@@ -168,7 +174,7 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
     const uint32_t st_thr = smem_u32(stages) + strip_id * kStStrip;            // + stage * kStBytes
     const uint32_t a_strip = a_addr0 + strip_id * kATileBytes;
     const uint32_t kc = (uint32_t)k >> 3, kl = ((uint32_t)k & 7u) * 2u;
-    const uint32_t a_thr = a_strip + kl;
+    const uint32_t a_thr = AMN ? a_strip + kc * 128u + ((uint32_t)k & 7u) * 16u : a_strip + kl;
 
     const int C = q.G * q.gc, row_stride = q.W * C;
 
@@ -219,10 +225,15 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
     if (tid == 0) {   // the A tiles start (and after every product restart) as zeros: bulk copy, async proxy
-        mbar_expect_tx(&zero_bar, kStrips * kATileBytes);
-        bulk_fill(a_addr0, g_zero_tile, kStrips * kATileBytes, &zero_bar);
+        if (pp.refill_st) {
+            st_bulk_zero(a_addr0, kStrips * kATileBytes);
+            mbar_arrive(&zero_bar);
+        } else {
+            mbar_expect_tx(&zero_bar, kStrips * kATileBytes);
+            bulk_fill(a_addr0, g_zero_tile, kStrips * kATileBytes, &zero_bar);
+        }
     }
-    const uint32_t idesc = umma_idesc(std::is_same<T, __nv_bfloat16>::value ? 1 : 0, 128, NB);
+    const uint32_t idesc = umma_idesc(std::is_same<T, __nv_bfloat16>::value ? 1 : 0, 128, NB) | (AMN ? 1u << 15 : 0u);
 
     if (tid == 0) request(0, n, g, wo0, ho0);
 
@@ -298,6 +309,25 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                         if (VMMA_DIAG == 1) continue;
                         const uint32_t cx = (uint32_t)(int)fw, ry = (uint32_t)(int)fh;
                         const float hm = (1.f - lh) * m, lm = lh * m, hwt = 1.f - lw;
+                        if constexpr (AMN) {
+                            // word of (ry, cx): core-matrix group 2 ry + (cx >> 3) (1024 B each), word (cx & 7) >> 1
+                            const uint32_t cx1 = cx + 1u;
+                            const uint32_t e0 = a_thr + (ry * 2u + (cx >> 3)) * 1024u + ((cx & 6u) << 1);
+                            const uint32_t e1 = a_thr + (ry * 2u + (cx1 >> 3)) * 1024u + ((cx1 & 6u) << 1);
+                            const bool oddc = cx & 1u;
+                            float2 f0 = unpack2(lds32(e0), T()), f2 = unpack2(lds32(e0 + 2048u), T());
+                            if (oddc) { f0.y += hm * hwt; f2.y += lm * hwt; }
+                            else { f0.x += hm * hwt; f0.y += hm * lw; f2.x += lm * hwt; f2.y += lm * lw; }
+                            sts32(e0, pack2(f0.x, f0.y, T()));
+                            sts32(e0 + 2048u, pack2(f2.x, f2.y, T()));
+                            if (oddc) {
+                                float2 f1 = unpack2(lds32(e1), T()), f3 = unpack2(lds32(e1 + 2048u), T());
+                                f1.x += hm * lw; f3.x += lm * lw;
+                                sts32(e1, pack2(f1.x, f1.y, T()));
+                                sts32(e1 + 2048u, pack2(f3.x, f3.y, T()));
+                            }
+                            continue;
+                        }
                         const uint32_t e0 = a_thr + (ry * kBandW + cx) * 128u + ((kc ^ (cx & 7u)) << 4);
                         const uint32_t e1 = a_thr + (ry * kBandW + cx + 1u) * 128u + ((kc ^ ((cx + 1u) & 7u)) << 4);
                         const float a0 = f32_of((uint16_t)lds16(e0), T()), a1 = f32_of((uint16_t)lds16(e1), T());
@@ -342,8 +372,8 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                         const uint32_t bb = smem_u32(stages) + stage * kStBytes + st * kStStrip + kStGout;
 #pragma unroll
                         for (int j = 0; j < (VMMA_DIAG == 4 ? 0 : 4); ++j)   // K step = 16 pixels: 32 B of an A row, 256 B of the pixel-major B
-                            tc_mma(d, umma_desc_k_sw128(aa + j * 32), umma_desc_mn_plain(bb + j * 256, 128, 1024), idesc,
-                                   (uint32_t)(j > 0 || (blk == 0 && s > 0)));
+                            tc_mma(d, AMN ? umma_desc_mn_plain(aa + j * 256, 128, 1024) : umma_desc_k_sw128(aa + j * 32),
+                                   umma_desc_mn_plain(bb + j * 256, 128, 1024), idesc, (uint32_t)(j > 0 || (blk == 0 && s > 0)));
                         // the UPPER block (the one drained below) completes first: its own commit, so that the drain
                         // starts while the lower block's products still run
                         tc_commit(blk == 0 ? &mma_bar : &mma_bar1);
@@ -356,6 +386,9 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                 mbar_wait(&mma_bar1, commits & 1u);
                 if (VMMA_DIAG == 2) {
                     mbar_expect_tx(&zero_bar, 0);
+                } else if (pp.refill_st) {
+                    st_bulk_zero(a_addr0, kStrips * kATileBytes);
+                    mbar_arrive(&zero_bar);
                 } else {
                     mbar_expect_tx(&zero_bar, kStrips * kATileBytes);
                     bulk_fill(a_addr0, g_zero_tile, kStrips * kATileBytes, &zero_bar);
@@ -384,9 +417,13 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
 
 template <typename T>
 static bool launch_typed(const void *offset, const void *mask, const void *grad_out, float *gv_acc, const Geom &q,
-                         cudaStream_t stream, cudaError_t *err) {
+                         cudaStream_t stream, cudaError_t *err, const unsigned long long *cond, unsigned long long thr) {
     if (!backward_vmma_eligible(offset, mask, grad_out, gv_acc, q)) return false;
     VParams pp;
+    static const bool refill_st = [] { const char *e = std::getenv("DCNV3_VMMA_REFILL"); return e && e[0] == 's'; }();
+    pp.refill_st = refill_st;
+    pp.cond = cond;
+    pp.thr = thr;
     // nominal taps of a pixel x along an axis: x + a + i*sigma, i = 0..2, a = (1 - pad) - sigma; band centred on them
     const float a_w = (float)(1 - q.pw) - q.sigma, a_h = (float)(1 - q.ph) - q.sigma;
     pp.bx_rel = (int)std::floor(a_w + q.sigma + 0.5f * (kStripW - 1) + 0.5f - 0.5f * kBandW);
@@ -413,17 +450,20 @@ static bool launch_typed(const void *offset, const void *mask, const void *grad_
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    const int ctas = (int)std::min<long long>(total, (long long)kCtasPerSm * num_sms);
-    if (q.gc == 8) {
-        cudaFuncSetAttribute(bwd_vmma<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(16));
-        *err = pdl_launch(pdl_for(q), bwd_vmma<T, 8>, dim3(ctas), dim3(kThreadsV), smem_bytes(16), stream, to, tm, tg, gv_acc, q, pp);
-    } else if (q.gc == 16) {
-        cudaFuncSetAttribute(bwd_vmma<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(16));
-        *err = pdl_launch(pdl_for(q), bwd_vmma<T, 16>, dim3(ctas), dim3(kThreadsV), smem_bytes(16), stream, to, tm, tg, gv_acc, q, pp);
-    } else {
-        cudaFuncSetAttribute(bwd_vmma<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(32));
-        *err = pdl_launch(pdl_for(q), bwd_vmma<T, 32>, dim3(ctas), dim3(kThreadsV), smem_bytes(32), stream, to, tm, tg, gv_acc, q, pp);
-    }
+    // (as the conditional fall-back of dcnv3_backward_vres.cu the kernel almost always exits at once: one CTA per SM
+    // keeps that exit cheap; the work loop strides by the grid size)
+    const int ctas = (int)std::min<long long>(total, (long long)(cond ? 1 : kCtasPerSm) * num_sms);
+    // coefficient-tile layout: K-major swizzled tile (default); DCNV3_VMMA_A=m = MN-major with paired 32-bit
+    // read-modify-writes (measured: 10 % fewer shared-memory wavefronts, but +8 us -- the kernel is bound by its
+    // serial phases, not by the scatter's bank conflicts)
+    static const bool a_mn = [] { const char *e = std::getenv("DCNV3_VMMA_A"); return e && (e[0] == 'm' || e[0] == 'M'); }();
+    auto go = [&](auto kern, int nb) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(nb));
+        *err = pdl_launch(pdl_for(q) || cond, kern, dim3(ctas), dim3(kThreadsV), smem_bytes(nb), stream, to, tm, tg, gv_acc, q, pp);
+    };
+    if (q.gc == 8) { if (a_mn) go(bwd_vmma<T, 8, true>, 16); else go(bwd_vmma<T, 8, false>, 16); }
+    else if (q.gc == 16) { if (a_mn) go(bwd_vmma<T, 16, true>, 16); else go(bwd_vmma<T, 16, false>, 16); }
+    else { if (a_mn) go(bwd_vmma<T, 32, true>, 32); else go(bwd_vmma<T, 32, false>, 32); }
     if (*err == cudaSuccess) *err = cudaGetLastError();
     return true;
 }
@@ -443,10 +483,11 @@ bool backward_vmma_eligible(const void *offset, const void *mask, const void *gr
 
 // grad_value only (accumulated into the zeroed fp32 plane gv_acc); tcgen05 / TMEM form.
 bool try_launch_backward_vmma(const void *offset, const void *mask, const void *grad_out, float *gv_acc,
-                              const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err) {
+                              const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err,
+                              const unsigned long long *cond, unsigned long long thr) {
     if ((long long)q.N * q.Ho * q.Wo == 0) return false;
-    if (dtype == 1) return vmma::launch_typed<__half>(offset, mask, grad_out, gv_acc, q, stream, err);
-    if (dtype == 2) return vmma::launch_typed<__nv_bfloat16>(offset, mask, grad_out, gv_acc, q, stream, err);
+    if (dtype == 1) return vmma::launch_typed<__half>(offset, mask, grad_out, gv_acc, q, stream, err, cond, thr);
+    if (dtype == 2) return vmma::launch_typed<__nv_bfloat16>(offset, mask, grad_out, gv_acc, q, stream, err, cond, thr);
     return false;
 }
 

@@ -1,0 +1,666 @@
+// dcnv3_backward_vres.cu -- grad_value of the DCNv3 core backward for 16-bit I/O, group_channels == 16,
+// 3x3 / stride 1 / dilation 1, with the accumulator of a whole band of the value map RESIDENT in tensor memory:
+// no fp32 plane in HBM, no reductions, no zeroing pass, no narrowing pass.
+//
+// What it computes (reference dcnv3_im2col_cuda.cuh:82-147, col2im bilinear), per (image, group):
+//     grad_value[cell, c] = sum over (pixel, point, corner) hitting `cell` of  w_corner * m * grad_out[pixel, c]
+// i.e. the sparse product  D[cells x 16 ch] = A[cells x pixels] . G[pixels x 16 ch]  (as dcnv3_backward_vmma.cu).
+//
+// Why a third form (profiles/README.md, r2): in dcnv3_backward_vmma.cu the band of a strip is 16 cells wide for 8
+// pixels, neighbouring strips' bands overlap and the sum of the overlapping blocks is formed in HBM -- the fp32
+// plane is zeroed (105 MB at cfg2), receives 2.4x its size in vector reductions, is read back and narrowed: 480 MB
+// of DRAM traffic and three passes for a 52 MB result -- and its four warps run inputs -> build -> product -> drain
+// strictly one after the other (45 % of its stall samples are the CTA barrier and the mbarrier waits).  Here
+//   * tensor memory holds the accumulator as 8 x 8-cell BLOCKS: tcgen05.mma with M = 64 writes row i of D to lane
+//     (i / 16) * 32 + i % 16, and the D address may carry a lane offset of 16 (scripts/probes/m64_probe.cu), so one
+//     16-column tile holds two independent blocks and the 512 columns hold 64 blocks = 4096 cells x 16 channels.
+//     A patch of 8 x 8 pixels touches exactly the 2 x 2 blocks around it (the block grid is the patch grid shifted
+//     by the band origin, -4 cells for pad 1), so the blocks of neighbouring patches coincide instead of
+//     overlapping: their sums form in tensor memory.  Blocks are kept for the full width of the map and a ring of
+//     R block rows (R = 5 at W = 80); a block row is final once the patch row below it is done -- it leaves through
+//     tcgen05.ld as plain 32-byte stores of the 16-bit result, once;
+//   * one persistent CTA per SM owns a contiguous run of the flattened (image, group, patch row) list; the block row
+//     at the head of its run also needs the patch row above, which the CTA builds a second time (one patch row in
+//     ~18: 5.8 % extra builds) instead of exchanging partial sums with its neighbour: every cell has ONE writer;
+//   * warp-specialised: 8 builder warps (4 groups x 64 threads, thread <-> pixel, the same 16-bit scatter into a
+//     K-major swizzled coefficient tile as dcnv3_backward_vmma.cu, four 64-cell sub-tiles), one warp that refills a
+//     finished slot with zeros (32 KB bulk copy) and requests the next patch's offsets / masks / grad_out by TMA,
+//     one warp that issues the 16 products of a patch (M 64, N 16, K 16) and the commits, four drain warps
+//     (one per tensor-memory lane quarter).  Five slots (coefficient tile + inputs) rotate between them through
+//     mbarriers; nobody executes a CTA-wide barrier inside the loop.
+// A point whose corner block leaves the 16 x 16 band of its patch (|offset| beyond ~3 px; rare for trained offsets)
+// is only flagged (one 16-bit mask per pixel and group); `far_points` adds those afterwards with 16-bit vector
+// atomics -- one extra rounding of the stored result for the cells they touch.
+#include "dcnv3_common.cuh"
+#include "dcnv3_launch.h"
+#include "dcnv3_tma.cuh"
+#include "dcnv3_strip_io.cuh"
+#include "dcnv3_tc.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <type_traits>
+
+namespace dcnv3 {
+namespace vres {
+
+using namespace strip;
+using namespace tc;
+
+#ifndef VRES_TPP
+#define VRES_TPP 2
+#endif
+constexpr int kTpp = VRES_TPP;                     // builder threads per pixel (2: one owns the even band rows, one the odd)
+constexpr int kSlots = 5;                          // coefficient tiles in rotation
+constexpr int kAhead = 3;                          // a patch's inputs are requested this many patches before its tile
+constexpr int kStages = kSlots + kAhead;           // staged inputs (offsets, masks, grad_out) in rotation
+constexpr int kGroups = 4;                         // builder groups (64 kTpp threads = the pixels of a patch)
+constexpr int kGroupWarps = 2 * kTpp;
+constexpr int kDrainWarp0 = kGroupWarps * kGroups; // four drain warps: tensor-memory lane quarter = warp & 3
+constexpr int kLoadWarp = kDrainWarp0 + 4, kMmaWarp = kLoadWarp + 1;
+constexpr int kThreads = (kMmaWarp + 1) * 32;      // 448 / 704
+constexpr int kBand = 16;                          // band of a patch: 16 x 16 cells = 2 x 2 blocks
+constexpr int kSubBytes = 64 * 128;                // one block's coefficients: 64 cells x 64 pixels x 2 B
+constexpr int kATileBytes = 4 * kSubBytes;         // 32768
+constexpr int kOffRow = 48, kMskRow = 32;          // staged bytes per pixel (36 / 18 used, 16-byte multiples)
+constexpr int kStOff = 0, kStMsk = 64 * kOffRow, kStGout = kStMsk + 64 * kMskRow;
+constexpr int kStBytes = kStGout + 2 * 1024;       // + grad_out as [8-channel half][64 px][16 B]: 7168
+constexpr int kSmemBytes = 1024 + kSlots * kATileBytes + kStages * kStBytes;   // 222208
+constexpr int kMaxRing = 5;
+constexpr int kTmemCols = 512;
+
+// Zeros for the refill of a coefficient tile: a 32 KB bulk copy from this L2-resident page (async proxy, no LSU
+// instructions).  Measured alternatives: two dedicated warps storing zeros (slot turn-around 3000 -> 2000 cycles, but
+// the builders slow down by as much: backward +7 us); st.bulk / UMEMSETS (+31 us in dcnv3_backward_vmma.cu); a shared ->
+// shared bulk copy (illegal instruction without a cluster launch).
+__device__ __align__(128) unsigned char g_zero_tile[kATileBytes];
+__device__ __forceinline__ void bulk_fill(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// a wait that yields its issue slots while it polls (roles that wait for long: drain, refill, builders out of slots)
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, unsigned parity, unsigned ns) {
+    for (;;) {
+        uint32_t ok;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+        __nanosleep(ns);
+    }
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// development only (DCNV3_VRES_DIAG & 1): cycle stamps of CTA 0, per patch -- builder [0..2], loader [3..4], products [5..7]
+__device__ long long g_vres_dbg[256][8];
+
+struct RParams {
+    int diag;
+    int bx_rel, by_rel;      // origin of the block grid relative to the patch grid (cells; -4 for pad 1, sigma 1)
+    int S, PR;               // strips per patch row, patch rows per image
+    int nbxp, ring;          // blocks per block row (even), block rows resident
+    int total_rows;          // N * G * PR
+    int cpg;                 // CTAs per group (0: one flat split of the list)
+};
+
+// The CTA's list of patch rows.  Every role walks the same list, so event numbers (= owned block rows in the order
+// of their first product) agree without communication.
+struct Row {
+    int n, g, i;
+    bool dup;                // the patch row above the CTA's run: built again for the block row below it only
+    bool up_own, down_own;   // does this CTA own block row i / i + 1
+    bool up_fresh;           // block row i gets its first product from this patch row
+    int ev_up, ev_down;
+};
+// The list is GROUP-major, f = (g * N + n) * PR + i: every group's share of the list is cut into CTA runs the same way, so at
+// any moment all groups work on the same few images and the 576-byte offset / 288-byte mask rows of a pixel (all groups
+// side by side) are fetched from DRAM once, not once per group (image-major order: 598 MB of DRAM reads for 264 MB).
+struct Sched {
+    int cur, hi, PR, N, ev, last_down;
+    bool pending_dup;
+    __device__ Sched(int lo, int hi_, int PR_, int N_) : cur(lo), hi(hi_), PR(PR_), N(N_), ev(0), last_down(-1),
+                                                          pending_dup(lo < hi_ && lo % PR_ != 0) {}
+    __device__ bool next(Row &r) {
+        if (pending_dup) {
+            pending_dup = false;
+            const int f = cur - 1, ng = f / PR;
+            r.i = f - ng * PR; r.n = ng % N; r.g = ng / N;
+            r.dup = true; r.up_own = false; r.down_own = true; r.up_fresh = false;
+            r.ev_up = -1; r.ev_down = ev++; last_down = r.ev_down;
+            return true;
+        }
+        if (cur >= hi) return false;
+        const int f = cur++, ng = f / PR;
+        r.i = f - ng * PR; r.n = ng % N; r.g = ng / N;
+        r.dup = false; r.up_own = true; r.up_fresh = r.i == 0;
+        r.down_own = r.i == PR - 1 || cur < hi;
+        r.ev_up = r.up_fresh ? ev++ : last_down;
+        if (r.down_own) { r.ev_down = ev++; last_down = r.ev_down; } else r.ev_down = -1;
+        return true;
+    }
+};
+
+__device__ __forceinline__ size_t far_index(const RParams &pp, const Geom &q, int n, int g, int i, int j) {
+    return ((((size_t)n * q.G + g) * pp.PR + i) * pp.S + j) * 64;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ CUtensorMap tmap_msk,
+         const __grid_constant__ CUtensorMap tmap_gout, T *__restrict__ grad_value, uint16_t *__restrict__ far_mask,
+         unsigned long long *__restrict__ far_count, const Geom q, const RParams pp) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t a_ready[kSlots], a_full[kSlots], a_done[kSlots], in_full[kStages], row_done[kMaxRing], acc_free[kMaxRing];
+    __shared__ uint32_t tmem_base_s;
+
+    // (the warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the product warp's
+    // descriptors in uniform registers -- with `tid >> 5` every tcgen05.mma was wrapped in an elect / R2UR loop,
+    // ~80 cycles per product)
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t slot0 = smem_u32(base), stage0 = slot0 + kSlots * kATileBytes;
+
+    // this CTA's run of the flattened patch-row list
+    // (pp.cpg CTAs per group, every group's rows cut the same way: all groups walk the images in lock step)
+    int lo, hi;
+    if (pp.cpg > 0) {
+        const int g = blockIdx.x % q.G, c = blockIdx.x / q.G, np = q.N * pp.PR;
+        lo = g * np + (int)((long long)np * c / pp.cpg);
+        hi = g * np + (int)((long long)np * (c + 1) / pp.cpg);
+    } else {
+        lo = (int)((long long)pp.total_rows * blockIdx.x / gridDim.x);
+        hi = (int)((long long)pp.total_rows * (blockIdx.x + 1) / gridDim.x);
+    }
+
+    if (tid == 0) {
+        for (int i = 0; i < kSlots; ++i) { mbar_init(&a_ready[i], 1); mbar_init(&a_full[i], 64 * kTpp); mbar_init(&a_done[i], 1); }
+        for (int i = 0; i < kStages; ++i) mbar_init(&in_full[i], 1);
+        for (int i = 0; i < kMaxRing; ++i) { mbar_init(&row_done[i], 1); mbar_init(&acc_free[i], 4); }
+        fence_barrier_init();
+        prefetch_tensormap(&tmap_off);
+        prefetch_tensormap(&tmap_msk);
+        prefetch_tensormap(&tmap_gout);
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    // Programmatic dependent launch: nothing this kernel reads or writes is touched by the channel-sum kernel in front of
+    // it except the far-point counter (zeroed there), so only the counter update at the very end waits for that grid --
+    // the whole pipeline overlaps the channel sums' last wave.  (Every thread executes the wait before it exits.)
+
+    const int C = q.G * q.gc;
+
+    if (warp < kDrainWarp0) {
+        // ================================================================== builders: thread <-> pixel of the patch
+        // (kTpp == 2: two threads per pixel; `par` owns the band rows of that parity, so each of a point's two rows has
+        // exactly one writer and the 16-bit read-modify-writes of a column never race)
+        const int grp = warp / kGroupWarps, wg = warp % kGroupWarps, hw = wg & 1, par = wg >> 1;
+        const int k = hw * 32 + lane;
+        const int px_x = lane & 7, px_y = hw * kPatchH + (lane >> 3);
+        const uint32_t kc = (uint32_t)k >> 3, kl = ((uint32_t)k & 7u) * 2u;
+        Sched sch(lo, hi, pp.PR, q.N);
+        Row row;
+        unsigned p = 0, far_total = 0;
+        while (sch.next(row)) {
+            const int ho = row.i * 8 + px_y;
+            const float bh = axis_base(ho, 3, 1, q.ph, 1, q.sigma) - (float)(row.i * 8 + pp.by_rel);
+            for (int j = 0; j < pp.S; ++j, ++p) {
+                if ((int)(p % kGroups) != grp) continue;
+                const unsigned slot = p % kSlots, stage = p % kStages;
+                const uint32_t a_thr = slot0 + slot * kATileBytes + kl;
+                const uint32_t sa = stage0 + stage * kStBytes;
+                const bool dbg = (pp.diag & 1) && blockIdx.x == 0 && wg == 0 && lane == 0 && p < 256u;
+                if (dbg) g_vres_dbg[p][0] = clock64();
+                mbar_wait_sleep(&in_full[stage], (p / kStages) & 1u, 32);
+                const int wo = j * 8 + px_x;
+                const bool live = wo < q.Wo && ho < q.Ho;
+                unsigned far = 0;
+                uint32_t off[kP] = {}, mw[5] = {};
+                if (live) {
+                    const uint4 o0 = lds128(sa + kStOff + k * kOffRow), o1 = lds128(sa + kStOff + k * kOffRow + 16),
+                                o2 = lds128(sa + kStOff + k * kOffRow + 32);
+                    const uint32_t w[12] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w, o2.x, o2.y, o2.z, o2.w};
+                    const unsigned osh = ((unsigned)(row.g * kP * 4) & 15u) >> 2;     // warp-uniform: 0..3 words
+#pragma unroll
+                    for (int pt = 0; pt < kP; ++pt) off[pt] = osh == 0 ? w[pt] : osh == 1 ? w[pt + 1] : osh == 2 ? w[pt + 2] : w[pt + 3];
+                    const uint4 m0 = lds128(sa + kStMsk + k * kMskRow), m1 = lds128(sa + kStMsk + k * kMskRow + 16);
+                    const uint32_t v[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+                    const unsigned esh = ((unsigned)(row.g * kP * 2) & 15u) >> 1;     // warp-uniform: 0..7 elements
+                    uint32_t u[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) u[t] = (esh & 1u) ? __funnelshift_r(v[t], t + 1 < 8 ? v[t + 1] : 0u, 16) : v[t];
+                    const unsigned ws = esh >> 1;
+#pragma unroll
+                    for (int t = 0; t < 5; ++t)
+                        mw[t] = ws == 0 ? u[t] : ws == 1 ? u[t + 1] : ws == 2 ? u[t + 2] : (t + 3 < 8 ? u[t + 3] : 0u);
+                }
+                mbar_wait_sleep(&a_ready[slot], (p / kSlots) & 1u, 32);      // the tile is zero again
+                if (dbg) g_vres_dbg[p][1] = clock64();
+                if (live) {
+                    const float bw = axis_base(wo, 3, 1, q.pw, 1, q.sigma) - (float)(j * 8 + pp.bx_rel);
+                    if constexpr (kTpp == 2) {
+                        // Two passes.  First every point's two word addresses and coefficients, branch-free (nine
+                        // independent chains the scheduler can interleave); then the read-modify-writes, which must stay
+                        // in order (two points of a pixel may hit the same cell).
+                        const uint32_t kcs = kc << 4;
+                        uint32_t ea[kP], eb[kP];
+                        float wa[kP], wb[kP];
+#pragma unroll
+                        for (int pt = 0; pt < kP; ++pt) {
+                            const float2 d = unpack2(off[pt], T());
+                            const float m = f32_of((uint16_t)(mw[pt >> 1] >> (16 * (pt & 1))), T());
+                            const float ub = bw + ((float)(pt / 3) + d.x) * q.sigma;
+                            const float vb = bh + ((float)(pt % 3) + d.y) * q.sigma;
+                            const float fw = floorf(ub), fh = floorf(vb);
+                            const float lw = ub - fw, lh = vb - fh;
+                            // 0 <= x < limit on the float's bit pattern: negative values and NaN compare as large unsigned
+                            const bool inb = __float_as_uint(ub) < __float_as_uint((float)(kBand - 1)) &&
+                                             __float_as_uint(vb) < __float_as_uint((float)(kBand - 1));
+                            far |= inb ? 0u : 1u << pt;
+                            const uint32_t cx = (uint32_t)(int)fw, ry = (uint32_t)(int)fh, cx1 = cx + 1u;
+                            // this thread's row of the point: the one whose parity it owns
+                            const bool top = (ry & 1u) == (uint32_t)par;
+                            const uint32_t rr = top ? ry : ry + 1u;
+                            // a block row this CTA does not own is never multiplied
+                            const bool act = inb && (rr < 8u ? row.up_own : row.down_own);
+                            const float vm = (top ? 1.f - lh : lh) * m;
+                            // cell (rr, cx) -> sub-tile (rr >> 3, cx >> 3), row (rr & 7) * 8 + (cx & 7), chunk kc ^ (cx & 7):
+                            // (cx & 7) * 0x90 = row * 128 | (cx & 7) * 16, the chunk's xor touches bits 4..6 only
+                            const uint32_t r0 = a_thr + ((rr & 8u) << 11) + ((rr & 7u) << 10);
+                            ea[pt] = act ? r0 + ((((cx & 7u) * 0x90u) ^ kcs) | ((cx & 8u) << 10)) : 0u;
+                            eb[pt] = r0 + ((((cx1 & 7u) * 0x90u) ^ kcs) | ((cx1 & 8u) << 10));
+                            wa[pt] = vm * (1.f - lw);
+                            wb[pt] = vm * lw;
+                        }
+#pragma unroll
+                        for (int pt = 0; pt < kP; ++pt)
+                            if (ea[pt]) {
+                                const float a0 = f32_of((uint16_t)lds16(ea[pt]), T()), a1 = f32_of((uint16_t)lds16(eb[pt]), T());
+                                sts16(ea[pt], bits16(a0 + wa[pt], T()));
+                                sts16(eb[pt], bits16(a1 + wb[pt], T()));
+                            }
+                    } else {
+#pragma unroll
+                    for (int pt = 0; pt < kP; ++pt) {
+                        const float2 d = unpack2(off[pt], T());
+                        const float m = f32_of((uint16_t)(mw[pt >> 1] >> (16 * (pt & 1))), T());
+                        const float ub = bw + ((float)(pt / 3) + d.x) * q.sigma;
+                        const float vb = bh + ((float)(pt % 3) + d.y) * q.sigma;
+                        const float fw = floorf(ub), fh = floorf(vb);
+                        const float lw = ub - fw, lh = vb - fh;
+                        if (__float_as_uint(ub) < __float_as_uint((float)(kBand - 1)) &&
+                            __float_as_uint(vb) < __float_as_uint((float)(kBand - 1))) {
+                            const uint32_t cx = (uint32_t)(int)fw, ry = (uint32_t)(int)fh, cx1 = cx + 1u;
+                            const uint32_t c0 = (cx >> 3) * kSubBytes + (cx & 7u) * 128u + ((kc ^ (cx & 7u)) << 4);
+                            const uint32_t c1 = (cx1 >> 3) * kSubBytes + (cx1 & 7u) * 128u + ((kc ^ (cx1 & 7u)) << 4);
+                            const float hwt = 1.f - lw;
+                            if ((!row.up_own && ry < 7u) || (!row.down_own && ry >= 8u)) continue;
+                            const float hm = (1.f - lh) * m, lm = lh * m;
+                            const uint32_t ry1 = ry + 1u;
+                            const uint32_t r0 = a_thr + (ry >> 3) * (2 * kSubBytes) + (ry & 7u) * 1024u;
+                            const uint32_t r1 = a_thr + (ry1 >> 3) * (2 * kSubBytes) + (ry1 & 7u) * 1024u;
+                            const float a0 = f32_of((uint16_t)lds16(r0 + c0), T()), a1 = f32_of((uint16_t)lds16(r0 + c1), T());
+                            const float a2 = f32_of((uint16_t)lds16(r1 + c0), T()), a3 = f32_of((uint16_t)lds16(r1 + c1), T());
+                            sts16(r0 + c0, bits16(a0 + hm * hwt, T()));
+                            sts16(r0 + c1, bits16(a1 + hm * lw, T()));
+                            sts16(r1 + c0, bits16(a2 + lm * hwt, T()));
+                            sts16(r1 + c1, bits16(a3 + lm * lw, T()));
+                        } else {
+                            far |= 1u << pt;
+                        }
+                    }
+                    }
+                }
+                if (dbg) g_vres_dbg[p][2] = clock64();
+                fence_proxy_async();
+                mbar_arrive(&a_full[slot]);
+                if (!row.dup && par == 0) {
+                    far_mask[far_index(pp, q, row.n, row.g, row.i, j) + k] = (uint16_t)far;
+                    far_total += __popc(far);
+                }
+            }
+        }
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        far_total = __reduce_add_sync(0xffffffffu, far_total);
+        if (lane == 0 && far_total) atomicAdd(far_count, (unsigned long long)far_total);
+    } else if (warp < kLoadWarp) {
+        // ================================================================== drain: one tensor-memory lane quarter each
+        const int wq = warp & 3;
+        Sched sch(lo, hi, pp.PR, q.N);
+        Row row;
+        auto drain = [&](int ev, int r, int n, int g) {
+            const int sr = ev % pp.ring;
+            mbar_wait_sleep(&row_done[sr], (unsigned)(ev / pp.ring) & 1u, 256);
+            tc_fence_after();
+            const int y = r * 8 + pp.by_rel + 2 * wq + ((lane >> 3) & 1);
+            const bool oky = (unsigned)y < (unsigned)q.H;
+            T *rowp = grad_value + ((size_t)n * q.H + (oky ? y : 0)) * q.W * C + g * kCh;
+            const int half = lane >> 4, cx = lane & 7;
+            const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(sr * (pp.nbxp >> 1) * 16);
+            for (int t = 0; t < (pp.nbxp >> 1); ++t) {
+                float v[16];
+                VMMA_TMEM_LD_16(taddr + (uint32_t)(t * 16), v);
+                tmem_ld_wait();
+                const int x = (2 * t + half) * 8 + pp.bx_rel + cx;
+                if (oky && (unsigned)x < (unsigned)q.W) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(rowp + (size_t)x * C);
+                    dst[0] = pack<T>(v);
+                    dst[1] = pack<T>(v + 8);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_free[sr]);
+        };
+        while (sch.next(row)) {
+            if (row.up_own) drain(row.ev_up, row.i, row.n, row.g);
+            if (row.i == pp.PR - 1 && row.down_own) drain(row.ev_down, pp.PR, row.n, row.g);
+        }
+    } else if (warp == kLoadWarp) {
+        // ================================================================== refill + inputs of the next patches
+        if (lane == 0) {
+            Sched sch(lo, hi, pp.PR, q.N), sch_in(lo, hi, pp.PR, q.N);
+            Row row, rin;
+            int jin = 0;
+            unsigned pin = 0;
+            bool more_in = sch_in.next(rin);
+            auto request_inputs = [&]() {   // offsets / masks / grad_out of patch `pin`, kAhead patches before its tile
+                if (!more_in) return;
+                unsigned char *st = base + kSlots * kATileBytes + (pin % kStages) * kStBytes;
+                uint64_t *bar = &in_full[pin % kStages];
+                mbar_expect_tx(bar, kStBytes);
+                // a box starts on a 16-byte boundary of the row: the group's run begins 0..3 words / 0..7 elements in
+                tma_load_4d(st + kStOff, &tmap_off, bar, (rin.g * kP * 4 & ~15) >> 1, jin * 8, rin.i * 8, rin.n);
+                tma_load_4d(st + kStMsk, &tmap_msk, bar, (rin.g * kP * 2 & ~15) >> 1, jin * 8, rin.i * 8, rin.n);
+                tma_load_4d(st + kStGout, &tmap_gout, bar, rin.g * kCh, jin * 8, rin.i * 8, rin.n);
+                tma_load_4d(st + kStGout + 1024, &tmap_gout, bar, rin.g * kCh + 8, jin * 8, rin.i * 8, rin.n);
+                ++pin;
+                if (++jin == pp.S) { jin = 0; more_in = sch_in.next(rin); }
+            };
+            for (int t = 0; t < kAhead; ++t) request_inputs();
+            unsigned p = 0;
+            while (sch.next(row)) {
+                for (int j = 0; j < pp.S; ++j, ++p) {
+                    const unsigned slot = p % kSlots;
+                    const bool dbg = (pp.diag & 1) && blockIdx.x == 0 && p < 256u;
+                    if (dbg) g_vres_dbg[p][3] = clock64();
+                    // patch p - kSlots is through its products: its tile can be zeroed for patch p, and its input stage
+                    // (p - kSlots) % kStages = (p + kAhead) % kStages takes the inputs of patch p + kAhead
+                    if (p >= (unsigned)kSlots) mbar_wait_sleep(&a_done[slot], (p / kSlots - 1u) & 1u, 32);
+                    if (dbg) g_vres_dbg[p][4] = clock64();
+                    mbar_expect_tx(&a_ready[slot], kATileBytes);
+                    bulk_fill(slot0 + slot * kATileBytes, g_zero_tile, kATileBytes, &a_ready[slot]);
+                    request_inputs();
+                }
+            }
+        }
+    } else {
+        // ================================================================== products (the whole warp walks the list;
+        // one elected lane issues)
+        {
+            const uint32_t idesc = umma_idesc(std::is_same<T, __nv_bfloat16>::value ? 1 : 0, 64, kCh);
+            // descriptors of slot 0 / block 0 / K step 0; the others differ in the 14-bit address field only
+            const uint64_t adesc0 = umma_desc_k_sw128(slot0), bdesc0 = umma_desc_mn_plain(stage0 + kStGout, 128, 1024);
+            Sched sch(lo, hi, pp.PR, q.N);
+            Row row;
+            unsigned p = 0;
+            while (sch.next(row)) {
+                // a block row that starts here takes over a ring place: its previous tenant must have been drained
+                if (row.up_own && row.up_fresh && row.ev_up >= pp.ring)
+                    mbar_wait(&acc_free[row.ev_up % pp.ring], (unsigned)(row.ev_up / pp.ring - 1) & 1u);
+                if (row.down_own && row.ev_down >= pp.ring)
+                    mbar_wait(&acc_free[row.ev_down % pp.ring], (unsigned)(row.ev_down / pp.ring - 1) & 1u);
+                tc_fence_after();
+                const int base_up = row.up_own ? (row.ev_up % pp.ring) * pp.nbxp : 0;
+                const int base_down = row.down_own ? (row.ev_down % pp.ring) * pp.nbxp : 0;
+                for (int j = 0; j < pp.S; ++j, ++p) {
+                    const unsigned slot = p % kSlots;
+                    const uint64_t ad = adesc0 + (uint64_t)((slot * kATileBytes) >> 4), bd = bdesc0 + (uint64_t)(((p % kStages) * kStBytes) >> 4);
+                    const bool dbg = (pp.diag & 1) && blockIdx.x == 0 && p < 256u;
+                    if (dbg && lane == 0) g_vres_dbg[p][5] = clock64();
+                    mbar_wait(&a_full[slot], (p / kSlots) & 1u);
+                    if (dbg && lane == 0) g_vres_dbg[p][6] = clock64();
+                    tc_fence_after();
+                    // K-step-major: consecutive products go to DIFFERENT accumulator blocks.  Products into the same
+                    // block form a dependent chain that advances one product per pipeline latency (~80 cycles measured
+                    // for these N = 16 shapes); the four blocks' chains interleave.
+                    uint32_t dd[4];
+                    bool first[4], own[4];
+#pragma unroll
+                    for (int sub = 0; sub < 4; ++sub) {
+                        const bool down = sub >> 1;
+                        own[sub] = down ? row.down_own : row.up_own;
+                        const int blk = (down ? base_down : base_up) + j + (sub & 1);
+                        dd[sub] = tmem_base + ((uint32_t)(blk & 1) << 20) + ((uint32_t)(blk >> 1) << 4);
+                        first[sub] = (down || row.up_fresh) && ((sub & 1) || j == 0);
+                    }
+                    if (elect_one()) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)   // K step = 16 pixels: 32 B of an A row, 256 B of the pixel-major B
+#pragma unroll
+                            for (int sub = 0; sub < 4; ++sub)
+                                if (own[sub])
+                                    tc_mma(dd[sub], ad + (uint64_t)((sub * kSubBytes + ks * 32) >> 4), bd + (uint64_t)((ks * 256) >> 4), idesc,
+                                           (uint32_t)(ks > 0 || !first[sub]));
+                        tc_commit(&a_done[slot]);
+                        if (j == pp.S - 1) {
+                            if (row.up_own) tc_commit(&row_done[row.ev_up % pp.ring]);
+                            if (row.i == pp.PR - 1 && row.down_own) tc_commit(&row_done[row.ev_down % pp.ring]);
+                        }
+                    }
+                    __syncwarp();
+                    if (dbg && lane == 0) g_vres_dbg[p][7] = clock64();
+                }
+            }
+        }
+    }
+
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();   // the drain warps have seen the last commit: every product and refill has completed
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Points that left the band of their patch: thread <-> (pixel, group); almost every thread reads a zero mask and exits.
+// 128-bit vector reduction of eight 16-bit values (REDG.E.ADD.BF16x8 / F16x8): fire and forget
+__device__ __forceinline__ void red_add8(__nv_bfloat16 *p, uint4 v) {
+    asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void red_add8(__half *p, uint4 v) {
+    asm volatile("red.global.add.noftz.v4.f16x2 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// One far point: four coefficient x grad_out rows added to the stored 16-bit result with vector atomics.
+template <typename T>
+__device__ __noinline__ void far_pixel(unsigned far, size_t idx, const T *__restrict__ offset, const T *__restrict__ mask,
+                                       const T *__restrict__ grad_out, T *__restrict__ grad_value, const Geom &q, const RParams &pp) {
+    const int k = (int)(idx & 63);
+    size_t t = idx >> 6;
+    const int j = (int)(t % pp.S); t /= pp.S;
+    const int i = (int)(t % pp.PR); t /= pp.PR;
+    const int g = (int)(t % q.G), n = (int)(t / q.G);
+    const int wo = j * 8 + (k & 7), ho = i * 8 + (k >> 3);
+    if (wo >= q.Wo || ho >= q.Ho) return;
+    const int C = q.G * q.gc;
+    const size_t pix = ((size_t)n * q.Ho + ho) * q.Wo + wo;
+    const T *op = offset + (pix * q.G + g) * (kP * 2), *mp = mask + (pix * q.G + g) * kP;
+    float gch[kCh];
+    {
+        const uint4 *gp = reinterpret_cast<const uint4 *>(grad_out + pix * C + g * kCh);
+        unpack<T>(gp[0], gch);
+        unpack<T>(gp[1], gch + 8);
+    }
+    const float bw = axis_base(wo, 3, 1, q.pw, 1, q.sigma), bh = axis_base(ho, 3, 1, q.ph, 1, q.sigma);
+    T *gv_img = grad_value + (size_t)n * q.H * q.W * C + g * kCh;
+    for (; far; far &= far - 1) {
+        const int pt = __ffs(far) - 1;
+        const float m = to_f32(mp[pt]);
+        const float lw_abs = bw + ((float)(pt / 3) + to_f32(op[2 * pt])) * q.sigma;
+        const float lh_abs = bh + ((float)(pt % 3) + to_f32(op[2 * pt + 1])) * q.sigma;
+        if (!(lh_abs > -1.f && lw_abs > -1.f && lh_abs < (float)q.H && lw_abs < (float)q.W)) continue;   // (:262-263)
+        const float fw = floorf(lw_abs), fh = floorf(lh_abs);
+        const float lw = lw_abs - fw, lh = lh_abs - fh;
+        const float cf[4] = {(1.f - lh) * m * (1.f - lw), (1.f - lh) * m * lw, lh * m * (1.f - lw), lh * m * lw};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int hh = (int)fh + (c >> 1), ww = (int)fw + (c & 1);
+            if ((unsigned)hh < (unsigned)q.H && (unsigned)ww < (unsigned)q.W && cf[c] != 0.f) {
+                T *dst = gv_img + ((size_t)hh * q.W + ww) * C;
+                float pr[kCh];
+#pragma unroll
+                for (int e = 0; e < kCh; ++e) pr[e] = cf[c] * gch[e];
+                red_add8(dst, pack<T>(pr));
+                red_add8(dst + 8, pack<T>(pr + 8));
+            }
+        }
+    }
+}
+
+// After the product kernel: thread <-> eight (pixel, group) masks; almost every thread reads 16 zero bytes and exits.
+// If the call produced more far points than `thr`, nothing is added here: the caller's fall-back (the plane form,
+// launched behind this kernel on the same condition) recomputes grad_value, and this kernel zeroes its fp32 plane.
+template <typename T>
+__global__ void __launch_bounds__(256)
+far_points(const uint16_t *__restrict__ far_mask, const unsigned long long *__restrict__ far_count, unsigned long long thr,
+           const T *__restrict__ offset, const T *__restrict__ mask, const T *__restrict__ grad_out, T *__restrict__ grad_value,
+           float4 *__restrict__ plane, size_t plane_vec, const Geom q, const RParams pp, size_t total) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const size_t tid = (size_t)blockIdx.x * 256 + threadIdx.x;
+    // (volatile asm loads: with plain loads through `const __restrict__` pointers the compiler hoisted the counter's
+    // LDG.CONSTANT ABOVE the grid-dependency wait -- the kernel then saw the count before the product kernel had
+    // finished adding to it, and took the sparse path while the caller's fall-back kernels saw the final count)
+    unsigned long long count;
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(count) : "l"(far_count) : "memory");
+    if (count > thr) {
+        for (size_t i = tid; i < plane_vec; i += (size_t)gridDim.x * 256) plane[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    const size_t idx = tid * 8;
+    if (idx >= total) return;
+    uint4 w;                                                            // (total is a multiple of 64)
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(far_mask + idx) : "memory");
+    if (!(w.x | w.y | w.z | w.w) || (pp.diag & 4)) return;
+    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll 1
+    for (int e = 0; e < 8; ++e) {
+        const unsigned far = (ww[e >> 1] >> (16 * (e & 1))) & 0xffffu;
+        if (far) far_pixel<T>(far, idx + e, offset, mask, grad_out, grad_value, q, pp);
+    }
+}
+
+static bool plan(const Geom &q, RParams *pp) {
+    if (q.gc != kCh || q.kh != 3 || q.kw != 3 || q.sh != 1 || q.sw != 1 || q.dh != 1 || q.dw != 1 || q.G % 8) return false;
+    if (!(q.sigma >= 0.5f && q.sigma <= 1.25f)) return false;   // band = taps +- 3 px
+    if ((long long)q.N * q.Ho * q.Wo == 0) return false;
+    // nominal taps of a pixel x along an axis: x + a + i*sigma, i = 0..2, a = (1 - pad) - sigma; band centred on them
+    const float a_w = (float)(1 - q.pw) - q.sigma, a_h = (float)(1 - q.ph) - q.sigma;
+    pp->bx_rel = (int)std::floor(a_w + q.sigma + 0.5f * 7 + 0.5f - 0.5f * kBand);
+    pp->by_rel = (int)std::floor(a_h + q.sigma + 0.5f * 7 + 0.5f - 0.5f * kBand);
+    pp->S = (q.Wo + 7) / 8;
+    pp->PR = (q.Ho + 7) / 8;
+    // every cell of the map must lie in a block somebody drains: blocks 0..S x 0..PR from the grid origin
+    if (pp->bx_rel > 0 || pp->by_rel > 0 || (pp->S + 1) * 8 + pp->bx_rel < q.W || (pp->PR + 1) * 8 + pp->by_rel < q.H) return false;
+    pp->nbxp = (pp->S + 2) & ~1;                        // S + 1 blocks per block row, padded to a whole tile
+    pp->ring = std::min(kMaxRing, 64 / pp->nbxp);
+    if (pp->ring < 3) return false;                     // two rows in work + one leaving
+    const long long rows = (long long)q.N * q.G * pp->PR;
+    if (rows >= (1LL << 30)) return false;
+    pp->total_rows = (int)rows;
+    return true;
+}
+
+template <typename T>
+static bool launch_typed(const void *offset, const void *mask, const void *grad_out, void *grad_value, void *scratch,
+                         size_t scratch_bytes, unsigned long long *counter, unsigned long long *thr_out, const Geom &q,
+                         cudaStream_t stream, cudaError_t *err) {
+    RParams pp;
+    if (!plan(q, &pp)) return false;
+    static const int diag = [] { const char *e = std::getenv("DCNV3_VRES_DIAG"); return e ? atoi(e) : 0; }();
+    pp.diag = diag;
+    CUtensorMap to, tm, tg;
+    const int dtype = std::is_same<T, __half>::value ? 1 : 2;
+    if (!make_run_tensor_map(&to, offset, dtype, q.N, q.Ho, q.Wo, q.G * kP * 2, kOffRow / 2)) return false;
+    if (!make_run_tensor_map(&tm, mask, dtype, q.N, q.Ho, q.Wo, q.G * kP, kMskRow / 2)) return false;
+    if (!make_run_tensor_map(&tg, grad_out, dtype, q.N, q.Ho, q.Wo, q.G * q.gc, 8)) return false;
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    int ctas = std::min(pp.total_rows, num_sms);
+    pp.cpg = 0;
+    if (q.G <= num_sms && q.N * pp.PR >= num_sms / q.G) {
+        pp.cpg = num_sms / q.G;
+        ctas = pp.cpg * q.G;
+    }
+    if (const char *e = std::getenv("DCNV3_VRES_FLAT")) if (e[0] == '1') { pp.cpg = 0; ctas = std::min(pp.total_rows, num_sms); }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(bwd_vres<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        attr_set = true;
+    }
+    uint16_t *far = static_cast<uint16_t *>(scratch);
+    const size_t total = (size_t)pp.total_rows * pp.S * 64;
+    if (total * sizeof(uint16_t) > scratch_bytes) return false;
+    // beyond 1 / 32 of all points on the far path the caller's fall-back takes over
+    const unsigned long long thr = (unsigned long long)q.N * q.Ho * q.Wo * q.G * kP / 32;
+    *thr_out = thr;
+    *err = pdl_launch(true, bwd_vres<T>, dim3(ctas), dim3(kThreads), kSmemBytes, stream, to, tm, tg,
+                      static_cast<T *>(grad_value), far, counter, q, pp);
+    if (*err == cudaSuccess) *err = cudaGetLastError();
+    if (*err != cudaSuccess) return true;
+    const size_t threads = total / 8;
+    *err = pdl_launch(true, far_points<T>, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, stream,
+                      static_cast<const uint16_t *>(far), static_cast<const unsigned long long *>(counter), thr,
+                      static_cast<const T *>(offset), static_cast<const T *>(mask), static_cast<const T *>(grad_out),
+                      static_cast<T *>(grad_value), static_cast<float4 *>(scratch), scratch_bytes / 16, q, pp, total);
+    if (*err == cudaSuccess) *err = cudaGetLastError();
+    return true;
+}
+
+}  // namespace vres
+
+bool backward_vres_eligible(const void *offset, const void *mask, const void *grad_out, const void *grad_value, const Geom &q) {
+    vres::RParams pp;
+    if (((uintptr_t)grad_out | (uintptr_t)grad_value | (uintptr_t)offset | (uintptr_t)mask) % 16) return false;
+    return vres::plan(q, &pp);
+}
+
+size_t backward_vres_scratch_bytes(const Geom &q) {
+    vres::RParams pp;
+    if (!vres::plan(q, &pp)) return 0;
+    return (size_t)pp.total_rows * pp.S * 64 * sizeof(uint16_t);
+}
+
+// grad_value written directly (16-bit); `scratch` holds the far-point masks (backward_vres_scratch_bytes)
+bool try_launch_backward_vres(const void *offset, const void *mask, const void *grad_out, void *grad_value, void *scratch,
+                              size_t scratch_bytes, unsigned long long *counter, unsigned long long *thr,
+                              const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err) {
+    if (!backward_vres_eligible(offset, mask, grad_out, grad_value, q) || ((uintptr_t)scratch | scratch_bytes) % 16) return false;
+    if (dtype == 1) return vres::launch_typed<__half>(offset, mask, grad_out, grad_value, scratch, scratch_bytes, counter, thr, q, stream, err);
+    if (dtype == 2) return vres::launch_typed<__nv_bfloat16>(offset, mask, grad_out, grad_value, scratch, scratch_bytes, counter, thr, q, stream, err);
+    return false;
+}
+
+}  // namespace dcnv3
+
+// development only: the cycle stamps of the last launch (scripts/vres_timeline.py)
+extern "C" __attribute__((visibility("default"))) int dcnv3_vres_debug_read(void *dst) {
+    return (int)cudaMemcpyFromSymbol(dst, dcnv3::vres::g_vres_dbg, sizeof(dcnv3::vres::g_vres_dbg));
+}

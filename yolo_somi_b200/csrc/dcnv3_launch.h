@@ -65,7 +65,19 @@ bool try_launch_backward_vstrip(const void *offset, const void *mask, const void
                                 const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err);
 // grad_value as a tcgen05 product with TMEM accumulators (dcnv3_backward_vmma.cu)
 bool backward_vmma_eligible(const void *offset, const void *mask, const void *grad_out, const float *gv_acc, const Geom &q);
+// (`cond` / `thr`: if given, the kernel runs only when *cond > thr -- read on the device after the preceding kernel)
 bool try_launch_backward_vmma(const void *offset, const void *mask, const void *grad_out, float *gv_acc,
+                              const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err,
+                              const unsigned long long *cond = nullptr, unsigned long long thr = 0);
+
+// grad_value with the accumulator resident in tensor memory, written once in the I/O dtype (dcnv3_backward_vres.cu);
+// `scratch`: backward_vres_scratch_bytes(q) bytes (one 16-bit far-point mask per pixel and group)
+bool backward_vres_eligible(const void *offset, const void *mask, const void *grad_out, const void *grad_value, const Geom &q);
+size_t backward_vres_scratch_bytes(const Geom &q);
+// `counter`: 64-bit far-point count, zeroed by the caller's previous kernel; `*thr`: the count above which the result is
+// NOT final (too many far points for the 16-bit atomics: the caller then runs the plane form, conditionally, on top)
+bool try_launch_backward_vres(const void *offset, const void *mask, const void *grad_out, void *grad_value, void *scratch,
+                              size_t scratch_bytes, unsigned long long *counter, unsigned long long *thr,
                               const Geom &q, int dtype, cudaStream_t stream, cudaError_t *err);
 
 // grad_value with the coefficient columns built dense in registers and a circular TMEM band (dcnv3_backward_vband.cu)

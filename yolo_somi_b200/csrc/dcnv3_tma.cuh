@@ -51,6 +51,24 @@ inline bool make_nhwc_tensor_map(CUtensorMap *map, const void *base, int dtype /
               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// 4-D tensor map over a [N, Ho, Wo, row_elems] tensor of 16-bit elements, box (box_elems, 8, 8, 1).  The box
+// may start at any element (a group's run) and run past the row / the map: the hardware zero-fills.
+inline bool make_run_tensor_map(CUtensorMap *map, const void *base, int dtype, int N, int Ho, int Wo, int row_elems,
+                                int box_elems) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t es = 2;
+    const CUtensorMapDataType dt = dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const cuuint64_t dims[4] = {(cuuint64_t)row_elems, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)row_elems * es, (cuuint64_t)Wo * row_elems * es,
+                                   (cuuint64_t)Ho * Wo * row_elems * es};
+    const cuuint32_t box[4] = {(cuuint32_t)box_elems, 8u, 8u, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    return fn(map, dt, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // ---------------------------------------------------------------------------------- device side
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
