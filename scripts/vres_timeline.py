@@ -20,15 +20,16 @@ buf = np.zeros((256, 8), dtype=np.int64)
 rc = lib.dcnv3_vres_debug_read(buf.ctypes.data_as(ctypes.c_void_p))
 assert rc == 0, rc
 n = int((buf[:, 7] > 0).sum())
-t0 = buf[0, 3]
-print("patch | builder: start wait_slot build | loader: start wait_done | products: start wait_full issue   (cycles from the first stamp)")
-for p in range(min(n, 48)):
+t0 = buf[0, 0]
+print("patch | builder: start +wait_inputs +wait_tile +build | loader: refill issued | products: start +wait_full +issue   (cycles from the first stamp)")
+for p in range(min(n, 40)):
     r = buf[p] - t0
-    print(f"{p:4d} | b {r[0]:7d} +{r[1]-r[0]:6d} +{r[2]-r[1]:6d} | l {r[3]:7d} +{r[4]-r[3]:6d} | m {r[5]:7d} +{r[6]-r[5]:6d} +{r[7]-r[6]:5d}")
+    print(f"{p:4d} | b {r[0]:7d} +{r[3]-r[0]:6d} +{r[1]-r[3]:6d} +{r[2]-r[1]:6d} | l {r[4]:7d} | m {r[5]:7d} +{r[6]-r[5]:6d} +{r[7]-r[6]:5d}")
 r = buf[20:n]
 print("means over patches 20..%d:" % n)
-print("  builder wait_slot %.0f  build %.0f" % ((r[:, 1]-r[:, 0]).mean(), (r[:, 2]-r[:, 1]).mean()))
-print("  loader wait_done %.0f" % (r[:, 4]-r[:, 3]).mean())
+print("  builder wait_inputs %.0f  wait_tile %.0f  build %.0f" % ((r[:, 3]-r[:, 0]).mean(), (r[:, 1]-r[:, 3]).mean(), (r[:, 2]-r[:, 1]).mean()))
 print("  products wait_full %.0f  issue %.0f" % ((r[:, 6]-r[:, 5]).mean(), (r[:, 7]-r[:, 6]).mean()))
 print("  patch-to-patch (product issue) %.0f cycles" % np.diff(buf[20:n, 7]).mean())
-print("  slot turn-around: a_full(p) -> slot_ready seen by builder of p+5: %.0f" % (buf[25:n, 1] - buf[20:n-5, 6]).mean())
+print("  builder group: end of build(p) -> start of patch p+4: %.0f" % (buf[24:n, 0] - buf[20:n-4, 2]).mean())
+print("  refill issued(p) -> tile ready seen by builder: %.0f" % (buf[20:n, 1] - buf[20:n, 4]).mean())
+print("  products done issuing(p) -> refill issued for p+6: %.0f" % (buf[26:n, 4] - buf[20:n-6, 7]).mean())

@@ -59,7 +59,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     OBJ_DIR.mkdir(exist_ok=True)
 
     sources = SOURCES + (EXPERIMENTS if WITH_EXPERIMENTS else [])
-    flags = NVCC_FLAGS + (["-DDCNV3_EXPERIMENTS"] if WITH_EXPERIMENTS else [])
+    # (development: DCNV3_NVCC_EXTRA="-DVRES_TPP=2 -DVRES_GROUPS=4" builds a kernel variant)
+    flags = NVCC_FLAGS + (["-DDCNV3_EXPERIMENTS"] if WITH_EXPERIMENTS else []) + os.environ.get("DCNV3_NVCC_EXTRA", "").split()
 
     def compile_one(src: str) -> Path:
         obj = OBJ_DIR / (Path(src).stem + ".o")

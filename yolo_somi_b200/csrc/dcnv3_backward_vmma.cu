@@ -93,6 +93,12 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
+}
+
 struct VParams {
     // run only if *cond > thr (the far-point count of dcnv3_backward_vres.cu; nullptr = always)
     const unsigned long long *cond;
@@ -159,7 +165,10 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
         asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(count) : "l"(pp.cond) : "memory");
         if (count <= pp.thr) return;
     }
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // (the warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the descriptors of the
+    // elected issuing lane in uniform registers; with `tid == 0` every tcgen05.mma sat in an elect / R2UR loop,
+    // ~80 cycles per product -- measured in dcnv3_backward_vres.cu)
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     // warps 0-1 (par == 0): builders, thread <-> pixel of the 8 x 8 patch; warps 2-3 join for the drain
     // (a tcgen05.ld reaches the 32 TMEM lanes of the warp's quarter, so 128 cells need four warps)
     const int strip_id = 0, hw = warp & 1, par = warp >> 1;
@@ -361,7 +370,7 @@ bwd_vmma(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
             fence_proxy_async();
             tc_fence_before();
             __syncthreads();
-            if (tid == 0) {
+            if (warp == 0 && elect_one_sync()) {
                 tc_fence_after();
 #pragma unroll
                 for (int st = 0; st < kStrips; ++st)

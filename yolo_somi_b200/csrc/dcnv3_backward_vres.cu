@@ -19,18 +19,37 @@
 //     overlapping: their sums form in tensor memory.  Blocks are kept for the full width of the map and a ring of
 //     R block rows (R = 5 at W = 80); a block row is final once the patch row below it is done -- it leaves through
 //     tcgen05.ld as plain 32-byte stores of the 16-bit result, once;
-//   * one persistent CTA per SM owns a contiguous run of the flattened (image, group, patch row) list; the block row
-//     at the head of its run also needs the patch row above, which the CTA builds a second time (one patch row in
-//     ~18: 5.8 % extra builds) instead of exchanging partial sums with its neighbour: every cell has ONE writer;
-//   * warp-specialised: 8 builder warps (4 groups x 64 threads, thread <-> pixel, the same 16-bit scatter into a
-//     K-major swizzled coefficient tile as dcnv3_backward_vmma.cu, four 64-cell sub-tiles), one warp that refills a
-//     finished slot with zeros (32 KB bulk copy) and requests the next patch's offsets / masks / grad_out by TMA,
-//     one warp that issues the 16 products of a patch (M 64, N 16, K 16) and the commits, four drain warps
-//     (one per tensor-memory lane quarter).  Five slots (coefficient tile + inputs) rotate between them through
-//     mbarriers; nobody executes a CTA-wide barrier inside the loop.
+//   * one persistent CTA per SM owns a contiguous run of the (group, image, patch row) list -- group-major, with the
+//     same cuts for every group, so all groups walk the images in lock step and a pixel's offset / mask rows (all
+//     groups side by side) come from DRAM once: 148 MB instead of 586 MB of DRAM reads; the block row at the head of a
+//     run also needs the patch row above, which the CTA builds a second time (one patch row in ~18: 5.8 % extra
+//     builds) instead of exchanging partial sums with its neighbour: every cell has ONE writer;
+//   * warp-specialised, nobody executes a CTA-wide barrier inside the loop:
+//       - 16 builder warps = 4 groups x 128 threads: two threads per pixel of the patch, one owns the even band rows,
+//         one the odd (so each of a point's two rows has one writer and the 16-bit read-modify-writes of the pixel's
+//         column of the K-major swizzled coefficient tile never race); two passes per patch -- all nine points'
+//         addresses / coefficients first (independent chains), then the read-modify-writes in order;
+//       - one warp requests the inputs by TMA (offsets / masks into four buffers, free again as soon as a group has
+//         them in registers; grad_out = the B operand next to its coefficient tile) and refills a tile with zeros
+//         (32 KB bulk copy) once its products are done;
+//       - one warp issues the 16 products of a patch (M 64, N 16, K 16; the whole warp walks the schedule so that the
+//         descriptors stay in uniform registers, one elected lane issues) and the commits;
+//       - four drain warps, one per tensor-memory lane quarter.
+//     Six slots (coefficient tile + grad_out) rotate between them through mbarriers.
 // A point whose corner block leaves the 16 x 16 band of its patch (|offset| beyond ~3 px; rare for trained offsets)
 // is only flagged (one 16-bit mask per pixel and group); `far_points` adds those afterwards with 16-bit vector
-// atomics -- one extra rounding of the stored result for the cells they touch.
+// reductions (REDG.ADD.BF16x8) -- one extra rounding of the stored result for the cells they touch, and grad_value is
+// reproducible only up to the order of those additions.  If more than 1 / 32 of all points are far, the caller's
+// fall-back (the plane form) recomputes grad_value; both decide on the device from a counter, no host round trip.
+//
+// Measured on cfg2 bf16 (profiles/README.md, r2): 152 us (ncu) against 149 + 23 (narrow) + ~8 (plane zeroing inside
+// the channel-sum kernel) for the plane form; backward pass 264.4 -> 259.8 us, its DRAM traffic 816 -> 440 MB.
+// What bounds it: the builders (per patch ~3000 cycles of build in a group, four groups in flight; ~850 shared-memory
+// wavefronts per patch = 63 % of the LSU's cycles, the 16-bit scatter conflicting ~3.4-fold for N(0, 1) offsets in
+// any operand layout).  Variants measured on the way (same file, -DVRES_TPP / -DVRES_GROUPS): one thread per pixel
+// with four / five / six groups 273 / 264 / 271 us; five slots 261.7 us; refill by two dedicated warps (+7 us), by the
+// builders themselves (+19 us), by st.bulk (no change); products issued by `lane == 0` instead of an elected lane of
+// a warp-uniform loop: 1300 instead of 550 cycles per patch (every tcgen05.mma sat in an elect / R2UR loop).
 #include "dcnv3_common.cuh"
 #include "dcnv3_launch.h"
 #include "dcnv3_tma.cuh"
@@ -51,22 +70,30 @@ using namespace tc;
 #ifndef VRES_TPP
 #define VRES_TPP 2
 #endif
+#ifndef VRES_GROUPS
+#define VRES_GROUPS (VRES_TPP == 1 ? 5 : 4)
+#endif
 constexpr int kTpp = VRES_TPP;                     // builder threads per pixel (2: one owns the even band rows, one the odd)
-constexpr int kSlots = 5;                          // coefficient tiles in rotation
-constexpr int kAhead = 3;                          // a patch's inputs are requested this many patches before its tile
-constexpr int kStages = kSlots + kAhead;           // staged inputs (offsets, masks, grad_out) in rotation
-constexpr int kGroups = 4;                         // builder groups (64 kTpp threads = the pixels of a patch)
+constexpr int kSlots = 6;                          // coefficient tiles (+ the patch's grad_out, the B operand) in rotation
+constexpr int kGroups = VRES_GROUPS;               // builder groups (64 kTpp threads = the pixels of a patch)
+constexpr int kOmStages = 4;                       // staged offsets / masks in rotation: free again after the group's decode
 constexpr int kGroupWarps = 2 * kTpp;
-constexpr int kDrainWarp0 = kGroupWarps * kGroups; // four drain warps: tensor-memory lane quarter = warp & 3
-constexpr int kLoadWarp = kDrainWarp0 + 4, kMmaWarp = kLoadWarp + 1;
-constexpr int kThreads = (kMmaWarp + 1) * 32;      // 448 / 704
+constexpr int kBuilderWarps = kGroupWarps * kGroups;
+// four drain warps, warp index = 0 mod 4 first (a warp reads the tensor-memory lane quarter warp & 3); the two single-lane
+// roles sit before them when the builders end on a half quartet, behind them otherwise
+constexpr bool kRolesFirst = kBuilderWarps % 4 == 2;
+constexpr int kLoadWarp = kRolesFirst ? kBuilderWarps : kBuilderWarps + 4, kMmaWarp = kLoadWarp + 1;
+constexpr int kDrainWarp0 = kRolesFirst ? kBuilderWarps + 2 : kBuilderWarps;
+constexpr int kThreads = (kBuilderWarps + 6) * 32; // 512 (kTpp 1, five groups) / 704 (kTpp 2, four groups)
+static_assert(kDrainWarp0 % 4 == 0, "drain warp w must own tensor-memory lane quarter w & 3");
 constexpr int kBand = 16;                          // band of a patch: 16 x 16 cells = 2 x 2 blocks
 constexpr int kSubBytes = 64 * 128;                // one block's coefficients: 64 cells x 64 pixels x 2 B
 constexpr int kATileBytes = 4 * kSubBytes;         // 32768
 constexpr int kOffRow = 48, kMskRow = 32;          // staged bytes per pixel (36 / 18 used, 16-byte multiples)
-constexpr int kStOff = 0, kStMsk = 64 * kOffRow, kStGout = kStMsk + 64 * kMskRow;
-constexpr int kStBytes = kStGout + 2 * 1024;       // + grad_out as [8-channel half][64 px][16 B]: 7168
-constexpr int kSmemBytes = 1024 + kSlots * kATileBytes + kStages * kStBytes;   // 222208
+constexpr int kStOff = 0, kStMsk = 64 * kOffRow;
+constexpr int kOmBytes = kStMsk + 64 * kMskRow;    // 5120
+constexpr int kGoutBytes = 2 * 1024;               // grad_out of a patch as [8-channel half][64 px][16 B]
+constexpr int kSmemBytes = 1024 + kSlots * (kATileBytes + kGoutBytes) + kOmStages * kOmBytes;   // 230400
 constexpr int kMaxRing = 5;
 constexpr int kTmemCols = 512;
 
@@ -80,14 +107,29 @@ __device__ __forceinline__ void bulk_fill(uint32_t dst, const void *src, uint32_
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// development only (-DVRES_HANG_DEBUG): a waiter that has polled ~2^20 times reports (role, barrier tag, patch) into host-mapped memory set by
+// dcnv3_vres_debug_hang(ptr) -- a hung pipeline can then be read from the host while the kernel still spins
+__device__ unsigned long long *g_vres_hang;
+__device__ __noinline__ void report_hang(int tag, unsigned p, unsigned parity) {
+    unsigned long long *h = g_vres_hang;
+    if (!h || blockIdx.x >= 2) return;
+    const unsigned slot = atomicAdd((unsigned *)h, 1u);
+    if (slot < 60) h[1 + slot] = ((unsigned long long)blockIdx.x << 48) | ((unsigned long long)(threadIdx.x >> 5) << 40) |
+                                 ((unsigned long long)tag << 32) | ((unsigned long long)parity << 31) | p;
+    __threadfence_system();
+}
+
 // a wait that yields its issue slots while it polls (roles that wait for long: drain, refill, builders out of slots)
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, unsigned parity, unsigned ns) {
-    for (;;) {
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, unsigned parity, unsigned ns, int tag = 0, unsigned p = 0) {
+    for (unsigned it = 0;; ++it) {
+#ifdef VRES_HANG_DEBUG
+        if (it == (1u << 20)) report_hang(tag, p, parity);
+#endif
         uint32_t ok;
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
         if (ok) return;
-        __nanosleep(ns);
+        if (ns) __nanosleep(ns);
     }
 }
 __device__ __forceinline__ bool elect_one() {
@@ -158,15 +200,20 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
          const __grid_constant__ CUtensorMap tmap_gout, T *__restrict__ grad_value, uint16_t *__restrict__ far_mask,
          unsigned long long *__restrict__ far_count, const Geom q, const RParams pp) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t a_ready[kSlots], a_full[kSlots], a_done[kSlots], in_full[kStages], row_done[kMaxRing], acc_free[kMaxRing];
+    __shared__ __align__(8) uint64_t a_ready[kSlots], a_full[kSlots], a_done[kSlots], om_full[kOmStages], om_free[kOmStages],
+        row_done[kMaxRing], acc_free[kMaxRing];
     __shared__ uint32_t tmem_base_s;
+    // which patch a staged offsets / masks buffer currently belongs to.  There are fewer buffers than builder groups, and
+    // a group may run more than kOmStages patches ahead of another: a parity wait alone would then be satisfied by the
+    // phase before last (measured: a dead-locked pipeline).  A builder first waits for its patch number to appear here.
+    __shared__ volatile uint32_t om_seq[kOmStages];
 
     // (the warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the product warp's
     // descriptors in uniform registers -- with `tid >> 5` every tcgen05.mma was wrapped in an elect / R2UR loop,
     // ~80 cycles per product)
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     unsigned char *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const uint32_t slot0 = smem_u32(base), stage0 = slot0 + kSlots * kATileBytes;
+    const uint32_t slot0 = smem_u32(base), gout0 = slot0 + kSlots * kATileBytes, om0 = gout0 + kSlots * kGoutBytes;
 
     // this CTA's run of the flattened patch-row list
     // (pp.cpg CTAs per group, every group's rows cut the same way: all groups walk the images in lock step)
@@ -182,7 +229,7 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
 
     if (tid == 0) {
         for (int i = 0; i < kSlots; ++i) { mbar_init(&a_ready[i], 1); mbar_init(&a_full[i], 64 * kTpp); mbar_init(&a_done[i], 1); }
-        for (int i = 0; i < kStages; ++i) mbar_init(&in_full[i], 1);
+        for (int i = 0; i < kOmStages; ++i) { mbar_init(&om_full[i], 1); mbar_init(&om_free[i], kGroupWarps); om_seq[i] = 0xffffffffu; }
         for (int i = 0; i < kMaxRing; ++i) { mbar_init(&row_done[i], 1); mbar_init(&acc_free[i], 4); }
         fence_barrier_init();
         prefetch_tensormap(&tmap_off);
@@ -203,7 +250,7 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
 
     const int C = q.G * q.gc;
 
-    if (warp < kDrainWarp0) {
+    if (warp < kBuilderWarps) {
         // ================================================================== builders: thread <-> pixel of the patch
         // (kTpp == 2: two threads per pixel; `par` owns the band rows of that parity, so each of a point's two rows has
         // exactly one writer and the 16-bit read-modify-writes of a column never race)
@@ -219,12 +266,14 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
             const float bh = axis_base(ho, 3, 1, q.ph, 1, q.sigma) - (float)(row.i * 8 + pp.by_rel);
             for (int j = 0; j < pp.S; ++j, ++p) {
                 if ((int)(p % kGroups) != grp) continue;
-                const unsigned slot = p % kSlots, stage = p % kStages;
+                const unsigned slot = p % kSlots, stage = p % kOmStages;
                 const uint32_t a_thr = slot0 + slot * kATileBytes + kl;
-                const uint32_t sa = stage0 + stage * kStBytes;
+                const uint32_t sa = om0 + stage * kOmBytes;
                 const bool dbg = (pp.diag & 1) && blockIdx.x == 0 && wg == 0 && lane == 0 && p < 256u;
                 if (dbg) g_vres_dbg[p][0] = clock64();
-                mbar_wait_sleep(&in_full[stage], (p / kStages) & 1u, 32);
+                if (kOmStages < kGroups) while (om_seq[stage] != p) __nanosleep(32);
+                mbar_wait_sleep(&om_full[stage], (p / kOmStages) & 1u, (pp.diag & 32) ? 0 : 32, 1, p);
+                if (dbg) g_vres_dbg[p][3] = clock64();
                 const int wo = j * 8 + px_x;
                 const bool live = wo < q.Wo && ho < q.Ho;
                 unsigned far = 0;
@@ -247,7 +296,9 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                     for (int t = 0; t < 5; ++t)
                         mw[t] = ws == 0 ? u[t] : ws == 1 ? u[t + 1] : ws == 2 ? u[t + 2] : (t + 3 < 8 ? u[t + 3] : 0u);
                 }
-                mbar_wait_sleep(&a_ready[slot], (p / kSlots) & 1u, 32);      // the tile is zero again
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&om_free[stage]);                 // offsets / masks are in registers
+                mbar_wait_sleep(&a_ready[slot], (p / kSlots) & 1u, (pp.diag & 32) ? 0 : 32, 2, p);      // the tile is zero again
                 if (dbg) g_vres_dbg[p][1] = clock64();
                 if (live) {
                     const float bw = axis_base(wo, 3, 1, q.pw, 1, q.sigma) - (float)(j * 8 + pp.bx_rel);
@@ -293,35 +344,47 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                                 sts16(eb[pt], bits16(a1 + wb[pt], T()));
                             }
                     } else {
+                        // one thread per pixel: batches of three points -- first their four word addresses and
+                        // coefficients (independent chains), then the read-modify-writes in order
+                        const uint32_t kcs = kc << 4;
 #pragma unroll
-                    for (int pt = 0; pt < kP; ++pt) {
-                        const float2 d = unpack2(off[pt], T());
-                        const float m = f32_of((uint16_t)(mw[pt >> 1] >> (16 * (pt & 1))), T());
-                        const float ub = bw + ((float)(pt / 3) + d.x) * q.sigma;
-                        const float vb = bh + ((float)(pt % 3) + d.y) * q.sigma;
-                        const float fw = floorf(ub), fh = floorf(vb);
-                        const float lw = ub - fw, lh = vb - fh;
-                        if (__float_as_uint(ub) < __float_as_uint((float)(kBand - 1)) &&
-                            __float_as_uint(vb) < __float_as_uint((float)(kBand - 1))) {
-                            const uint32_t cx = (uint32_t)(int)fw, ry = (uint32_t)(int)fh, cx1 = cx + 1u;
-                            const uint32_t c0 = (cx >> 3) * kSubBytes + (cx & 7u) * 128u + ((kc ^ (cx & 7u)) << 4);
-                            const uint32_t c1 = (cx1 >> 3) * kSubBytes + (cx1 & 7u) * 128u + ((kc ^ (cx1 & 7u)) << 4);
-                            const float hwt = 1.f - lw;
-                            if ((!row.up_own && ry < 7u) || (!row.down_own && ry >= 8u)) continue;
-                            const float hm = (1.f - lh) * m, lm = lh * m;
-                            const uint32_t ry1 = ry + 1u;
-                            const uint32_t r0 = a_thr + (ry >> 3) * (2 * kSubBytes) + (ry & 7u) * 1024u;
-                            const uint32_t r1 = a_thr + (ry1 >> 3) * (2 * kSubBytes) + (ry1 & 7u) * 1024u;
-                            const float a0 = f32_of((uint16_t)lds16(r0 + c0), T()), a1 = f32_of((uint16_t)lds16(r0 + c1), T());
-                            const float a2 = f32_of((uint16_t)lds16(r1 + c0), T()), a3 = f32_of((uint16_t)lds16(r1 + c1), T());
-                            sts16(r0 + c0, bits16(a0 + hm * hwt, T()));
-                            sts16(r0 + c1, bits16(a1 + hm * lw, T()));
-                            sts16(r1 + c0, bits16(a2 + lm * hwt, T()));
-                            sts16(r1 + c1, bits16(a3 + lm * lw, T()));
-                        } else {
-                            far |= 1u << pt;
+                        for (int b3 = 0; b3 < kP; b3 += 3) {
+                            uint32_t e0[3], e1[3], e2[3], e3[3];
+                            float w0[3], w1[3], w2[3], w3[3];
+#pragma unroll
+                            for (int u = 0; u < 3; ++u) {
+                                const int pt = b3 + u;
+                                const float2 d = unpack2(off[pt], T());
+                                const float m = f32_of((uint16_t)(mw[pt >> 1] >> (16 * (pt & 1))), T());
+                                const float ub = bw + ((float)(pt / 3) + d.x) * q.sigma;
+                                const float vb = bh + ((float)(pt % 3) + d.y) * q.sigma;
+                                const float fw = floorf(ub), fh = floorf(vb);
+                                const float lw = ub - fw, lh = vb - fh;
+                                const bool inb = __float_as_uint(ub) < __float_as_uint((float)(kBand - 1)) &&
+                                                 __float_as_uint(vb) < __float_as_uint((float)(kBand - 1));
+                                far |= inb ? 0u : 1u << pt;
+                                const uint32_t cx = (uint32_t)(int)fw, ry = (uint32_t)(int)fh, cx1 = cx + 1u, ry1 = ry + 1u;
+                                // a block row this CTA does not own is never multiplied: skip points entirely inside it
+                                const bool act = inb && !((!row.up_own && ry < 7u) || (!row.down_own && ry >= 8u));
+                                const float hm = (1.f - lh) * m, lm = lh * m, hwt = 1.f - lw;
+                                const uint32_t r0 = a_thr + ((ry & 8u) << 11) + ((ry & 7u) << 10);
+                                const uint32_t r1 = a_thr + ((ry1 & 8u) << 11) + ((ry1 & 7u) << 10);
+                                const uint32_t c0 = (((cx & 7u) * 0x90u) ^ kcs) | ((cx & 8u) << 10);
+                                const uint32_t c1 = (((cx1 & 7u) * 0x90u) ^ kcs) | ((cx1 & 8u) << 10);
+                                e0[u] = act ? r0 + c0 : 0u; e1[u] = r0 + c1; e2[u] = r1 + c0; e3[u] = r1 + c1;
+                                w0[u] = hm * hwt; w1[u] = hm * lw; w2[u] = lm * hwt; w3[u] = lm * lw;
+                            }
+#pragma unroll
+                            for (int u = 0; u < 3; ++u)
+                                if (e0[u]) {
+                                    const float a0 = f32_of((uint16_t)lds16(e0[u]), T()), a1 = f32_of((uint16_t)lds16(e1[u]), T());
+                                    const float a2 = f32_of((uint16_t)lds16(e2[u]), T()), a3 = f32_of((uint16_t)lds16(e3[u]), T());
+                                    sts16(e0[u], bits16(a0 + w0[u], T()));
+                                    sts16(e1[u], bits16(a1 + w1[u], T()));
+                                    sts16(e2[u], bits16(a2 + w2[u], T()));
+                                    sts16(e3[u], bits16(a3 + w3[u], T()));
+                                }
                         }
-                    }
                     }
                 }
                 if (dbg) g_vres_dbg[p][2] = clock64();
@@ -336,14 +399,14 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
         asm volatile("griddepcontrol.wait;" ::: "memory");
         far_total = __reduce_add_sync(0xffffffffu, far_total);
         if (lane == 0 && far_total) atomicAdd(far_count, (unsigned long long)far_total);
-    } else if (warp < kLoadWarp) {
+    } else if (warp >= kDrainWarp0 && warp < kDrainWarp0 + 4) {
         // ================================================================== drain: one tensor-memory lane quarter each
         const int wq = warp & 3;
         Sched sch(lo, hi, pp.PR, q.N);
         Row row;
         auto drain = [&](int ev, int r, int n, int g) {
             const int sr = ev % pp.ring;
-            mbar_wait_sleep(&row_done[sr], (unsigned)(ev / pp.ring) & 1u, 256);
+            mbar_wait_sleep(&row_done[sr], (unsigned)(ev / pp.ring) & 1u, 256, 5, (unsigned)ev);
             tc_fence_after();
             const int y = r * 8 + pp.by_rel + 2 * wq + ((lane >> 3) & 1);
             const bool oky = (unsigned)y < (unsigned)q.H;
@@ -372,38 +435,33 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
     } else if (warp == kLoadWarp) {
         // ================================================================== refill + inputs of the next patches
         if (lane == 0) {
-            Sched sch(lo, hi, pp.PR, q.N), sch_in(lo, hi, pp.PR, q.N);
-            Row row, rin;
-            int jin = 0;
-            unsigned pin = 0;
-            bool more_in = sch_in.next(rin);
-            auto request_inputs = [&]() {   // offsets / masks / grad_out of patch `pin`, kAhead patches before its tile
-                if (!more_in) return;
-                unsigned char *st = base + kSlots * kATileBytes + (pin % kStages) * kStBytes;
-                uint64_t *bar = &in_full[pin % kStages];
-                mbar_expect_tx(bar, kStBytes);
-                // a box starts on a 16-byte boundary of the row: the group's run begins 0..3 words / 0..7 elements in
-                tma_load_4d(st + kStOff, &tmap_off, bar, (rin.g * kP * 4 & ~15) >> 1, jin * 8, rin.i * 8, rin.n);
-                tma_load_4d(st + kStMsk, &tmap_msk, bar, (rin.g * kP * 2 & ~15) >> 1, jin * 8, rin.i * 8, rin.n);
-                tma_load_4d(st + kStGout, &tmap_gout, bar, rin.g * kCh, jin * 8, rin.i * 8, rin.n);
-                tma_load_4d(st + kStGout + 1024, &tmap_gout, bar, rin.g * kCh + 8, jin * 8, rin.i * 8, rin.n);
-                ++pin;
-                if (++jin == pp.S) { jin = 0; more_in = sch_in.next(rin); }
-            };
-            for (int t = 0; t < kAhead; ++t) request_inputs();
+            Sched sch(lo, hi, pp.PR, q.N);
+            Row row;
             unsigned p = 0;
             while (sch.next(row)) {
                 for (int j = 0; j < pp.S; ++j, ++p) {
-                    const unsigned slot = p % kSlots;
+                    const unsigned slot = p % kSlots, stage = p % kOmStages;
                     const bool dbg = (pp.diag & 1) && blockIdx.x == 0 && p < 256u;
-                    if (dbg) g_vres_dbg[p][3] = clock64();
-                    // patch p - kSlots is through its products: its tile can be zeroed for patch p, and its input stage
-                    // (p - kSlots) % kStages = (p + kAhead) % kStages takes the inputs of patch p + kAhead
-                    if (p >= (unsigned)kSlots) mbar_wait_sleep(&a_done[slot], (p / kSlots - 1u) & 1u, 32);
+                    // offsets / masks: the buffer is free once the group of patch p - kOmStages has decoded them
+                    if (p >= (unsigned)kOmStages) mbar_wait_sleep(&om_free[stage], (p / kOmStages - 1u) & 1u, (pp.diag & 64) ? 0 : 32, 3, p);
+                    {
+                        unsigned char *st = base + kSlots * (kATileBytes + kGoutBytes) + stage * kOmBytes;
+                        uint64_t *bar = &om_full[stage];
+                        om_seq[stage] = p;
+                        mbar_expect_tx(bar, kOmBytes);
+                        // a box starts on a 16-byte boundary of the row: the group's run begins 0..3 words / 0..7 elements in
+                        tma_load_4d(st + kStOff, &tmap_off, bar, (row.g * kP * 4 & ~15) >> 1, j * 8, row.i * 8, row.n);
+                        tma_load_4d(st + kStMsk, &tmap_msk, bar, (row.g * kP * 2 & ~15) >> 1, j * 8, row.i * 8, row.n);
+                    }
+                    // patch p - kSlots is through its products: its tile is zeroed for patch p and its grad_out replaced
+                    if (p >= (unsigned)kSlots) mbar_wait_sleep(&a_done[slot], (p / kSlots - 1u) & 1u, (pp.diag & 64) ? 0 : 32, 4, p);
                     if (dbg) g_vres_dbg[p][4] = clock64();
-                    mbar_expect_tx(&a_ready[slot], kATileBytes);
-                    bulk_fill(slot0 + slot * kATileBytes, g_zero_tile, kATileBytes, &a_ready[slot]);
-                    request_inputs();
+                    uint64_t *bar = &a_ready[slot];
+                    mbar_expect_tx(bar, kATileBytes + kGoutBytes);
+                    bulk_fill(slot0 + slot * kATileBytes, g_zero_tile, kATileBytes, bar);
+                    unsigned char *gs = base + kSlots * kATileBytes + slot * kGoutBytes;
+                    tma_load_4d(gs, &tmap_gout, bar, row.g * kCh, j * 8, row.i * 8, row.n);
+                    tma_load_4d(gs + 1024, &tmap_gout, bar, row.g * kCh + 8, j * 8, row.i * 8, row.n);
                 }
             }
         }
@@ -413,7 +471,7 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
         {
             const uint32_t idesc = umma_idesc(std::is_same<T, __nv_bfloat16>::value ? 1 : 0, 64, kCh);
             // descriptors of slot 0 / block 0 / K step 0; the others differ in the 14-bit address field only
-            const uint64_t adesc0 = umma_desc_k_sw128(slot0), bdesc0 = umma_desc_mn_plain(stage0 + kStGout, 128, 1024);
+            const uint64_t adesc0 = umma_desc_k_sw128(slot0), bdesc0 = umma_desc_mn_plain(gout0, 128, 1024);
             Sched sch(lo, hi, pp.PR, q.N);
             Row row;
             unsigned p = 0;
@@ -428,7 +486,7 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                 const int base_down = row.down_own ? (row.ev_down % pp.ring) * pp.nbxp : 0;
                 for (int j = 0; j < pp.S; ++j, ++p) {
                     const unsigned slot = p % kSlots;
-                    const uint64_t ad = adesc0 + (uint64_t)((slot * kATileBytes) >> 4), bd = bdesc0 + (uint64_t)(((p % kStages) * kStBytes) >> 4);
+                    const uint64_t ad = adesc0 + (uint64_t)((slot * kATileBytes) >> 4), bd = bdesc0 + (uint64_t)((slot * kGoutBytes) >> 4);
                     const bool dbg = (pp.diag & 1) && blockIdx.x == 0 && p < 256u;
                     if (dbg && lane == 0) g_vres_dbg[p][5] = clock64();
                     mbar_wait(&a_full[slot], (p / kSlots) & 1u);
@@ -661,6 +719,10 @@ bool try_launch_backward_vres(const void *offset, const void *mask, const void *
 }  // namespace dcnv3
 
 // development only: the cycle stamps of the last launch (scripts/vres_timeline.py)
+extern "C" __attribute__((visibility("default"))) int dcnv3_vres_debug_hang(void *host_mapped) {
+    unsigned long long *p = static_cast<unsigned long long *>(host_mapped);
+    return (int)cudaMemcpyToSymbol(dcnv3::vres::g_vres_hang, &p, sizeof(p));
+}
 extern "C" __attribute__((visibility("default"))) int dcnv3_vres_debug_read(void *dst) {
     return (int)cudaMemcpyFromSymbol(dst, dcnv3::vres::g_vres_dbg, sizeof(dcnv3::vres::g_vres_dbg));
 }
