@@ -663,7 +663,7 @@ def run_ours(args, rank, world, local_rank):
                 "pipeline_over_bare_copy": (e2e_ms / e2e_steps) / (bare_ms / e2e_steps),
                 "cpu_cores_bound": cpu_bind},
         "gpu_launches": 4 * args.steps,   # fwd_gs, bwd_dots, bwd_vmma, narrow_f32 (the memset is the driver's)
-        "roofline": {"bound": "hbm", "kernel": "backward pass: bdots::bwd_dots (also zeroes the fp32 plane) + vmma::bwd_vmma (tcgen05 / TMEM) + narrow_f32, chained by programmatic dependent launch",
+        "roofline": {"bound": "hbm", "kernel": "backward pass: bdots::bwd_dots (channel sums) + vres::bwd_vres (grad_value, tcgen05 with the accumulator resident in TMEM, written once) + vres::far_points (+ two conditional fall-back launches that exit at once), chained by programmatic dependent launch",
                      "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes": ab["bwd"], "avg_ms": bwd_t * 1e3},

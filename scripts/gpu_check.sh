@@ -13,7 +13,7 @@ if [ "${NCU:-1}" = "1" ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv \
       --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-train > gpurun_out/ncu_list.log 2>&1
   echo "ncu list rc=$?"
-  ncu --set full --clock-control none --import-source on -k regex:"fwd_|bwd_" -s 6 -c 4 \
+  ncu --set full --clock-control none --import-source on -k regex:"fwd_|bwd_|far_points" -s 6 -c 6 \
       -o gpurun_out/prof_r2 -f python bench.py --steps 2 --warmup 1 --no-cpu --no-train > gpurun_out/ncu_full.log 2>&1
   echo "ncu full rc=$?"
 fi

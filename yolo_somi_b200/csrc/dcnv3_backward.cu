@@ -471,7 +471,12 @@ static cudaError_t backward_typed(const void *value, const void *offset, const v
     const size_t n_out = (size_t)q.N * q.Ho * q.Wo * q.G * q.gc;
     const bool vec_ok = (((uintptr_t)value | (uintptr_t)grad_out | (uintptr_t)grad_value) % 16 == 0) &&
                         (((uintptr_t)offset | (uintptr_t)grad_offset) % (2 * sizeof(T)) == 0);
-    const int aux_blocks = 148 * 8;
+    static const int num_sms = [] {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        return n;
+    }();
+    const int aux_blocks = num_sms * 8;
     cudaError_t err;
     if (plane == 0) return cudaSuccess;
 

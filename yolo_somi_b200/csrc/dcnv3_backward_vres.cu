@@ -37,10 +37,11 @@
 //       - four drain warps, one per tensor-memory lane quarter.
 //     Six slots (coefficient tile + grad_out) rotate between them through mbarriers.
 // A point whose corner block leaves the 16 x 16 band of its patch (|offset| beyond ~3 px; rare for trained offsets)
-// is only flagged (one 16-bit mask per pixel and group); `far_points` adds those afterwards with 16-bit vector
-// reductions (REDG.ADD.BF16x8) -- one extra rounding of the stored result for the cells they touch, and grad_value is
-// reproducible only up to the order of those additions.  If more than 1 / 32 of all points are far, the caller's
-// fall-back (the plane form) recomputes grad_value; both decide on the device from a counter, no host round trip.
+// is only LISTED (a builder warp reserves its places with one atomic on the call's far-point counter); `far_points`
+// adds those afterwards, one warp per point, with 16-bit reductions -- one extra rounding of the stored result for
+// the cells they touch, and grad_value is reproducible only up to the order of those additions.  If more than 1 / 32
+// of all points are far, the caller's fall-back (the plane form) recomputes grad_value; both decide on the device
+// from the counter, no host round trip.
 //
 // Measured on cfg2 bf16 (profiles/README.md, r2): 152 us (ncu) against 149 + 23 (narrow) + ~8 (plane zeroing inside
 // the channel-sum kernel) for the plane form; backward pass 264.4 -> 259.8 us, its DRAM traffic 816 -> 440 MB.
@@ -151,6 +152,7 @@ struct RParams {
     int nbxp, ring;          // blocks per block row (even), block rows resident
     int total_rows;          // N * G * PR
     int cpg;                 // CTAs per group (0: one flat split of the list)
+    unsigned long long far_cap;   // entries the far-point list can take (= the fall-back threshold)
 };
 
 // The CTA's list of patch rows.  Every role walks the same list, so event numbers (= owned block rows in the order
@@ -190,14 +192,10 @@ struct Sched {
     }
 };
 
-__device__ __forceinline__ size_t far_index(const RParams &pp, const Geom &q, int n, int g, int i, int j) {
-    return ((((size_t)n * q.G + g) * pp.PR + i) * pp.S + j) * 64;
-}
-
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 1)
 bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ CUtensorMap tmap_msk,
-         const __grid_constant__ CUtensorMap tmap_gout, T *__restrict__ grad_value, uint16_t *__restrict__ far_mask,
+         const __grid_constant__ CUtensorMap tmap_gout, T *__restrict__ grad_value, uint32_t *__restrict__ far_list,
          unsigned long long *__restrict__ far_count, const Geom q, const RParams pp) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t a_ready[kSlots], a_full[kSlots], a_done[kSlots], om_full[kOmStages], om_free[kOmStages],
@@ -244,10 +242,10 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
-    // Programmatic dependent launch: nothing this kernel reads or writes is touched by the channel-sum kernel in front of
-    // it except the far-point counter (zeroed there), so only the counter update at the very end waits for that grid --
-    // the whole pipeline overlaps the channel sums' last wave.  (Every thread executes the wait before it exits.)
-
+    // Programmatic dependent launch: the prologue above runs under the channel-sum kernel's last wave; the far-point
+    // counter is zeroed by that kernel, so everything below waits for it.  (Waiting only at the end -- the pipeline
+    // overlapping the channel sums' tail -- was measured: no difference, a CTA of this kernel needs a whole SM.)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int C = q.G * q.gc;
 
     if (warp < kBuilderWarps) {
@@ -260,7 +258,7 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
         const uint32_t kc = (uint32_t)k >> 3, kl = ((uint32_t)k & 7u) * 2u;
         Sched sch(lo, hi, pp.PR, q.N);
         Row row;
-        unsigned p = 0, far_total = 0;
+        unsigned p = 0;
         while (sch.next(row)) {
             const int ho = row.i * 8 + px_y;
             const float bh = axis_base(ho, 3, 1, q.ph, 1, q.sigma) - (float)(row.i * 8 + pp.by_rel);
@@ -390,15 +388,25 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                 if (dbg) g_vres_dbg[p][2] = clock64();
                 fence_proxy_async();
                 mbar_arrive(&a_full[slot]);
-                if (!row.dup && par == 0) {
-                    far_mask[far_index(pp, q, row.n, row.g, row.i, j) + k] = (uint16_t)far;
-                    far_total += __popc(far);
+                if (!row.dup && par == 0 && __ballot_sync(0xffffffffu, far != 0u)) {
+                    // rare: the warp appends its far points to the list (one atomic per warp for the positions)
+                    const int nf = __popc(far);
+                    int incl = nf;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += t;
+                    }
+                    const int total = __shfl_sync(0xffffffffu, incl, 31);
+                    unsigned long long pos = 0;
+                    if (lane == 0) pos = atomicAdd(far_count, (unsigned long long)total);
+                    pos = __shfl_sync(0xffffffffu, pos, 0) + (unsigned long long)(incl - nf);
+                    const uint32_t pg = (uint32_t)((((size_t)row.n * q.Ho + ho) * q.Wo + wo) * q.G + row.g);
+                    for (unsigned f = far; f; f &= f - 1u, ++pos)
+                        if (pos < pp.far_cap) far_list[pos] = (pg << 4) | (uint32_t)(__ffs(f) - 1);
                 }
             }
         }
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-        far_total = __reduce_add_sync(0xffffffffu, far_total);
-        if (lane == 0 && far_total) atomicAdd(far_count, (unsigned long long)far_total);
     } else if (warp >= kDrainWarp0 && warp < kDrainWarp0 + 4) {
         // ================================================================== drain: one tensor-memory lane quarter each
         const int wq = warp & 3;
@@ -526,7 +534,6 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
         }
     }
 
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     tc_fence_before();
     __syncthreads();   // the drain warps have seen the last commit: every product and refill has completed
@@ -535,89 +542,56 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
 
 // ------------------------------------------------------------------------------------------------------------------
 // Points that left the band of their patch: thread <-> (pixel, group); almost every thread reads a zero mask and exits.
-// 128-bit vector reduction of eight 16-bit values (REDG.E.ADD.BF16x8 / F16x8): fire and forget
-__device__ __forceinline__ void red_add8(__nv_bfloat16 *p, uint4 v) {
-    asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ void red_add8(__half *p, uint4 v) {
-    asm volatile("red.global.add.noftz.v4.f16x2 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
+// 32-bit reduction of two 16-bit values
+__device__ __forceinline__ void red_add2(__nv_bfloat16 *p, uint32_t v) { asm volatile("red.global.add.noftz.bf16x2 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void red_add2(__half *p, uint32_t v) { asm volatile("red.global.add.noftz.f16x2 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-// One far point: four coefficient x grad_out rows added to the stored 16-bit result with vector atomics.
-template <typename T>
-__device__ __noinline__ void far_pixel(unsigned far, size_t idx, const T *__restrict__ offset, const T *__restrict__ mask,
-                                       const T *__restrict__ grad_out, T *__restrict__ grad_value, const Geom &q, const RParams &pp) {
-    const int k = (int)(idx & 63);
-    size_t t = idx >> 6;
-    const int j = (int)(t % pp.S); t /= pp.S;
-    const int i = (int)(t % pp.PR); t /= pp.PR;
-    const int g = (int)(t % q.G), n = (int)(t / q.G);
-    const int wo = j * 8 + (k & 7), ho = i * 8 + (k >> 3);
-    if (wo >= q.Wo || ho >= q.Ho) return;
-    const int C = q.G * q.gc;
-    const size_t pix = ((size_t)n * q.Ho + ho) * q.Wo + wo;
-    const T *op = offset + (pix * q.G + g) * (kP * 2), *mp = mask + (pix * q.G + g) * kP;
-    float gch[kCh];
-    {
-        const uint4 *gp = reinterpret_cast<const uint4 *>(grad_out + pix * C + g * kCh);
-        unpack<T>(gp[0], gch);
-        unpack<T>(gp[1], gch + 8);
-    }
-    const float bw = axis_base(wo, 3, 1, q.pw, 1, q.sigma), bh = axis_base(ho, 3, 1, q.ph, 1, q.sigma);
-    T *gv_img = grad_value + (size_t)n * q.H * q.W * C + g * kCh;
-    for (; far; far &= far - 1) {
-        const int pt = __ffs(far) - 1;
-        const float m = to_f32(mp[pt]);
-        const float lw_abs = bw + ((float)(pt / 3) + to_f32(op[2 * pt])) * q.sigma;
-        const float lh_abs = bh + ((float)(pt % 3) + to_f32(op[2 * pt + 1])) * q.sigma;
-        if (!(lh_abs > -1.f && lw_abs > -1.f && lh_abs < (float)q.H && lw_abs < (float)q.W)) continue;   // (:262-263)
-        const float fw = floorf(lw_abs), fh = floorf(lh_abs);
-        const float lw = lw_abs - fw, lh = lh_abs - fh;
-        const float cf[4] = {(1.f - lh) * m * (1.f - lw), (1.f - lh) * m * lw, lh * m * (1.f - lw), lh * m * lw};
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int hh = (int)fh + (c >> 1), ww = (int)fw + (c & 1);
-            if ((unsigned)hh < (unsigned)q.H && (unsigned)ww < (unsigned)q.W && cf[c] != 0.f) {
-                T *dst = gv_img + ((size_t)hh * q.W + ww) * C;
-                float pr[kCh];
-#pragma unroll
-                for (int e = 0; e < kCh; ++e) pr[e] = cf[c] * gch[e];
-                red_add8(dst, pack<T>(pr));
-                red_add8(dst + 8, pack<T>(pr + 8));
-            }
-        }
-    }
-}
-
-// After the product kernel: thread <-> eight (pixel, group) masks; almost every thread reads 16 zero bytes and exits.
+// After the product kernel: one WARP per listed far point -- lane = (corner, channel pair): every lane computes the
+// point's location (broadcast loads of its offset / mask), takes its two grad_out channels and adds its corner's
+// share to the stored 16-bit result (a corner = one 32-byte sector of eight 32-bit reductions).
 // If the call produced more far points than `thr`, nothing is added here: the caller's fall-back (the plane form,
 // launched behind this kernel on the same condition) recomputes grad_value, and this kernel zeroes its fp32 plane.
+// (A first form scanned one 16-bit mask per pixel and group -- 3.3 MB -- and let single threads walk their points:
+// 19 us for ~3500 points, most of it the serial tail of the few threads that had any.)
 template <typename T>
 __global__ void __launch_bounds__(256)
-far_points(const uint16_t *__restrict__ far_mask, const unsigned long long *__restrict__ far_count, unsigned long long thr,
+far_points(const uint32_t *far_list, const unsigned long long *far_count, unsigned long long thr,
            const T *__restrict__ offset, const T *__restrict__ mask, const T *__restrict__ grad_out, T *__restrict__ grad_value,
-           float4 *__restrict__ plane, size_t plane_vec, const Geom q, const RParams pp, size_t total) {
+           float4 *__restrict__ plane, size_t plane_vec, const Geom q) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const size_t tid = (size_t)blockIdx.x * 256 + threadIdx.x;
     // (volatile asm loads: with plain loads through `const __restrict__` pointers the compiler hoisted the counter's
     // LDG.CONSTANT ABOVE the grid-dependency wait -- the kernel then saw the count before the product kernel had
     // finished adding to it, and took the sparse path while the caller's fall-back kernels saw the final count)
     unsigned long long count;
     asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(count) : "l"(far_count) : "memory");
+    const size_t tid = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (count > thr) {
         for (size_t i = tid; i < plane_vec; i += (size_t)gridDim.x * 256) plane[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         return;
     }
-    const size_t idx = tid * 8;
-    if (idx >= total) return;
-    uint4 w;                                                            // (total is a multiple of 64)
-    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(far_mask + idx) : "memory");
-    if (!(w.x | w.y | w.z | w.w) || (pp.diag & 4)) return;
-    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll 1
-    for (int e = 0; e < 8; ++e) {
-        const unsigned far = (ww[e >> 1] >> (16 * (e & 1))) & 0xffffu;
-        if (far) far_pixel<T>(far, idx + e, offset, mask, grad_out, grad_value, q, pp);
+    const int lane = threadIdx.x & 31, corner = lane >> 3, cp = lane & 7;
+    const int C = q.G * q.gc;
+    for (size_t i = tid >> 5; i < count; i += ((size_t)gridDim.x * 256) >> 5) {
+        uint32_t e;
+        asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(e) : "l"(far_list + i) : "memory");
+        const int pt = (int)(e & 15u);
+        size_t pg = e >> 4;
+        const int g = (int)(pg % q.G); pg /= q.G;        // pg: pixel (n, ho, wo) from here on
+        const int wo = (int)(pg % q.Wo), ho = (int)((pg / q.Wo) % q.Ho), n = (int)(pg / ((size_t)q.Wo * q.Ho));
+        const size_t pix = pg;
+        const T *op = offset + (pix * q.G + g) * (kP * 2) + 2 * pt;
+        const float m = to_f32(mask[(pix * q.G + g) * kP + pt]);
+        const float lw_abs = axis_base(wo, 3, 1, q.pw, 1, q.sigma) + ((float)(pt / 3) + to_f32(op[0])) * q.sigma;
+        const float lh_abs = axis_base(ho, 3, 1, q.ph, 1, q.sigma) + ((float)(pt % 3) + to_f32(op[1])) * q.sigma;
+        if (!(lh_abs > -1.f && lw_abs > -1.f && lh_abs < (float)q.H && lw_abs < (float)q.W)) continue;   // (:262-263)
+        const float fw = floorf(lw_abs), fh = floorf(lh_abs);
+        const float lw = lw_abs - fw, lh = lh_abs - fh;
+        const float cf = ((corner & 2) ? lh : 1.f - lh) * m * ((corner & 1) ? lw : 1.f - lw);
+        const int hh = (int)fh + (corner >> 1), ww = (int)fw + (corner & 1);
+        if ((unsigned)hh < (unsigned)q.H && (unsigned)ww < (unsigned)q.W && cf != 0.f) {
+            const float2 gq = unpack2(*reinterpret_cast<const uint32_t *>(grad_out + pix * C + g * kCh + 2 * cp), T());
+            red_add2(grad_value + (((size_t)n * q.H + hh) * q.W + ww) * C + g * kCh + 2 * cp, pack2(cf * gq.x, cf * gq.y, T()));
+        }
     }
 }
 
@@ -636,6 +610,7 @@ static bool plan(const Geom &q, RParams *pp) {
     pp->nbxp = (pp->S + 2) & ~1;                        // S + 1 blocks per block row, padded to a whole tile
     pp->ring = std::min(kMaxRing, 64 / pp->nbxp);
     if (pp->ring < 3) return false;                     // two rows in work + one leaving
+    if ((long long)q.N * q.Ho * q.Wo * q.G >= (1LL << 28)) return false;   // a far-list entry = (pixel, group) << 4 | point
     const long long rows = (long long)q.N * q.G * pp->PR;
     if (rows >= (1LL << 30)) return false;
     pp->total_rows = (int)rows;
@@ -673,21 +648,20 @@ static bool launch_typed(const void *offset, const void *mask, const void *grad_
         cudaFuncSetAttribute(bwd_vres<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         attr_set = true;
     }
-    uint16_t *far = static_cast<uint16_t *>(scratch);
-    const size_t total = (size_t)pp.total_rows * pp.S * 64;
-    if (total * sizeof(uint16_t) > scratch_bytes) return false;
-    // beyond 1 / 32 of all points on the far path the caller's fall-back takes over
+    // beyond 1 / 32 of all points on the far path the caller's fall-back takes over; the list holds that many entries
     const unsigned long long thr = (unsigned long long)q.N * q.Ho * q.Wo * q.G * kP / 32;
+    if (thr * sizeof(uint32_t) > scratch_bytes) return false;
+    uint32_t *far = static_cast<uint32_t *>(scratch);
+    pp.far_cap = thr;
     *thr_out = thr;
     *err = pdl_launch(true, bwd_vres<T>, dim3(ctas), dim3(kThreads), kSmemBytes, stream, to, tm, tg,
                       static_cast<T *>(grad_value), far, counter, q, pp);
     if (*err == cudaSuccess) *err = cudaGetLastError();
     if (*err != cudaSuccess) return true;
-    const size_t threads = total / 8;
-    *err = pdl_launch(true, far_points<T>, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, stream,
-                      static_cast<const uint16_t *>(far), static_cast<const unsigned long long *>(counter), thr,
+    *err = pdl_launch(true, far_points<T>, dim3(num_sms * 4), dim3(256), 0, stream,
+                      static_cast<const uint32_t *>(far), static_cast<const unsigned long long *>(counter), thr,
                       static_cast<const T *>(offset), static_cast<const T *>(mask), static_cast<const T *>(grad_out),
-                      static_cast<T *>(grad_value), static_cast<float4 *>(scratch), scratch_bytes / 16, q, pp, total);
+                      static_cast<T *>(grad_value), static_cast<float4 *>(scratch), scratch_bytes / 16, q);
     if (*err == cudaSuccess) *err = cudaGetLastError();
     return true;
 }
@@ -703,7 +677,7 @@ bool backward_vres_eligible(const void *offset, const void *mask, const void *gr
 size_t backward_vres_scratch_bytes(const Geom &q) {
     vres::RParams pp;
     if (!vres::plan(q, &pp)) return 0;
-    return (size_t)pp.total_rows * pp.S * 64 * sizeof(uint16_t);
+    return (size_t)q.N * q.Ho * q.Wo * q.G * vres::kP / 32 * sizeof(uint32_t);
 }
 
 // grad_value written directly (16-bit); `scratch` holds the far-point masks (backward_vres_scratch_bytes)

@@ -99,6 +99,12 @@ static bool make_rows_tensor_map(CUtensorMap *map, const void *base, int dtype, 
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Diagnostic builds only (scripts/gpu_gsdiag.sh; results are WRONG, the timing shows what a part costs):
+// -DGS_DIAG=1 the gather's shared-memory loads without the arithmetic, 2 the arithmetic without the gather
+#ifndef GS_DIAG
+#define GS_DIAG 0
+#endif
+
 template <typename T, bool FAST, int GSH, int CH, int KG = kGroups>
 __global__ void __launch_bounds__(kPix * KG, KG == 4 ? 4 : CH == 8 ? 3 : 2)
 fwd_gs(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
@@ -187,8 +193,21 @@ fwd_gs(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUten
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const Weight<T, FAST> wt(w[t]);
+#if GS_DIAG == 1   // gather only: the eight 128-bit shared-memory loads of a point, consumed by three XORs each (WRONG results)
+            const uint4 qa = lds128(tl + o[t]);
+            acc_a[t] = __uint_as_float(((__float_as_uint(acc_a[t]) ^ qa.x ^ qa.y ^ qa.z ^ qa.w) & 0x007fffffu) | 0x3f800000u);   // (never NaN)
+            if (TWO) {
+                const uint4 qb = lds128((tl ^ 16u) + o[t]);
+                acc_b[t] = __uint_as_float(((__float_as_uint(acc_b[t]) ^ qb.x ^ qb.y ^ qb.z ^ qb.w) & 0x007fffffu) | 0x3f800000u);
+            }
+#elif GS_DIAG == 2   // arithmetic only: every point reads the window's first cell (no gather traffic; WRONG results)
+            axpy<T, FAST>(acc_a, lds128(win_addr), wt);
+            if (TWO) axpy<T, FAST>(acc_b, lds128(win_addr ^ 16u), wt);
+            if (t == 3) acc_a[0] += __uint_as_float(tl);   // (keeps the address arithmetic alive)
+#else
             axpy<T, FAST>(acc_a, lds128(tl + o[t]), wt);
             if (TWO) axpy<T, FAST>(acc_b, lds128((tl ^ 16u) + o[t]), wt);
+#endif
         }
     }
 

@@ -10,6 +10,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace dcnv3 {
 
@@ -19,7 +20,7 @@ using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_
                                    const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-inline EncodeTiledFn encode_tiled_fn() {
+inline EncodeTiledFn driver_encode_tiled_fn() {
     static EncodeTiledFn fn = [] {
         void *p = nullptr;
         cudaDriverEntryPointQueryResult q;
@@ -30,6 +31,39 @@ inline EncodeTiledFn encode_tiled_fn() {
     }();
     return fn;
 }
+
+// cuTensorMapEncodeTiled behind a small per-thread cache keyed by ALL of its arguments: a training loop calls the
+// same layer with the same buffers (caching allocator) and shapes step after step, and a backward pass needs up to
+// twelve maps -- on the small feature maps of a real model the encodes were a visible part of the launch cost.
+// (A map encodes nothing but its arguments, so an equal key is an equal map.)
+inline CUresult cached_encode_tiled(CUtensorMap *map, CUtensorMapDataType dt, cuuint32_t rank, void *base, const cuuint64_t *dims,
+                                    const cuuint64_t *strides, const cuuint32_t *box, const cuuint32_t *estr,
+                                    CUtensorMapInterleave il, CUtensorMapSwizzle sw, CUtensorMapL2promotion l2,
+                                    CUtensorMapFloatOOBfill oob) {
+    struct Key {
+        void *base;
+        cuuint64_t dims[5], strides[4];
+        cuuint32_t box[5], estr[5], rank;
+        int dt, il, sw, l2, oob;
+    };
+    struct Entry { Key key; CUtensorMap map; bool used; };
+    constexpr int kEntries = 64;
+    thread_local Entry cache[kEntries];
+    thread_local int next = 0;
+    EncodeTiledFn fn = driver_encode_tiled_fn();
+    if (!fn || rank > 5) return fn ? fn(map, dt, rank, base, dims, strides, box, estr, il, sw, l2, oob) : CUDA_ERROR_NOT_SUPPORTED;
+    Key k;
+    memset(&k, 0, sizeof(k));
+    k.base = base; k.rank = rank; k.dt = (int)dt; k.il = (int)il; k.sw = (int)sw; k.l2 = (int)l2; k.oob = (int)oob;
+    for (cuuint32_t i = 0; i < rank; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; k.estr[i] = estr[i]; if (i + 1 < rank) k.strides[i] = strides[i]; }
+    for (int i = 0; i < kEntries; ++i)
+        if (cache[i].used && memcmp(&cache[i].key, &k, sizeof(k)) == 0) { *map = cache[i].map; return CUDA_SUCCESS; }
+    const CUresult r = fn(map, dt, rank, base, dims, strides, box, estr, il, sw, l2, oob);
+    if (r == CUDA_SUCCESS) { cache[next].key = k; cache[next].map = *map; cache[next].used = true; next = (next + 1) % kEntries; }
+    return r;
+}
+
+inline EncodeTiledFn encode_tiled_fn() { return driver_encode_tiled_fn() ? &cached_encode_tiled : nullptr; }
 
 // Tensor map over a dense channels-last tensor [N,H,W,C] of `elem_bytes`-wide elements with a
 // box of (box_c, box_w, box_h, 1).  Returns false if the driver refuses (caller falls back to the
