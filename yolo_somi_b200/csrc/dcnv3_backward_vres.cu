@@ -77,7 +77,24 @@ using namespace tc;
 constexpr int kTpp = VRES_TPP;                     // builder threads per pixel (2: one owns the even band rows, one the odd)
 constexpr int kSlots = 6;                          // coefficient tiles (+ the patch's grad_out, the B operand) in rotation
 constexpr int kGroups = VRES_GROUPS;               // builder groups (64 kTpp threads = the pixels of a patch)
-constexpr int kOmStages = 4;                       // staged offsets / masks in rotation: free again after the group's decode
+#ifndef VRES_AMN
+#define VRES_AMN 0
+#endif
+// Layout of the coefficient tile.  false: K-major rows of 64 pixels, 128-byte swizzle, 16-bit read-modify-writes (two per
+// point row, ~3.4 shared-memory wavefronts each for N(0, 1) offsets).  true: MN-major core matrices [8 cells of a band
+// row][8 pixels] with the pixel's 16-byte place inside its group of eight ROTATED by twice the patch row,
+// k' = (k & ~7) | ((k & 7) + 2 (k >> 3)) & 7: a horizontal corner pair that starts on an even column is one 32-bit
+// word (1.5 accesses per point row), the bank group of a lane is fixed by its pixel, and the four lanes that share a
+// bank group are pixels two columns apart in four different patch rows, so for small offsets they hit four different
+// words (simulated for N(0, 1) offsets: 4.25 wavefronts per point row against 6.74).  The rotation is a permutation of
+// K: grad_out (the B operand) is written to the same permuted places by the builders.
+// MEASURED (-DVRES_AMN=1, parity-green): 18.4 M shared wavefronts instead of 23.3 M, 10.1 M conflicts instead of 16.5 M --
+// and 172 us instead of 155 us (backward 263.6 against 250.9 us): 11 % more instructions (unpack / pack of word pairs, the
+// second word under a divergent branch, the grad_out copy) at 66 % issue utilisation.  The builders are bound by their
+// instruction stream and its latencies, not by shared-memory bandwidth; the K-major tile stays the default.
+constexpr bool kAmn = VRES_AMN;
+static_assert(!kAmn || VRES_TPP == 2, "the MN-major tile is implemented for two threads per pixel");
+constexpr int kOmStages = kAmn ? 3 : 4;            // staged inputs in rotation: free again after the group's decode
 constexpr int kGroupWarps = 2 * kTpp;
 constexpr int kBuilderWarps = kGroupWarps * kGroups;
 // four drain warps, warp index = 0 mod 4 first (a warp reads the tensor-memory lane quarter warp & 3); the two single-lane
@@ -92,9 +109,10 @@ constexpr int kSubBytes = 64 * 128;                // one block's coefficients: 
 constexpr int kATileBytes = 4 * kSubBytes;         // 32768
 constexpr int kOffRow = 48, kMskRow = 32;          // staged bytes per pixel (36 / 18 used, 16-byte multiples)
 constexpr int kStOff = 0, kStMsk = 64 * kOffRow;
-constexpr int kOmBytes = kStMsk + 64 * kMskRow;    // 5120
 constexpr int kGoutBytes = 2 * 1024;               // grad_out of a patch as [8-channel half][64 px][16 B]
-constexpr int kSmemBytes = 1024 + kSlots * (kATileBytes + kGoutBytes) + kOmStages * kOmBytes;   // 230400
+constexpr int kStGout = kStMsk + 64 * kMskRow;     // (MN-major tile: grad_out is staged with the offsets / masks)
+constexpr int kOmBytes = kStGout + (kAmn ? kGoutBytes : 0);   // 5120 / 7168
+constexpr int kSmemBytes = 1024 + kSlots * (kATileBytes + kGoutBytes) + kOmStages * kOmBytes;   // 230400 / 231424
 constexpr int kMaxRing = 5;
 constexpr int kTmemCols = 512;
 
@@ -132,6 +150,9 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, unsigned parity, 
         if (ok) return;
         if (ns) __nanosleep(ns);
     }
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -265,7 +286,9 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
             for (int j = 0; j < pp.S; ++j, ++p) {
                 if ((int)(p % kGroups) != grp) continue;
                 const unsigned slot = p % kSlots, stage = p % kOmStages;
-                const uint32_t a_thr = slot0 + slot * kATileBytes + kl;
+                // (MN-major: the pixel's 16-byte place -- eight cells of a band row -- inside its group of eight pixels)
+                const uint32_t kp = ((uint32_t)k & ~7u) | ((((uint32_t)k & 7u) + 2u * kc) & 7u);
+                const uint32_t a_thr = kAmn ? slot0 + slot * kATileBytes + kp * 16u : slot0 + slot * kATileBytes + kl;
                 const uint32_t sa = om0 + stage * kOmBytes;
                 const bool dbg = (pp.diag & 1) && blockIdx.x == 0 && wg == 0 && lane == 0 && p < 256u;
                 if (dbg) g_vres_dbg[p][0] = clock64();
@@ -294,10 +317,19 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                     for (int t = 0; t < 5; ++t)
                         mw[t] = ws == 0 ? u[t] : ws == 1 ? u[t + 1] : ws == 2 ? u[t + 2] : (t + 3 < 8 ? u[t + 3] : 0u);
                 }
+                uint4 gq0 = make_uint4(0u, 0u, 0u, 0u), gq1 = gq0;
+                if (kAmn && par == 0) {   // this pixel's grad_out: to the B operand's permuted place once the slot is free
+                    gq0 = lds128(sa + kStGout + k * 16);
+                    gq1 = lds128(sa + kStGout + 1024 + k * 16);
+                }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&om_free[stage]);                 // offsets / masks are in registers
+                if (lane == 0) mbar_arrive(&om_free[stage]);                 // the staged inputs are in registers
                 mbar_wait_sleep(&a_ready[slot], (p / kSlots) & 1u, (pp.diag & 32) ? 0 : 32, 2, p);      // the tile is zero again
                 if (dbg) g_vres_dbg[p][1] = clock64();
+                if (kAmn && par == 0) {
+                    sts128(gout0 + slot * kGoutBytes + kp * 16u, gq0);
+                    sts128(gout0 + slot * kGoutBytes + 1024u + kp * 16u, gq1);
+                }
                 if (live) {
                     const float bw = axis_base(wo, 3, 1, q.pw, 1, q.sigma) - (float)(j * 8 + pp.bx_rel);
                     if constexpr (kTpp == 2) {
@@ -329,17 +361,37 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                             // cell (rr, cx) -> sub-tile (rr >> 3, cx >> 3), row (rr & 7) * 8 + (cx & 7), chunk kc ^ (cx & 7):
                             // (cx & 7) * 0x90 = row * 128 | (cx & 7) * 16, the chunk's xor touches bits 4..6 only
                             const uint32_t r0 = a_thr + ((rr & 8u) << 11) + ((rr & 7u) << 10);
-                            ea[pt] = act ? r0 + ((((cx & 7u) * 0x90u) ^ kcs) | ((cx & 8u) << 10)) : 0u;
-                            eb[pt] = r0 + ((((cx1 & 7u) * 0x90u) ^ kcs) | ((cx1 & 8u) << 10));
+                            if constexpr (kAmn) {
+                                // word of cell c in the row: sub-tile (c & 8) << 10, 32-bit word (c & 6) << 1 of the pixel's place;
+                                // an even column: both cells in ONE word (eb = 0), an odd one: high half, then the next word's low half
+                                ea[pt] = act ? r0 + ((cx & 8u) << 10) + ((cx & 6u) << 1) : 0u;
+                                eb[pt] = (cx & 1u) ? r0 + ((cx1 & 8u) << 10) + ((cx1 & 6u) << 1) : 0u;
+                            } else {
+                                ea[pt] = act ? r0 + ((((cx & 7u) * 0x90u) ^ kcs) | ((cx & 8u) << 10)) : 0u;
+                                eb[pt] = r0 + ((((cx1 & 7u) * 0x90u) ^ kcs) | ((cx1 & 8u) << 10));
+                            }
                             wa[pt] = vm * (1.f - lw);
                             wb[pt] = vm * lw;
                         }
 #pragma unroll
                         for (int pt = 0; pt < kP; ++pt)
                             if (ea[pt]) {
-                                const float a0 = f32_of((uint16_t)lds16(ea[pt]), T()), a1 = f32_of((uint16_t)lds16(eb[pt]), T());
-                                sts16(ea[pt], bits16(a0 + wa[pt], T()));
-                                sts16(eb[pt], bits16(a1 + wb[pt], T()));
+                                if constexpr (kAmn) {
+                                    const bool odd = eb[pt] != 0u;
+                                    float2 f = unpack2(lds32(ea[pt]), T());
+                                    f.x += odd ? 0.f : wa[pt];
+                                    f.y += odd ? wa[pt] : wb[pt];
+                                    sts32(ea[pt], pack2(f.x, f.y, T()));
+                                    if (odd) {   // the pair straddles two words: cell cx + 1 is the next word's low half
+                                        float2 h = unpack2(lds32(eb[pt]), T());
+                                        h.x += wb[pt];
+                                        sts32(eb[pt], pack2(h.x, h.y, T()));
+                                    }
+                                } else {
+                                    const float a0 = f32_of((uint16_t)lds16(ea[pt]), T()), a1 = f32_of((uint16_t)lds16(eb[pt]), T());
+                                    sts16(ea[pt], bits16(a0 + wa[pt], T()));
+                                    sts16(eb[pt], bits16(a1 + wb[pt], T()));
+                                }
                             }
                     } else {
                         // one thread per pixel: batches of three points -- first their four word addresses and
@@ -460,16 +512,22 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                         // a box starts on a 16-byte boundary of the row: the group's run begins 0..3 words / 0..7 elements in
                         tma_load_4d(st + kStOff, &tmap_off, bar, (row.g * kP * 4 & ~15) >> 1, j * 8, row.i * 8, row.n);
                         tma_load_4d(st + kStMsk, &tmap_msk, bar, (row.g * kP * 2 & ~15) >> 1, j * 8, row.i * 8, row.n);
+                        if (kAmn) {
+                            tma_load_4d(st + kStGout, &tmap_gout, bar, row.g * kCh, j * 8, row.i * 8, row.n);
+                            tma_load_4d(st + kStGout + 1024, &tmap_gout, bar, row.g * kCh + 8, j * 8, row.i * 8, row.n);
+                        }
                     }
                     // patch p - kSlots is through its products: its tile is zeroed for patch p and its grad_out replaced
                     if (p >= (unsigned)kSlots) mbar_wait_sleep(&a_done[slot], (p / kSlots - 1u) & 1u, (pp.diag & 64) ? 0 : 32, 4, p);
                     if (dbg) g_vres_dbg[p][4] = clock64();
                     uint64_t *bar = &a_ready[slot];
-                    mbar_expect_tx(bar, kATileBytes + kGoutBytes);
+                    mbar_expect_tx(bar, kATileBytes + (kAmn ? 0 : kGoutBytes));
                     bulk_fill(slot0 + slot * kATileBytes, g_zero_tile, kATileBytes, bar);
-                    unsigned char *gs = base + kSlots * kATileBytes + slot * kGoutBytes;
-                    tma_load_4d(gs, &tmap_gout, bar, row.g * kCh, j * 8, row.i * 8, row.n);
-                    tma_load_4d(gs + 1024, &tmap_gout, bar, row.g * kCh + 8, j * 8, row.i * 8, row.n);
+                    if (!kAmn) {
+                        unsigned char *gs = base + kSlots * kATileBytes + slot * kGoutBytes;
+                        tma_load_4d(gs, &tmap_gout, bar, row.g * kCh, j * 8, row.i * 8, row.n);
+                        tma_load_4d(gs + 1024, &tmap_gout, bar, row.g * kCh + 8, j * 8, row.i * 8, row.n);
+                    }
                 }
             }
         }
@@ -477,9 +535,9 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
         // ================================================================== products (the whole warp walks the list;
         // one elected lane issues)
         {
-            const uint32_t idesc = umma_idesc(std::is_same<T, __nv_bfloat16>::value ? 1 : 0, 64, kCh);
+            const uint32_t idesc = umma_idesc(std::is_same<T, __nv_bfloat16>::value ? 1 : 0, 64, kCh) | (kAmn ? 1u << 15 : 0u);
             // descriptors of slot 0 / block 0 / K step 0; the others differ in the 14-bit address field only
-            const uint64_t adesc0 = umma_desc_k_sw128(slot0), bdesc0 = umma_desc_mn_plain(gout0, 128, 1024);
+            const uint64_t adesc0 = kAmn ? umma_desc_mn_plain(slot0, 128, 1024) : umma_desc_k_sw128(slot0), bdesc0 = umma_desc_mn_plain(gout0, 128, 1024);
             Sched sch(lo, hi, pp.PR, q.N);
             Row row;
             unsigned p = 0;
@@ -519,7 +577,7 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
 #pragma unroll
                             for (int sub = 0; sub < 4; ++sub)
                                 if (own[sub])
-                                    tc_mma(dd[sub], ad + (uint64_t)((sub * kSubBytes + ks * 32) >> 4), bd + (uint64_t)((ks * 256) >> 4), idesc,
+                                    tc_mma(dd[sub], ad + (uint64_t)((sub * kSubBytes + ks * (kAmn ? 256 : 32)) >> 4), bd + (uint64_t)((ks * 256) >> 4), idesc,
                                            (uint32_t)(ks > 0 || !first[sub]));
                         tc_commit(&a_done[slot]);
                         if (j == pp.S - 1) {
