@@ -368,7 +368,7 @@ def _kernel_split(prof):
     return fam, {k: sorted(v)[:8] for k, v in names.items()}
 
 
-def train_row(args, rank, world, local_rank, dev, amp_dtype=torch.float16):
+def train_row(args, rank, world, local_rank, dev, amp_dtype=torch.float16, graph=False, weak=False):
     """BASELINE configs[3]: the YOLOv5l-DCNv3 training step on synthetic VisDrone-shaped 640 x 640 batches, GLOBAL batch
     128 split over the ranks (strong scaling: 128 / 64 / 32 / 16 images per GPU at 1 / 2 / 4 / 8), bf16 autocast,
     DistributedDataParallel over NCCL with one gradient all-reduce per optimizer step, SGD + fused EMA.  Every rank
@@ -379,13 +379,16 @@ def train_row(args, rank, world, local_rank, dev, amp_dtype=torch.float16):
     if gb % world:
         return None
     per = gb // world
+    if weak:                       # the same per-GPU batch at every N: global batch 128 x N
+        per, gb = gb, gb * world
     torch.manual_seed(0)
     torch.backends.cudnn.benchmark = True
     model = YOLOv5lDCNv3(nc=10).to(dev).to(memory_format=torch.channels_last)
     n_params = sum(p.numel() for p in model.parameters())
     ema = FusedModelEMA(model) if rank == 0 else None
-    ddp = wrap_ddp(model, local_rank)
-    ts = TrainStep(ddp, nc=10, optimizer=make_optimizer(model), ema=ema, autocast_dtype=amp_dtype)
+    side = torch.cuda.Stream(dev) if graph else None
+    ddp = wrap_ddp(model, local_rank, stream=side)
+    ts = TrainStep(ddp, nc=10, optimizer=make_optimizer(model), ema=ema, autocast_dtype=amp_dtype, graph=graph, graph_stream=side)
     # the reference's loader hands uint8 images on the host; the step copies them (train.py:249-250)
     imgs, targets = synthetic_batch(per, 640, device="cpu", seed=rank)
     host_u8 = (imgs * 255).to(torch.uint8).pin_memory()
@@ -402,7 +405,9 @@ def train_row(args, rank, world, local_rank, dev, amp_dtype=torch.float16):
         torch.cuda.synchronize()
 
     steps = int(os.environ.get("BENCH_TRAIN_STEPS", 6))
-    for _ in range(3):
+    # graph mode: `graph_after` eager steps (11 under DDP), the capturing step, one replay -- all before the timed region
+    n_warm = ts.graph_after + 2 if graph else 3
+    for _ in range(n_warm):
         one()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -430,7 +435,7 @@ def train_row(args, rank, world, local_rank, dev, amp_dtype=torch.float16):
         split = {"error": str(exc)[:200]}
     barrier()
     infer = None
-    if world == 1:
+    if world == 1 and not graph and not weak:
         m = ema.ema
         x = torch.rand(32, 3, 640, 640, device=dev).to(memory_format=torch.channels_last)
         with torch.no_grad(), torch.autocast("cuda", dtype=amp_dtype):
@@ -445,6 +450,7 @@ def train_row(args, rank, world, local_rank, dev, amp_dtype=torch.float16):
         infer = {"img_per_s": 32 * 10 / (a.elapsed_time(b) * 1e-3), "batch": 32, "ms_per_batch": a.elapsed_time(b) / 10,
                  "config": f"BASELINE configs[2]: YOLOv5l-DCNv3 inference, synthetic 640x640 batch 32, {str(amp_dtype)[6:]} autocast, EMA weights"}
     mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    graph_state = {"requested": bool(graph), "captured": ts._g is not None, "error": ts.graph_error, "eager_steps_before_capture": ts.graph_after}
     del ts, ddp, model, ema
     torch.cuda.empty_cache()
     if rank != 0:
@@ -455,7 +461,8 @@ def train_row(args, rank, world, local_rank, dev, amp_dtype=torch.float16):
         limiter = max(split, key=lambda k: split[k]["share"])
     return {
         "img_per_s": gb / (ms * 1e-3), "ms_per_step": ms, "global_batch": gb, "per_gpu_batch": per, "n_gpus": world,
-        "scaling": "strong", "steps": steps, "warmup": 3, "loss_last": loss_val, "peak_mem_gib": mem,
+        "scaling": "weak" if weak else "strong", "steps": steps, "warmup": n_warm, "loss_last": loss_val, "peak_mem_gib": mem,
+        "cuda_graph": graph_state,
         "model": "YOLOv5l-DCNv3 (stock YOLOv5l layout, the four head C3 stages are C3_DCNv3: 12 DCNv3 layers)",
         "params": n_params, "layers": layers(),
         "amp_dtype": str(amp_dtype)[6:],
@@ -465,7 +472,7 @@ def train_row(args, rank, world, local_rank, dev, amp_dtype=torch.float16):
         "ddp": {"backend": "nccl" if world > 1 else None, "gradient_as_bucket_view": True, "static_graph": True,
                 "broadcast_buffers": False, "bucket_cap_mb": 64, "allreduce_bytes_per_step": grad_bytes if world > 1 else 0},
         "gpu_time_split_rank0": split, "kernels_seen": kernels, "limiter": limiter, "inference": infer,
-        "config": "BASELINE configs[3]: YOLO-SOMI training step, synthetic VisDrone-shaped 640x640, global batch 128",
+        "config": "BASELINE configs[3]: YOLO-SOMI training step, synthetic VisDrone-shaped 640x640, global batch %d" % gb,
     }
 
 
@@ -626,67 +633,116 @@ def run_ours(args, rank, world, local_rank):
     # ---- BASELINE configs[2] / [3]: the model-level step, every rank takes part (NCCL gradient all-reduce)
     del sets, host_in, host_out
     torch.cuda.empty_cache()
-    train = None if args.no_train else train_row(args, rank, world, local_rank, dev)
+    train_on = not args.no_train and int(os.environ.get("BENCH_TRAIN_BATCH", 128)) % world == 0
+    train = train_row(args, rank, world, local_rank, dev) if train_on else None
     if train is not None and world == 1 and os.environ.get("BENCH_TRAIN_BF16", "1") != "0":
         # the same step in bf16: PyTorch 2.11 has no cuDNN BatchNorm for bf16 (native kernel: 2.9x slower,
         # scripts/bn_probe.py), which is why the headline row uses the reference's own AMP dtype
         alt = train_row(args, rank, world, local_rank, dev, amp_dtype=torch.bfloat16)
         train["bf16_autocast"] = {k: alt[k] for k in ("img_per_s", "ms_per_step", "limiter", "gpu_time_split_rank0")}
 
+    # ---- the same step as ONE captured CUDA graph (TrainStep(graph=True)), and at N > 1 the weak-scaling row (128 images
+    # per GPU).  Both run last and under a watchdog: a capture that hangs (NCCL inside a capture) must not cost the line.
+    extra_on = train_on and os.environ.get("BENCH_TRAIN_GRAPH", "1") != "0"
+
+    def finish(graph_row, weak_row):
+        if graph_row is not None and train is not None:
+            keep = ("img_per_s", "ms_per_step", "cuda_graph", "peak_mem_gib", "loss_last", "gpu_time_split_rank0", "limiter")
+            train["whole_step_cuda_graph"] = {k: graph_row.get(k) for k in keep} if "error" not in graph_row else graph_row
+            train["eager"] = {"img_per_s": train["img_per_s"], "ms_per_step": train["ms_per_step"]}
+            st = graph_row.get("cuda_graph") or {}
+            if st.get("captured") and not st.get("error") and graph_row["img_per_s"] > train["img_per_s"]:
+                train["img_per_s"], train["ms_per_step"] = graph_row["img_per_s"], graph_row["ms_per_step"]
+                train["mode"] = "whole step replayed as one CUDA graph (TrainStep(graph=True)); the eager step beside it"
+            else:
+                train["mode"] = "eager"
+        if weak_row is not None and train is not None:
+            train["weak_scaling_128_per_gpu"] = {k: weak_row.get(k) for k in ("img_per_s", "ms_per_step", "global_batch", "per_gpu_batch", "limiter")} \
+                if "error" not in weak_row else weak_row
+        pts = points_per_step()
+        value = world * pts * args.steps / (ms * 1e-3)
+        ab = algorithmic_bytes()
+        peak, peak_src = peaks()
+        traffic, traffic_src = measured_traffic()
+        bwd_t = statistics.mean(bwd_ms) * 1e-3
+        fwd_t = statistics.mean(fwd_ms) * 1e-3
+        ach = ab["bwd"] / bwd_t / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "per_gpu_batch": n, "points_per_step_per_gpu": pts,
+                       "l2": f"{ROTATE} rotating input sets (each step's operands ~390 MB > 126 MB L2)",
+                       "arithmetic": "fp32 accumulate, bf16 I/O, sampling coefficients rounded to bf16 (defaults)"},
+            "clocks": clocks,
+            "e2e": {"value": world * pts * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / e2e_steps,
+                    "api": "dcnv3_host_pipeline_run (C ABI, pinned host buffers, 8-image chunks, H2D | kernels | D2H on three streams)",
+                    "timing": "host clock around enqueue + drain of all steps (the pipeline owns its streams)",
+                    "bare_copy_ms_per_step": bare_ms / e2e_steps,
+                    "bare_copy": "the same H2D + D2H bytes as plain cudaMemcpyAsync per tensor on two streams, no kernels, all ranks at once",
+                    "pcie_gbs_each_way_per_gpu_bare": h2d / (bare_ms / e2e_steps * 1e-3) / 1e9,
+                    "host_link_gbs_aggregate_bare": world * (h2d + d2h) / (bare_ms / e2e_steps * 1e-3) / 1e9,
+                    "pipeline_over_bare_copy": (e2e_ms / e2e_steps) / (bare_ms / e2e_steps),
+                    "cpu_cores_bound": cpu_bind},
+            "gpu_launches": 4 * args.steps,   # fwd_gs, bwd_dots, bwd_vmma, narrow_f32 (the memset is the driver's)
+            "roofline": {"bound": "hbm", "kernel": "backward pass: bdots::bwd_dots (channel sums) + vres::bwd_vres (grad_value, tcgen05 with the accumulator resident in TMEM, written once) + vres::far_points (+ two conditional fall-back launches that exit at once), chained by programmatic dependent launch",
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "algorithmic_bytes": ab["bwd"], "avg_ms": bwd_t * 1e3},
+            "passes": {"fwd_ms": fwd_t * 1e3, "bwd_ms": bwd_t * 1e3,
+                       "fwd_gbs": ab["fwd"] / fwd_t / 1e9, "fwd_frac": ab["fwd"] / fwd_t / 1e9 / peak,
+                       "step_gbs": (ab["fwd"] + ab["bwd"]) / (ms / args.steps * 1e-3) / 1e9,
+                       "step_frac": (ab["fwd"] + ab["bwd"]) / (ms / args.steps * 1e-3) / 1e9 / peak},
+        }
+        if proj is not None:
+            line["next_rows"] = {"offset_mask_proj": proj, "layer": layer}
+        if modes is not None:
+            line["precision_modes"] = modes
+        if train is not None:
+            line["train_step"] = train
+            line["img_per_s"] = train["img_per_s"]
+        if world == 1 and not args.no_cpu:
+            # the CPU reference beside the GPU number, same run, same box: the full workload (all 16 images), 5 passes
+            times, threads, kind, desc = cpu_reference_run(CFG["N"], 5)
+            line["cpu_baseline"] = {
+                "value": points_per_step() / min(times), "unit": UNIT, "cores": threads, "kind": kind,
+                "sample": f"all {CFG['N']} images (the full workload), fp32 on bf16-rounded inputs, best of 5 after 1 warm-up "
+                          f"({sum(times):.1f} s of CPU work), {desc}"}
+        print(json.dumps(line))
+
+    graph_row = weak_row = None
+    if extra_on:
+        import threading
+        limit = int(os.environ.get("BENCH_TRAIN_GRAPH_TIMEOUT", 300))
+        done = threading.Event()
+
+        def bail():
+            if done.is_set():
+                return
+            if rank == 0:
+                msg = {"error": "did not finish within %d s (watchdog); the eager rows stand" % limit}
+                finish(msg if graph_row is None else graph_row, msg)
+                sys.stdout.flush()
+            os._exit(0)
+        timer = threading.Timer(limit, bail)
+        timer.daemon = True
+        timer.start()
+        try:
+            graph_row = train_row(args, rank, world, local_rank, dev, graph=True)
+        except Exception as exc:
+            graph_row = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
+        if world > 1 and os.environ.get("BENCH_TRAIN_WEAK", "1") != "0":
+            try:
+                weak_row = train_row(args, rank, world, local_rank, dev, weak=True)
+            except Exception as exc:
+                weak_row = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
+        done.set()
+        timer.cancel()
     if rank != 0:
         return
-    pts = points_per_step()
-    value = world * pts * args.steps / (ms * 1e-3)
-    ab = algorithmic_bytes()
-    peak, peak_src = peaks()
-    traffic, traffic_src = measured_traffic()
-    bwd_t = statistics.mean(bwd_ms) * 1e-3
-    fwd_t = statistics.mean(fwd_ms) * 1e-3
-    ach = ab["bwd"] / bwd_t / 1e9
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "per_gpu_batch": n, "points_per_step_per_gpu": pts,
-                   "l2": f"{ROTATE} rotating input sets (each step's operands ~390 MB > 126 MB L2)",
-                   "arithmetic": "fp32 accumulate, bf16 I/O, sampling coefficients rounded to bf16 (defaults)"},
-        "clocks": clocks,
-        "e2e": {"value": world * pts * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / e2e_steps,
-                "api": "dcnv3_host_pipeline_run (C ABI, pinned host buffers, 8-image chunks, H2D | kernels | D2H on three streams)",
-                "timing": "host clock around enqueue + drain of all steps (the pipeline owns its streams)",
-                "bare_copy_ms_per_step": bare_ms / e2e_steps,
-                "bare_copy": "the same H2D + D2H bytes as plain cudaMemcpyAsync per tensor on two streams, no kernels, all ranks at once",
-                "pcie_gbs_each_way_per_gpu_bare": h2d / (bare_ms / e2e_steps * 1e-3) / 1e9,
-                "host_link_gbs_aggregate_bare": world * (h2d + d2h) / (bare_ms / e2e_steps * 1e-3) / 1e9,
-                "pipeline_over_bare_copy": (e2e_ms / e2e_steps) / (bare_ms / e2e_steps),
-                "cpu_cores_bound": cpu_bind},
-        "gpu_launches": 4 * args.steps,   # fwd_gs, bwd_dots, bwd_vmma, narrow_f32 (the memset is the driver's)
-        "roofline": {"bound": "hbm", "kernel": "backward pass: bdots::bwd_dots (channel sums) + vres::bwd_vres (grad_value, tcgen05 with the accumulator resident in TMEM, written once) + vres::far_points (+ two conditional fall-back launches that exit at once), chained by programmatic dependent launch",
-                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                     "algorithmic_bytes": ab["bwd"], "avg_ms": bwd_t * 1e3},
-        "passes": {"fwd_ms": fwd_t * 1e3, "bwd_ms": bwd_t * 1e3,
-                   "fwd_gbs": ab["fwd"] / fwd_t / 1e9, "fwd_frac": ab["fwd"] / fwd_t / 1e9 / peak,
-                   "step_gbs": (ab["fwd"] + ab["bwd"]) / (ms / args.steps * 1e-3) / 1e9,
-                   "step_frac": (ab["fwd"] + ab["bwd"]) / (ms / args.steps * 1e-3) / 1e9 / peak},
-    }
-    if proj is not None:
-        line["next_rows"] = {"offset_mask_proj": proj, "layer": layer}
-    if modes is not None:
-        line["precision_modes"] = modes
-    if train is not None:
-        line["train_step"] = train
-        line["img_per_s"] = train["img_per_s"]
-    if world == 1 and not args.no_cpu:
-        # the CPU reference beside the GPU number, same run, same box: the full workload (all 16 images), 5 passes
-        times, threads, kind, desc = cpu_reference_run(CFG["N"], 5)
-        line["cpu_baseline"] = {
-            "value": points_per_step() / min(times), "unit": UNIT, "cores": threads, "kind": kind,
-            "sample": f"all {CFG['N']} images (the full workload), fp32 on bf16-rounded inputs, best of 5 after 1 warm-up "
-                      f"({sum(times):.1f} s of CPU work), {desc}"}
-    print(json.dumps(line))
+    finish(graph_row, weak_row)
 
 
 def main():

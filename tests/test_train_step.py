@@ -228,3 +228,38 @@ def test_training_step_runs_on_gpu():
     step, mean_loss = ts.loss_for_log()
     assert step == 2 and mean_loss == mean_loss
     assert ema.updates == 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("amp", [torch.bfloat16, torch.float16])
+def test_whole_step_cuda_graph_follows_the_eager_step(amp):
+    """TrainStep(graph=True): three eager steps, a captured step, replays -- losses, parameters and the EMA follow an
+    eager TrainStep fed the same batches (atomics in the samplers' backward: close, not bit-equal)."""
+    from yolo_somi_b200.train_step import FusedModelEMA, TrainStep, make_optimizer, synthetic_batch
+    from yolo_somi_b200.yolov5l_dcnv3 import YOLOv5lDCNv3
+    runs = {}
+    batches = [synthetic_batch(2, 256, device="cuda", seed=s) for s in range(7)]
+    for mode in ("eager", "graph"):
+        torch.manual_seed(0)
+        model = YOLOv5lDCNv3(nc=10).cuda().to(memory_format=torch.channels_last)
+        ema = FusedModelEMA(model)
+        ts = TrainStep(model, nc=10, optimizer=make_optimizer(model, lr=0.01), ema=ema, autocast_dtype=amp, log_every=7,
+                       graph=(mode == "graph"))
+        losses = []
+        for imgs, targets in batches:
+            losses.append(float(ts.step(imgs.to(memory_format=torch.channels_last), targets)))
+        torch.cuda.synchronize()
+        if mode == "graph":
+            assert ts.graph_error is None and ts._g is not None, ts.graph_error
+        assert ema.updates == 7 and ts.loss_for_log()[0] == 7
+        runs[mode] = (losses, [p.detach().float().clone() for p in model.parameters()],
+                      [p.detach().float().clone() for p in ema.ema.parameters()], ts.loss_for_log()[1])
+    le, pe, ee, me = runs["eager"]
+    lg, pg, eg, mg = runs["graph"]
+    assert all(l == l for l in lg)
+    assert max(abs(a - b) for a, b in zip(le, lg)) < 0.05 * max(abs(a) for a in le), (le, lg)
+    assert abs(me - mg) < 0.05 * abs(me)
+    for a, b in zip(pe, pg):
+        assert (a - b).norm() <= 0.05 * a.norm() + 1e-3
+    for a, b in zip(ee, eg):
+        assert (a - b).norm() <= 0.05 * a.norm() + 1e-3

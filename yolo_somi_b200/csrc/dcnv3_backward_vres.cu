@@ -93,6 +93,13 @@ constexpr int kGroups = VRES_GROUPS;               // builder groups (64 kTpp th
 // second word under a divergent branch, the grad_out copy) at 66 % issue utilisation.  The builders are bound by their
 // instruction stream and its latencies, not by shared-memory bandwidth; the K-major tile stays the default.
 constexpr bool kAmn = VRES_AMN;
+// -DVRES_PIPE=1: the builders' read-modify-writes software-pipelined (the loads of point pt + 1 issued before the stores
+// of point pt unless the two share a cell).  MEASURED, parity-green: backward 274.9 us against 250.8 us -- the address
+// comparisons and the extra live registers cost more than the shortened chains save; off by default.
+#ifndef VRES_PIPE
+#define VRES_PIPE 0
+#endif
+constexpr bool kPipe = VRES_PIPE;
 static_assert(!kAmn || VRES_TPP == 2, "the MN-major tile is implemented for two threads per pixel");
 constexpr int kOmStages = kAmn ? 3 : 4;            // staged inputs in rotation: free again after the group's decode
 constexpr int kGroupWarps = 2 * kTpp;
@@ -373,6 +380,28 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                             wa[pt] = vm * (1.f - lw);
                             wb[pt] = vm * lw;
                         }
+                        if constexpr (!kAmn && kPipe) {
+                            // The read-modify-writes, software-pipelined: the loads of point pt + 1 are issued BEFORE the stores
+                            // of point pt unless the two points share a cell (then they wait for the stores) -- a column's
+                            // nine read-modify-write pairs are otherwise one serial chain of shared-memory round trips.
+                            uint32_t la = 0, lb = 0;
+                            if (ea[0]) { la = lds16(ea[0]); lb = lds16(eb[0]); }
+#pragma unroll
+                            for (int pt = 0; pt < kP; ++pt) {
+                                uint32_t na = 0, nb = 0;
+                                bool late = false;
+                                if (pt + 1 < kP && ea[pt + 1]) {
+                                    late = ea[pt] && (ea[pt + 1] == ea[pt] || ea[pt + 1] == eb[pt] || eb[pt + 1] == ea[pt] || eb[pt + 1] == eb[pt]);
+                                    if (!late) { na = lds16(ea[pt + 1]); nb = lds16(eb[pt + 1]); }
+                                }
+                                if (ea[pt]) {
+                                    sts16(ea[pt], bits16(f32_of((uint16_t)la, T()) + wa[pt], T()));
+                                    sts16(eb[pt], bits16(f32_of((uint16_t)lb, T()) + wb[pt], T()));
+                                }
+                                if (late) { na = lds16(ea[pt + 1]); nb = lds16(eb[pt + 1]); }
+                                la = na; lb = nb;
+                            }
+                        } else {
 #pragma unroll
                         for (int pt = 0; pt < kP; ++pt)
                             if (ea[pt]) {
@@ -393,6 +422,7 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                                     sts16(eb[pt], bits16(a1 + wb[pt], T()));
                                 }
                             }
+                        }
                     } else {
                         // one thread per pixel: batches of three points -- first their four word addresses and
                         // coefficients (independent chains), then the read-modify-writes in order

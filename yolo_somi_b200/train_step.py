@@ -54,6 +54,7 @@ class FusedModelEMA:
     def __init__(self, model: nn.Module, decay: float = 0.9999, updates: int = 0):
         self.ema = deepcopy(_de_parallel(model)).eval()
         self.updates = updates
+        self.decay_base, self.decay_tau = decay, 2000.0
         self.decay = lambda x: decay * (1 - math.exp(-x / 2000))
         for p in self.ema.parameters():
             p.requires_grad_(False)
@@ -75,11 +76,21 @@ class FusedModelEMA:
     def _fingerprint(*mods: nn.Module) -> list:
         return [t.data_ptr() for mod in mods for t in itertools.chain(mod.parameters(), mod.buffers())]
 
-    def update(self, model: nn.Module) -> None:
+    def update(self, model: nn.Module, device_count: torch.Tensor | None = None) -> None:
+        """One EMA update.  ``device_count`` (a 0-dim float64 CUDA tensor holding the number of updates so far) moves
+        the decay schedule onto the device: the counter is incremented and ``d`` computed there (fp64, rounded to the
+        tensors' fp32 exactly where the host form rounds), so the update can live inside a captured CUDA graph whose
+        replays must not bake in one step's decay.  The host counter ``updates`` is the caller's to advance then."""
         model = _de_parallel(model)
         with torch.no_grad():
-            self.updates += 1
-            d = self.decay(self.updates)
+            if device_count is None:
+                self.updates += 1
+                d = self.decay(self.updates)
+                rest = 1 - d
+            else:
+                device_count += 1
+                d64 = self.decay_base * (1 - torch.exp(-device_count / self.decay_tau))
+                d, rest = d64.float(), (1 - d64).float()
             # the tensor lists are rebuilt only when a tensor of either model moved (.to(), new parameters, ...)
             ptrs = self._fingerprint(model, self.ema)
             bound = getattr(self, "_bound", None)
@@ -87,7 +98,7 @@ class FusedModelEMA:
                 self._bind(model, ptrs)
             for es, ss in self._groups:
                 torch._foreach_mul_(es, d)                       # v *= d
-                scaled = torch._foreach_mul(ss, 1 - d)           # (1 - d) * m   (in m's dtype, as the reference)
+                scaled = torch._foreach_mul(ss, rest)            # (1 - d) * m   (in m's dtype, as the reference)
                 torch._foreach_add_(es, scaled)                  # v += ...
 
     def update_attr(self, model: nn.Module, include: Sequence[str] = (),
@@ -197,7 +208,7 @@ def setup_process_group(backend: str | None = None) -> tuple[int, int, int]:
     return rank, local_rank, world
 
 
-def wrap_ddp(model: nn.Module, local_rank: int | None = None, sync_bn: bool = False) -> nn.Module:
+def wrap_ddp(model: nn.Module, local_rank: int | None = None, sync_bn: bool = False, stream=None) -> nn.Module:
     """train.py:165-208: optional SyncBatchNorm conversion, then DistributedDataParallel -- with the settings above.
     Returns the model unchanged when there is one rank.  (static_graph: the FIRST backward must be a synchronised one --
     DDP records the graph there -- so accumulation starts with a closing micro-step, as the reference's warm-up does.)"""
@@ -207,8 +218,18 @@ def wrap_ddp(model: nn.Module, local_rank: int | None = None, sync_bn: bool = Fa
     if sync_bn and on_gpu:
         model = nn.SyncBatchNorm.convert_sync_batchnorm(model)
     kw = dict(device_ids=[local_rank], output_device=local_rank) if on_gpu else {}
-    return nn.parallel.DistributedDataParallel(model, gradient_as_bucket_view=True, static_graph=True,
-                                               broadcast_buffers=False, bucket_cap_mb=64, **kw)
+    # `stream`: a step that will be captured whole (TrainStep(graph=True, graph_stream=stream)) needs DDP constructed on
+    # the side stream the capture will run on (PyTorch's CUDA-graphs note on DistributedDataParallel)
+    ctx = contextlib.nullcontext()
+    if stream is not None and on_gpu:
+        stream.wait_stream(torch.cuda.current_stream())
+        ctx = torch.cuda.stream(stream)
+    with ctx:
+        ddp = nn.parallel.DistributedDataParallel(model, gradient_as_bucket_view=True, static_graph=True,
+                                                  broadcast_buffers=False, bucket_cap_mb=64, **kw)
+    if stream is not None and on_gpu:
+        torch.cuda.current_stream().wait_stream(stream)
+    return ddp
 
 
 def make_optimizer(model: nn.Module, lr: float = 0.01, momentum: float = 0.937, weight_decay: float = 5e-4):
@@ -242,7 +263,7 @@ def yolo_surrogate_loss(preds, targets, nc: int):
         gx = (targets[:, 2] * w).long().clamp_(0, w - 1)
         gy = (targets[:, 3] * h).long().clamp_(0, h - 1)
         obj = torch.zeros(b, na, h, w, device=p.device)
-        obj[img, :, gy, gx] = 1.0
+        obj[img, :, gy, gx] = obj.new_ones(())           # a device scalar: no host -> device copy inside the step
         total = total + nn.functional.binary_cross_entropy_with_logits(p[..., 4], obj)
         sel = p[img, :, gy, gx]                                         # [T, na, no]
         want_cls = nn.functional.one_hot(cls, nc).float()[:, None].expand(-1, na, -1)
@@ -255,25 +276,42 @@ class TrainStep:
     """One optimizer step of the reference's loop (train.py:249-283) without its per-iteration host synchronisations.
 
     step(imgs, targets, last_micro=True): autocast forward, loss, backward (under no_sync() unless `last_micro`), and on
-    the last micro-step optimizer step + zero_grad + EMA.  The running mean loss lives on the device; `loss_for_log()`
-    returns the value recorded at the last `log_every` boundary (read through a pinned buffer guarded by an event)."""
+    the last micro-step optimizer step + zero_grad + EMA.  The running loss sum lives on the device; `loss_for_log()`
+    returns the mean recorded at the last `log_every` boundary (read through a pinned buffer guarded by an event).
+
+    graph=True: the WHOLE step -- forward, loss, backward with DDP's bucketed all-reduce, unscale, clip, fused SGD,
+    EMA, loss sum -- is captured into one CUDA graph after `graph_after` eager steps (each a real step on its own
+    batch, run on the capture stream so that everything created lazily exists: cuDNN plans, tensor maps, DDP's
+    rebuilt buckets and its first ten iterations of runtime statistics) and replayed from static input buffers.
+    At 16 images per GPU (global batch 128 on eight GPUs) the eager step is bound by the host's enqueue time of
+    ~3000 kernels, not by the GPU (profiles/README.md); a replay is one launch.  Whole steps only (no accumulation),
+    static shapes; the EMA's decay schedule runs on the device (`FusedModelEMA.update(device_count=...)`).  A learning
+    rate schedule must write into a tensor lr (`make_optimizer(..., lr=torch.tensor(...))`): a float is baked in."""
 
     def __init__(self, model: nn.Module, nc: int, optimizer=None, ema: FusedModelEMA | None = None,
-                 autocast_dtype: torch.dtype | None = torch.bfloat16, log_every: int = 50, max_norm: float = 10.0):
+                 autocast_dtype: torch.dtype | None = torch.bfloat16, log_every: int = 50, max_norm: float = 10.0,
+                 graph: bool = False, graph_after: int | None = None, graph_stream=None):
         self.model, self.nc = model, nc
         self.optimizer = optimizer or make_optimizer(model)
         self.ema, self.dtype, self.log_every, self.max_norm = ema, autocast_dtype, log_every, max_norm
         dev = next(model.parameters()).device
         self.device = dev
-        self._mloss = torch.zeros((), device=dev)
+        self._lsum = torch.zeros((), device=dev)
         self._steps = 0
         self._host = torch.zeros((), pin_memory=True) if dev.type == "cuda" else torch.zeros(())
         self._event = torch.cuda.Event() if dev.type == "cuda" else None
         self._logged = None
         # fp16 autocast (the reference's AMP dtype, train.py:263) needs the reference's GradScaler (train.py:217,268-274)
         self.scaler = torch.amp.GradScaler(dev.type) if (autocast_dtype == torch.float16 and dev.type == "cuda") else None
+        self.graph = bool(graph) and dev.type == "cuda"
+        ddp = isinstance(model, nn.parallel.DistributedDataParallel)
+        self.graph_after = (11 if ddp else 3) if graph_after is None else graph_after
+        self._g = self._static = self._ema_count = None
+        self._stream = graph_stream
+        self.graph_error = None
 
-    def step(self, imgs: torch.Tensor, targets: torch.Tensor, last_micro: bool = True) -> torch.Tensor:
+    # -- the step's device work: everything between the inputs and the loss sum -------------------------------------
+    def _work(self, imgs: torch.Tensor, targets: torch.Tensor, last_micro: bool, ema_count=None) -> torch.Tensor:
         ddp = isinstance(self.model, nn.parallel.DistributedDataParallel)
         sync_ctx = self.model.no_sync() if (ddp and not last_micro) else contextlib.nullcontext()
         amp = torch.autocast(self.device.type, dtype=self.dtype) if self.dtype is not None else contextlib.nullcontext()
@@ -296,15 +334,73 @@ class TrainStep:
                 self.optimizer.step()
             self.optimizer.zero_grad(set_to_none=True)
             if self.ema is not None:
-                self.ema.update(self.model)
-            self._steps += 1
-            self._mloss.mul_(1.0 - 1.0 / self._steps).add_(loss.detach() / self._steps)
-            if self._steps % self.log_every == 0:
-                self._host.copy_(self._mloss, non_blocking=True)
-                if self._event is not None:
-                    self._event.record()
-                self._logged = self._steps
+                self.ema.update(self.model, device_count=ema_count)
+            self._lsum += loss.detach()
         return loss.detach()
+
+    def _after(self) -> None:
+        self._steps += 1
+        if self._steps % self.log_every == 0:
+            self._host.copy_(self._lsum, non_blocking=True)
+            if self._event is not None:
+                self._event.record()
+            self._logged = self._steps
+
+    def step(self, imgs: torch.Tensor, targets: torch.Tensor, last_micro: bool = True) -> torch.Tensor:
+        if self.graph and self.graph_error is None:
+            if not last_micro:
+                raise ValueError("TrainStep(graph=True) captures whole optimizer steps; accumulate with graph=False")
+            return self._graph_step(imgs, targets)
+        loss = self._work(imgs, targets, last_micro)
+        if last_micro:
+            self._after()
+        return loss
+
+    # -- graph mode -------------------------------------------------------------------------------------------------
+    def _graph_step(self, imgs: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+        cur = torch.cuda.current_stream(self.device)
+        if self._static is None:
+            if self._stream is None:
+                self._stream = torch.cuda.Stream(self.device)
+            self._static = (torch.empty_like(imgs), torch.empty_like(targets))       # preserves channels_last strides
+            self._loss_out = torch.zeros((), device=self.device)
+            if self.ema is not None:
+                self._ema_count = torch.full((), float(self.ema.updates), dtype=torch.float64, device=self.device)
+        sx, st = self._static
+        if sx.shape != imgs.shape or st.shape != targets.shape:
+            raise ValueError("TrainStep(graph=True): static shapes only (drop the last, ragged batch)")
+        # the copies into the static buffers run on the caller's stream; the step's stream waits for them
+        sx.copy_(imgs, non_blocking=True)
+        st.copy_(targets, non_blocking=True)
+        self._stream.wait_stream(cur)
+        with torch.cuda.stream(self._stream):
+            if self._g is None and self._steps >= self.graph_after:
+                try:
+                    self._capture()
+                except Exception as exc:                  # stay correct: fall back to eager steps, say why
+                    self.graph_error = "%s: %s" % (type(exc).__name__, str(exc)[:300])
+                    self._g = None
+            if self._g is not None:
+                self._g.replay()
+                if self.ema is not None:
+                    self.ema.updates += 1
+            else:
+                # eager warm-up steps (real steps) -- and the fall-back if capture failed
+                self._loss_out.copy_(self._work(sx, st, True, ema_count=self._ema_count if self.graph_error is None else None))
+                if self.ema is not None and self.graph_error is None:
+                    self.ema.updates += 1
+            self._after()
+        cur.wait_stream(self._stream)
+        return self._loss_out
+
+    def _capture(self) -> None:
+        sx, st = self._static
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        self.optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(g, stream=self._stream):
+            self._loss_out.copy_(self._work(sx, st, True, ema_count=self._ema_count))
+        self._g = g
 
     def loss_for_log(self):
         """(step, mean loss) of the last logging boundary, or None; waits only for that boundary's copy."""
@@ -312,7 +408,7 @@ class TrainStep:
             return None
         if self._event is not None:
             self._event.synchronize()
-        return self._logged, float(self._host)
+        return self._logged, float(self._host) / self._logged
 
 
 def synthetic_batch(batch: int, size: int = 640, nc: int = 10, boxes_per_image: int = 64, device="cuda", seed: int = 0):
