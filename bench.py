@@ -686,7 +686,7 @@ def run_ours(args, rank, world, local_rank):
                     "host_link_gbs_aggregate_bare": world * (h2d + d2h) / (bare_ms / e2e_steps * 1e-3) / 1e9,
                     "pipeline_over_bare_copy": (e2e_ms / e2e_steps) / (bare_ms / e2e_steps),
                     "cpu_cores_bound": cpu_bind},
-            "gpu_launches": 4 * args.steps,   # fwd_gs, bwd_dots, bwd_vmma, narrow_f32 (the memset is the driver's)
+            "gpu_launches": 6 * args.steps,   # per step: fwd_gs | bwd_dots, bwd_vres, far_points + the two conditional fall-back launches (bwd_vmma, narrow_f32: they exit at once)
             "roofline": {"bound": "hbm", "kernel": "backward pass: bdots::bwd_dots (channel sums) + vres::bwd_vres (grad_value, tcgen05 with the accumulator resident in TMEM, written once) + vres::far_points (+ two conditional fall-back launches that exit at once), chained by programmatic dependent launch",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
