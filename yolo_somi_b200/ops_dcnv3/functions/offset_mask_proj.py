@@ -56,6 +56,18 @@ def _pack(lib, w_off, b_off, w_msk, b_msk, group, points, dtype):
     return w_cat, b_cat
 
 
+def column_sums(g2):
+    """Column sums of a tall 16-bit [M, n] matrix as a ones-row GEMM; fp32 out where cuBLAS offers it (a sum over
+    M = 102,400 loss-scaled fp16 gradients overflows a 16-bit result long before it overflows the accumulator)."""
+    ones = torch.ones(1, g2.shape[0], dtype=g2.dtype, device=g2.device)
+    if g2.is_cuda:
+        try:
+            return torch.mm(ones, g2, out_dtype=torch.float32).reshape(-1)
+        except (TypeError, RuntimeError):
+            pass
+    return (ones @ g2).reshape(-1)
+
+
 class OffsetMaskProj(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x1, w_off, b_off, w_msk, b_msk, group, dtype):
@@ -99,9 +111,8 @@ class OffsetMaskProj(torch.autograd.Function):
         gw_msk = (g_logit.t() @ x2).to(w_msk.dtype)
         # column sums of tall [M, n] matrices as a ones-row GEMM (fp32 accumulation inside cuBLAS):
         # at M = 102,400 PyTorch's dim-0 reduction kernel takes 100-300 us per tensor, the GEMV ~15 us
-        ones = torch.ones(1, m, dtype=x2.dtype, device=x2.device)
-        gb_off = (ones @ g_off).reshape(-1)
-        gb_msk = (ones @ g_logit).reshape(-1)
+        gb_off = column_sums(g_off)
+        gb_msk = column_sums(g_logit)
         return gx.reshape(*ctx.lead, -1).to(ctx.in_dtype), gw_off, gb_off.to(w_off.dtype), gw_msk, gb_msk.to(w_msk.dtype), None, None
 
 

@@ -70,30 +70,40 @@ def _is_power_of_2(n):
 class _TallLinear(torch.autograd.Function):
     """``F.linear`` for tall 16-bit activations [M, C] with M >> C: identical forward; the backward
     takes the bias gradient as a ones-row GEMM instead of autograd's dim-0 reduction kernel, which at
-    the layer's M = N*H*W = 102,400 costs 100-300 us per projection (profiles/README.md, r1_v4)."""
+    the layer's M = N*H*W = 102,400 costs 100-300 us per projection (profiles/README.md, r1_v4).
+
+    Under autocast (fp32 parameters, 16-bit activations: the training step's mode) the operands are cast
+    to the autocast dtype here, as autocast's own ``linear`` does, and the gradients go back in the
+    parameters' dtype -- ``nn.Linear`` under autocast would take autograd's reduction for the bias."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
-        ctx.save_for_backward(x, weight)
-        return F.linear(x, weight, bias)
+    def forward(ctx, x, weight, bias, dtype):
+        with torch.autocast(x.device.type, enabled=False):
+            x16, w16 = x.to(dtype), weight.to(dtype)
+            ctx.save_for_backward(x16, w16)
+            ctx.dtypes = (x.dtype, weight.dtype, bias.dtype)
+            return F.linear(x16, w16, bias.to(dtype))
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
-        g2, x2 = g.reshape(-1, g.shape[-1]), x.reshape(-1, x.shape[-1])
-        gx = (g2 @ weight).reshape(x.shape) if ctx.needs_input_grad[0] else None
-        gw = g2.t() @ x2 if ctx.needs_input_grad[1] else None
+        xd, wd, bd = ctx.dtypes
+        g2, x2 = g.reshape(-1, g.shape[-1]).to(x.dtype), x.reshape(-1, x.shape[-1])
+        gx = (g2 @ weight).reshape(x.shape).to(xd) if ctx.needs_input_grad[0] else None
+        gw = (g2.t() @ x2).to(wd) if ctx.needs_input_grad[1] else None
         gb = None
         if ctx.needs_input_grad[2]:
-            gb = (torch.ones(1, g2.shape[0], dtype=g2.dtype, device=g2.device) @ g2).reshape(-1)
-        return gx, gw, gb
+            gb = offset_mask_proj.column_sums(g2).to(bd)
+        return gx, gw, gb, None
 
 
 def _linear(x, lin):
-    if (x.is_cuda and x.dtype in (torch.float16, torch.bfloat16) and lin.bias is not None
-            and lin.weight.dtype == x.dtype and torch.is_grad_enabled() and x.numel() // x.shape[-1] >= 4096):
-        return _TallLinear.apply(x, lin.weight, lin.bias)
+    if x.is_cuda and lin.bias is not None and torch.is_grad_enabled() and x.numel() // x.shape[-1] >= 4096:
+        amp = torch.is_autocast_enabled("cuda")
+        dtype = torch.get_autocast_dtype("cuda") if amp else x.dtype
+        if dtype in (torch.float16, torch.bfloat16) and (amp or lin.weight.dtype == x.dtype):
+            return _TallLinear.apply(x, lin.weight, lin.bias, dtype)
     return lin(x)
 
 
