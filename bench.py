@@ -307,8 +307,8 @@ def layer_row(dev, dtype):
     xs = [torch.randn(CFG["N"], CFG["H"], CFG["W"], CFG["C"], device=dev, dtype=dtype, requires_grad=True) for _ in range(2)]
     go = torch.randn(CFG["N"], CFG["H"], CFG["W"], CFG["C"], device=dev, dtype=dtype)
 
-    def timed(n=10):
-        for i in range(3):
+    def timed(n=30):
+        for i in range(6):
             layer(xs[i % 2]).backward(go)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -449,6 +449,29 @@ def train_row(args, rank, world, local_rank, dev, amp_dtype=torch.float16, graph
             b.record(); torch.cuda.synchronize()
         infer = {"img_per_s": 32 * 10 / (a.elapsed_time(b) * 1e-3), "batch": 32, "ms_per_batch": a.elapsed_time(b) / 10,
                  "config": f"BASELINE configs[2]: YOLOv5l-DCNv3 inference, synthetic 640x640 batch 32, {str(amp_dtype)[6:]} autocast, EMA weights"}
+        # the deployment form: BatchNorms folded (the reference's fuse() before val / detect) and the forward replayed
+        # as one CUDA graph (hosting.fuse_for_inference, hosting.GraphedInference); the eager number stays beside it
+        try:
+            import copy
+            from yolo_somi_b200.hosting import GraphedInference, fuse_for_inference
+            fm = fuse_for_inference(copy.deepcopy(m))
+            gi = GraphedInference(fm, x, autocast_dtype=amp_dtype)
+            for _ in range(3):
+                gi(x)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(10):
+                gi(x)
+            b.record(); torch.cuda.synchronize()
+            infer["eager"] = {"img_per_s": infer["img_per_s"], "ms_per_batch": infer["ms_per_batch"]}
+            g_ips = 32 * 10 / (a.elapsed_time(b) * 1e-3)
+            infer["fused_bn_cuda_graph"] = {"img_per_s": g_ips, "ms_per_batch": a.elapsed_time(b) / 10}
+            if g_ips > infer["img_per_s"]:
+                infer["img_per_s"], infer["ms_per_batch"] = g_ips, a.elapsed_time(b) / 10
+                infer["mode"] = "BatchNorm folded into conv / output_proj, forward replayed as one CUDA graph"
+            del gi, fm
+        except Exception as exc:
+            infer["fused_bn_cuda_graph"] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
     mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
     graph_state = {"requested": bool(graph), "captured": ts._g is not None, "error": ts.graph_error, "eager_steps_before_capture": ts.graph_after}
     del ts, ddp, model, ema

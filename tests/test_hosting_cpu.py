@@ -71,3 +71,32 @@ def test_parse_model_patch_on_the_builder_shape():
         ast.parse(text)
         lists = _lists(text)
         assert any("C3_DCNv3" in l and "Conv" in l for l in lists) and any("C3_DCNv3" in l and "BottleneckCSP" in l for l in lists)
+
+
+def test_fuse_for_inference_folds_every_batchnorm_and_keeps_the_outputs():
+    """The reference's fuse() (models/yolo.py over utils/torch_utils.py:202-222) restated for the zoo's Conv blocks AND
+    the BatchNorm behind a DCNv3 layer (folded into output_proj): same eval-mode function, no BatchNorm left."""
+    import copy
+    import torch
+    from torch import nn
+    from yolo_somi_b200 import hosting
+    torch.manual_seed(0)
+    conv = hosting.Conv(8, 16, 3, 1)
+    with torch.no_grad():
+        conv.bn.running_mean.normal_(); conv.bn.running_var.uniform_(0.5, 2.0); conv.bn.weight.normal_(); conv.bn.bias.normal_()
+    x = torch.randn(2, 8, 10, 10)
+    want = conv.eval()(x)
+    fused = hosting.fuse_for_inference(copy.deepcopy(conv))
+    assert isinstance(fused.bn, nn.Identity) and fused.conv.bias is not None
+    assert torch.allclose(fused(x), want, rtol=1e-5, atol=1e-5)
+    # the wrapper's BatchNorm goes into output_proj: check the affine map itself (the DCNv3 core needs a GPU)
+    blk = hosting.DCNv3_YOLO(16, 16, 3)
+    with torch.no_grad():
+        blk.bn.running_mean.normal_(); blk.bn.running_var.uniform_(0.5, 2.0); blk.bn.weight.normal_(); blk.bn.bias.normal_()
+    y = torch.randn(5, 7, 7, 16)                     # what the sampler hands to output_proj (NHWC)
+    want = blk.eval().bn(blk.dcn.output_proj(y).permute(0, 3, 1, 2))
+    fused = hosting.fuse_for_inference(copy.deepcopy(blk))
+    assert isinstance(fused.bn, nn.Identity)
+    assert torch.allclose(fused.dcn.output_proj(y).permute(0, 3, 1, 2), want, rtol=1e-5, atol=1e-5)
+    assert not any(isinstance(m, nn.BatchNorm2d) for m in fused.modules())
+    assert not any(p.requires_grad for p in fused.parameters())

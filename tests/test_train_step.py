@@ -263,3 +263,32 @@ def test_whole_step_cuda_graph_follows_the_eager_step(amp):
         assert (a - b).norm() <= 0.05 * a.norm() + 1e-3
     for a, b in zip(ee, eg):
         assert (a - b).norm() <= 0.05 * a.norm() + 1e-3
+
+
+@pytest.mark.gpu
+def test_fused_graphed_inference_matches_the_eager_model():
+    """hosting.fuse_for_inference + GraphedInference (BASELINE configs[2] deployment form): same detections as the
+    eager eval-mode model with its BatchNorms, within fp16 rounding."""
+    import copy
+    from yolo_somi_b200.hosting import GraphedInference, fuse_for_inference
+    from yolo_somi_b200.yolov5l_dcnv3 import YOLOv5lDCNv3
+    torch.manual_seed(0)
+    model = YOLOv5lDCNv3(nc=10).cuda().to(memory_format=torch.channels_last).eval()
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.8, 1.2); m.weight.normal_(1, 0.1); m.bias.normal_(0, 0.1)
+        for l in model.dcnv3_layers():
+            l.offset.weight.normal_(0, 0.02); l.mask.weight.normal_(0, 0.1)
+    x = torch.rand(2, 3, 256, 256, device="cuda").to(memory_format=torch.channels_last)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        want = [t.float() for t in model(x)]
+    gi = GraphedInference(fuse_for_inference(copy.deepcopy(model)), x)
+    x2 = torch.rand_like(x)
+    gi(x2)                                        # another input in between: the replay must take the new one
+    got = [t.float().clone() for t in gi(x)]
+    torch.cuda.synchronize()
+    assert not any(isinstance(m, torch.nn.BatchNorm2d) for m in gi.model.modules())
+    for a, b in zip(got, want):
+        assert a.shape == b.shape
+        assert (a - b).norm() <= 2e-2 * b.norm() + 1e-3, float((a - b).norm() / b.norm())

@@ -142,3 +142,86 @@ class C2f_DCNv3(C2f):
     def __init__(self, c1, c2, n=1, shortcut=False, g=None, e=0.5):
         super().__init__(c1, c2, n, shortcut, 1, e)
         self.m = nn.ModuleList(Bottleneck_DCNv3(self.c, self.c, shortcut, g, e=1.0) for _ in range(n))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Inference form (BASELINE configs[2]).  The reference folds every Conv's BatchNorm into the convolution before
+# validation / detection (models/yolo.py `fuse()` over utils/torch_utils.py:202-222, called by attempt_load(fuse=True));
+# the same folding applies to the BatchNorm behind a DCNv3 layer: it is an affine map per channel, so it goes into the
+# layer's output_proj.  `GraphedInference` then replays the whole forward as one CUDA graph.
+def _bn_scale_shift(bn: nn.BatchNorm2d):
+    inv = torch.rsqrt(bn.running_var.double() + bn.eps)
+    gamma = bn.weight.double() if bn.affine else torch.ones_like(inv)
+    beta = bn.bias.double() if bn.affine else torch.zeros_like(inv)
+    scale = gamma * inv
+    return scale, beta - bn.running_mean.double() * scale
+
+
+@torch.no_grad()
+def fuse_for_inference(model: nn.Module) -> nn.Module:
+    """Fold eval-mode BatchNorm layers into what feeds them, in place: ``conv`` + ``bn`` pairs of the zoo's Conv blocks
+    (weight' = scale x weight, bias' = scale x bias + shift) and the BatchNorm of a ``DCNv3_YOLO`` wrapper into the
+    DCNv3 layer's ``output_proj``.  The folded norms become ``nn.Identity``.  Returns the model (in eval mode)."""
+    model.eval()
+    for m in model.modules():
+        if isinstance(m, DCNv3_YOLO) and isinstance(m.bn, nn.BatchNorm2d):
+            scale, shift = _bn_scale_shift(m.bn)
+            lin = m.dcn.output_proj
+            w = (lin.weight.double() * scale[:, None]).to(lin.weight.dtype)
+            b = ((lin.bias.double() if lin.bias is not None else 0.0) * scale + shift).to(lin.weight.dtype)
+            lin.weight.copy_(w)
+            if lin.bias is None:
+                lin.bias = nn.Parameter(b)
+            else:
+                lin.bias.copy_(b)
+            m.bn = nn.Identity()
+        elif (isinstance(getattr(m, "conv", None), nn.Conv2d) and isinstance(getattr(m, "bn", None), nn.BatchNorm2d)):
+            scale, shift = _bn_scale_shift(m.bn)
+            conv = m.conv
+            w = (conv.weight.double() * scale[:, None, None, None]).to(conv.weight.dtype)
+            b = ((conv.bias.double() if conv.bias is not None else 0.0) * scale + shift).to(conv.weight.dtype)
+            conv.weight.copy_(w)
+            if conv.bias is None:
+                conv.bias = nn.Parameter(b.to(conv.weight.device))
+            else:
+                conv.bias.copy_(b)
+            m.bn = nn.Identity()
+    for p in model.parameters():
+        p.requires_grad_(False)
+    return model
+
+
+class GraphedInference:
+    """The forward of an eval-mode model as ONE CUDA graph: ``y = GraphedInference(model, sample)(x)``.
+
+    ``sample`` fixes shape, dtype and memory format; ``warmup`` eager forwards run first on the capture stream (cuDNN
+    plans, tensor maps, the packed-weight caches of this library's fused producers -- frozen weights are packed once,
+    so the graph holds no repack).  Each call copies ``x`` into the static input and replays; the returned tensors are
+    the graph's static outputs (valid until the next call; clone to keep).  Weights must not change afterwards."""
+
+    def __init__(self, model: nn.Module, sample: torch.Tensor, autocast_dtype: torch.dtype | None = torch.float16, warmup: int = 3):
+        self.model = model.eval()
+        self.dtype = autocast_dtype
+        self._in = sample.clone()
+        self._stream = torch.cuda.Stream(sample.device)
+        self._stream.wait_stream(torch.cuda.current_stream(sample.device))
+        with torch.cuda.stream(self._stream):
+            for _ in range(warmup):
+                self._forward()
+        torch.cuda.current_stream(sample.device).wait_stream(self._stream)
+        torch.cuda.synchronize(sample.device)
+        self._g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._g, stream=self._stream):
+            self._out = self._forward()
+
+    def _forward(self):
+        amp = torch.autocast("cuda", dtype=self.dtype) if self.dtype is not None else torch.autocast("cuda", enabled=False)
+        with torch.no_grad(), amp:
+            return self.model(self._in)
+
+    def __call__(self, x: torch.Tensor):
+        if x.shape != self._in.shape:
+            raise ValueError("GraphedInference: static shape %s, got %s" % (tuple(self._in.shape), tuple(x.shape)))
+        self._in.copy_(x, non_blocking=True)
+        self._g.replay()
+        return self._out
