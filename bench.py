@@ -307,18 +307,30 @@ def layer_row(dev, dtype):
     xs = [torch.randn(CFG["N"], CFG["H"], CFG["W"], CFG["C"], device=dev, dtype=dtype, requires_grad=True) for _ in range(2)]
     go = torch.randn(CFG["N"], CFG["H"], CFG["W"], CFG["C"], device=dev, dtype=dtype)
 
-    def timed(n=30):
+    def timed(n=30, fn=None):
+        fn = fn or layer
         for i in range(6):
-            layer(xs[i % 2]).backward(go)
+            fn(xs[i % 2]).backward(go)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(n):
-            layer(xs[i % 2]).backward(go)
+            fn(xs[i % 2]).backward(go)
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n
 
-    fused_ms = timed()
+    fused_eager_ms = timed()
+    # eager, the ~75 launches of the layer's forward + backward take the host as long to enqueue as the GPU to run
+    # (scripts/layer_row_probe.py: 1.08 - 1.21 ms of enqueue against 1.15 - 1.26 ms): the row is the GPU's time,
+    # measured on the captured form (train_step.graph_block = make_graphed_callables), with the eager time beside it
+    fused_ms, graphed = fused_eager_ms, False
+    try:
+        from yolo_somi_b200.train_step import graph_block
+        gl = graph_block(layer, (xs[0].detach().clone().requires_grad_(True),))
+        fused_ms, graphed = min(fused_eager_ms, timed(fn=gl)), True
+        del gl
+    except Exception:
+        pass
     old = {k: os.environ.get(k) for k in ("DCNV3_FUSED_PROJ", "DCNV3_FUSED_DWCONV")}
     os.environ["DCNV3_FUSED_PROJ"] = "0"; os.environ["DCNV3_FUSED_DWCONV"] = "0"
     try:
@@ -329,7 +341,8 @@ def layer_row(dev, dtype):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
-    return {"fwd_bwd_ms_fused_producers": fused_ms, "fwd_bwd_ms_pytorch_producers": unfused_ms,
+    return {"fwd_bwd_ms_fused_producers": fused_ms, "fwd_bwd_ms_fused_producers_eager": fused_eager_ms,
+            "fused_row_from_cuda_graph": graphed, "fwd_bwd_ms_pytorch_producers": unfused_ms,
             "what": "DCNv3 layer forward + backward (input_proj, dwconv+LN+GELU, offset/mask, sampler, "
                     "output_proj), N=16 80x80 C=256 G=16 bf16; sampler = this library in both columns"}
 
