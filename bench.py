@@ -693,7 +693,7 @@ def run_ours(args, rank, world, local_rank):
             else:
                 train["mode"] = "eager"
         if weak_row is not None and train is not None:
-            train["weak_scaling_128_per_gpu"] = {k: weak_row.get(k) for k in ("img_per_s", "ms_per_step", "global_batch", "per_gpu_batch", "limiter")} \
+            train["weak_scaling_128_per_gpu"] = {k: weak_row.get(k) for k in ("img_per_s", "ms_per_step", "global_batch", "per_gpu_batch", "limiter", "cuda_graph")} \
                 if "error" not in weak_row else weak_row
         pts = points_per_step()
         value = world * pts * args.steps / (ms * 1e-3)
@@ -771,7 +771,7 @@ def run_ours(args, rank, world, local_rank):
             graph_row = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
         if world > 1 and os.environ.get("BENCH_TRAIN_WEAK", "1") != "0":
             try:
-                weak_row = train_row(args, rank, world, local_rank, dev, weak=True)
+                weak_row = train_row(args, rank, world, local_rank, dev, weak=True, graph=True)
             except Exception as exc:
                 weak_row = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
         done.set()

@@ -27,12 +27,19 @@ model = YOLOv5lDCNv3(nc=10).to(dev).to(memory_format=torch.channels_last)
 ts = TrainStep(model, nc=10, optimizer=make_optimizer(model), autocast_dtype=torch.float16)
 imgs, targets = synthetic_batch(B, 640, device="cuda")
 imgs = imgs.to(memory_format=torch.channels_last)
-for _ in range(3): ts.step(imgs, targets)
+import os
+import yolo_somi_b200.train_step as _ts
+_k = float(os.environ.get("TRAIN_LOSS_SCALE", 1))
+if _k != 1:      # what `loss * WORLD_SIZE` does to the updates at N ranks, on one GPU
+    _orig = _ts.yolo_surrogate_loss
+    _ts.yolo_surrogate_loss = lambda *a: _orig(*a) * _k
+for _ in range(int(os.environ.get("TRAIN_WARM", 3))): ts.step(imgs, targets)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     for _ in range(2): ts.step(imgs, targets)
     torch.cuda.synchronize()
-print("== training step, batch %d" % B); table(prof, 2)
+print("== training step, batch %d" % B); table(prof, 2, int(os.environ.get("TOP", 28)))
+if os.environ.get("STEP_ONLY"): sys.exit(0)
 del ts, model
 blk = DCNv3_YOLO(256, 256, 3).to(dev).to(memory_format=torch.channels_last)
 x = torch.randn(B, 256, 40, 40, device=dev).to(memory_format=torch.channels_last).requires_grad_(True)

@@ -319,8 +319,12 @@ class TrainStep:
             with amp:
                 preds = self.model(imgs)
             loss = yolo_surrogate_loss(preds, targets, self.nc)
-            if ddp:
-                loss = loss * dist.get_world_size()          # DDP averages the gradients (train.py:266-267)
+            # train.py:266-267 multiplies the loss by WORLD_SIZE because the reference's loss is a per-rank SUM (utils/loss.py
+            # returns loss * batch_size) that DDP's gradient averaging would otherwise shrink.  This harness' loss is a
+            # MEAN over the local batch: DDP's average of the ranks' gradients already is the gradient of the global mean,
+            # so the update for a given global batch is the same at every N.  (With the factor, eight ranks took 8x larger
+            # steps, the learned offsets left the value kernel's band within a dozen steps and the backward fell back to
+            # its plane form: profiles/README.md, round 2.)
             (self.scaler.scale(loss) if self.scaler is not None else loss).backward()
         if last_micro:
             if self.scaler is not None:
