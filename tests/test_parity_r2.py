@@ -250,12 +250,13 @@ def test_fused_dwconv_ln_gelu_backward_matches_fp64_autograd(N, H, W, C, dt):
             assert float(np.linalg.norm(a - wv) / (np.linalg.norm(wv) + 1e-30)) <= 1e-2, name
 
 
+@pytest.mark.parametrize("rows", [4321, 4320])      # rows % 8 == 0: the 128-bit form (eight rows per thread)
 @pytest.mark.parametrize("dt", ["bf16", "f16"])
-def test_mask_softmax_backward_kernel(dt):
+def test_mask_softmax_backward_kernel(dt, rows):
     from yolo_somi_b200 import _native
     lib = _native.load()
     dtype = TDT[dt]
-    rows, P = 4321, 9
+    P = 9
     gen = torch.Generator(device="cpu").manual_seed(5)
     mask = torch.softmax(torch.randn(rows, P, generator=gen), -1).to(dtype)
     gm = torch.randn(rows, P, generator=gen).to(dtype)
@@ -268,3 +269,11 @@ def test_mask_softmax_backward_kernel(dt):
     want = torch._softmax_backward_data(gm.double(), mask.double(), -1, torch.float64)
     eps = 2.0 ** -8 if dt == "bf16" else 2.0 ** -11
     assert float((out.double().cpu() - want).abs().max()) <= 1.01 * eps * float(want.abs().max()) + 1e-9
+    if rows % 8 == 0:
+        # bit-identical to the scalar form: the same rows inside a call whose row count is not a multiple of eight
+        dm2, dg2 = torch.cat([dm, dm[:1]]), torch.cat([dg, dg[:1]])
+        out2 = torch.empty_like(dm2)
+        rc = lib.dcnv3_mask_softmax_backward_sm100(dg2.data_ptr(), dm2.data_ptr(), out2.data_ptr(), rows + 1, P,
+                                                   _native.BF16 if dt == "bf16" else _native.F16,
+                                                   torch.cuda.current_stream().cuda_stream)
+        assert rc == 0 and torch.equal(out2[:rows].view(torch.int16), out.view(torch.int16))

@@ -64,13 +64,31 @@ ln_gelu_bwd(const T *__restrict__ conv_out, const T *__restrict__ grad_out, cons
     float s_b[8] = {}, s_g[8] = {}, s_t[8] = {};
     const long long stride = (long long)gridDim.x * kGroups;
     // (the whole CTA iterates together: the shuffles below always find every lane of the warp)
+    // The next pass's two 128-bit loads are issued before this pass's arithmetic (one pixel per lane group and pass,
+    // ~330 dependent instructions behind two loads: without the prefetch the kernel waited on them -- 4.8 warps per
+    // issue on the long scoreboard, issue-active 49 %, profiles/r2_dwconv_family_ncu_summary.txt).
+    uint4 nu = make_uint4(0u, 0u, 0u, 0u), ng = nu;
+    {
+        const long long p0 = (long long)blockIdx.x * kGroups + grp;
+        if ((long long)blockIdx.x * kGroups < pp.pixels) {
+            const size_t a0 = (size_t)(p0 < pp.pixels ? p0 : 0) * pp.C + ch0;
+            nu = __ldg(reinterpret_cast<const uint4 *>(conv_out + a0));
+            if (p0 < pp.pixels) ng = __ldg(reinterpret_cast<const uint4 *>(grad_out + a0));
+        }
+    }
     for (long long base = (long long)blockIdx.x * kGroups; base < pp.pixels; base += stride) {
         const long long p = base + grp;
         const bool live = p < pp.pixels;
         const size_t at = (size_t)(live ? p : 0) * pp.C + ch0;
         float u[8], gy[8];
-        unpack<T>(__ldg(reinterpret_cast<const uint4 *>(conv_out + at)), u);
-        unpack<T>(live ? __ldg(reinterpret_cast<const uint4 *>(grad_out + at)) : make_uint4(0u, 0u, 0u, 0u), gy);
+        unpack<T>(nu, u);
+        unpack<T>(ng, gy);
+        if (base + stride < pp.pixels) {
+            const long long p2 = base + stride + grp;
+            const size_t a2 = (size_t)(p2 < pp.pixels ? p2 : 0) * pp.C + ch0;
+            nu = __ldg(reinterpret_cast<const uint4 *>(conv_out + a2));
+            ng = p2 < pp.pixels ? __ldg(reinterpret_cast<const uint4 *>(grad_out + a2)) : make_uint4(0u, 0u, 0u, 0u);
+        }
         float s = 0.f;
 #pragma unroll
         for (int e = 0; e < 8; ++e) s += u[e];
@@ -228,7 +246,16 @@ static int launch(const void *x, const void *conv_out, const void *grad_out, con
     }
     const int cpp = C / 8, groups = kThreads / cpp;
     const long long want = (pp.pixels + groups - 1) / groups;
-    const int ctas1 = (int)std::min<long long>(want, (long long)num_sms * 8);
+    // one wave of resident CTAs, each striding over the pixels (148 x 8 CTAs at 3 resident per SM ran 2.7 waves)
+    static int resident[3] = {0, 0, 0};
+    const int ri = C == 256 ? 0 : C == 128 ? 1 : 2;
+    if (resident[ri] == 0) {
+        int occ = 0;
+        const void *fn = C == 256 ? (const void *)ln_gelu_bwd<T, 32> : C == 128 ? (const void *)ln_gelu_bwd<T, 16> : (const void *)ln_gelu_bwd<T, 8>;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, 0) != cudaSuccess || occ < 1) occ = 2;
+        resident[ri] = occ;
+    }
+    const int ctas1 = (int)std::min<long long>(want, (long long)num_sms * resident[ri]);
     const T *co = static_cast<const T *>(conv_out), *go = static_cast<const T *>(grad_out);
     T *dup = static_cast<T *>(du);
     if (C == 256) ln_gelu_bwd<T, 32><<<ctas1, kThreads, 0, stream>>>(co, go, gamma, beta, dup, g_b, g_gamma, g_beta, pp);
@@ -265,6 +292,47 @@ mask_softmax_bwd(const T *__restrict__ g_mask, const T *__restrict__ mask, T *__
     for (int p = 0; p < P; ++p) gl[p] = from_f32<T>(to_f32(mk[p]) * (to_f32(gm[p]) - dot));
 }
 
+// The same for P == 9 with 128-bit accesses: a thread owns EIGHT consecutive rows = 72 elements = nine 16-byte words of
+// each tensor (the scalar form issues 27 two-byte accesses per row and stalls on the load / store queue: 45 us for
+// 2 x 29.5 MB in, 29.5 MB out at cfg2 against ~15 us of HBM time; profiles/r2_dwconv_family_ncu_summary.txt).  Same
+// operation order per row as above, so the results are bit-identical.
+template <typename T>
+__global__ void __launch_bounds__(128)
+mask_softmax_bwd_p9x8(const uint4 *__restrict__ g_mask, const uint4 *__restrict__ mask, uint4 *__restrict__ g_logit, long long chunks) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= chunks) return;
+    uint32_t gw[36], mw[36];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        const uint4 a = __ldcs(g_mask + c * 9 + i), b = __ldg(mask + c * 9 + i);
+        gw[4 * i] = a.x; gw[4 * i + 1] = a.y; gw[4 * i + 2] = a.z; gw[4 * i + 3] = a.w;
+        mw[4 * i] = b.x; mw[4 * i + 1] = b.y; mw[4 * i + 2] = b.z; mw[4 * i + 3] = b.w;
+    }
+    float dot[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float d = 0.f;
+#pragma unroll
+        for (int p = 0; p < 9; ++p) {
+            const int e = 9 * j + p;
+            const float2 g2 = unpack2(gw[e >> 1], T()), m2 = unpack2(mw[e >> 1], T());
+            d = fmaf((e & 1) ? g2.y : g2.x, (e & 1) ? m2.y : m2.x, d);
+        }
+        dot[j] = d;
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int w = 4 * i + k, e0 = 2 * w, e1 = 2 * w + 1;
+            const float2 g2 = unpack2(gw[w], T()), m2 = unpack2(mw[w], T());
+            o[k] = pack2(m2.x * (g2.x - dot[e0 / 9]), m2.y * (g2.y - dot[e1 / 9]), T());
+        }
+        g_logit[c * 9 + i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 }  // namespace dwcb
 }  // namespace dcnv3
 
@@ -291,6 +359,17 @@ extern "C" int dcnv3_mask_softmax_backward_sm100(const void *grad_mask, const vo
     if (rows < 0 || points <= 0) return DCNV3_E_SHAPE;
     if (rows == 0) return DCNV3_OK;
     if (!grad_mask || !mask || !grad_logit) return DCNV3_E_NULL;
+    if (points == 9 && rows % 8 == 0 && (((uintptr_t)grad_mask | (uintptr_t)mask | (uintptr_t)grad_logit) % 16) == 0) {
+        const long long chunks = rows / 8, vb = (chunks + 127) / 128;
+        if (vb > 0x7fffffffLL) return DCNV3_E_TOO_LARGE;
+        if (dtype == DCNV3_F16)
+            dcnv3::dwcb::mask_softmax_bwd_p9x8<__half><<<(unsigned)vb, 128, 0, (cudaStream_t)stream>>>(
+                static_cast<const uint4 *>(grad_mask), static_cast<const uint4 *>(mask), static_cast<uint4 *>(grad_logit), chunks);
+        else
+            dcnv3::dwcb::mask_softmax_bwd_p9x8<__nv_bfloat16><<<(unsigned)vb, 128, 0, (cudaStream_t)stream>>>(
+                static_cast<const uint4 *>(grad_mask), static_cast<const uint4 *>(mask), static_cast<uint4 *>(grad_logit), chunks);
+        return (int)cudaGetLastError();
+    }
     const long long blocks = (rows + 255) / 256;
     if (blocks > 0x7fffffffLL) return DCNV3_E_TOO_LARGE;
     if (dtype == DCNV3_F16)
