@@ -680,6 +680,27 @@ def test_fused_dwconv_ln_gelu_matches_unfused(N, H, W, C, k, dt):
     assert allclose_frac(a, wv, rtol=1e-2, atol=1e-2 * rms) == 0.0, (max_abs(a, wv), rms)
 
 
+@pytest.mark.parametrize("N,H,W,C", [(16, 80, 80, 256), (64, 40, 40, 64), (7, 50, 61, 128)])
+def test_fused_dwconv_persistent_form_equals_the_one_shot_form(N, H, W, C, monkeypatch):
+    """k == 3 runs as a persistent kernel with two window buffers (several tiles per CTA at these sizes): bit-identical
+    to the one-CTA-per-tile form, outputs and the saved convolution result."""
+    from yolo_somi_b200.ops_dcnv3.functions import dwconv_ln_gelu as dlg
+    g = torch.Generator(device="cpu").manual_seed(C + N)
+    x = torch.randn(N, H, W, C, generator=g).to(torch.bfloat16).cuda().requires_grad_(True)
+    w = (torch.randn(C, 1, 3, 3, generator=g) / 3).cuda(); b = torch.randn(C, generator=g).cuda()
+    gamma, beta = (1 + 0.3 * torch.randn(C, generator=g)).cuda(), torch.randn(C, generator=g).cuda()
+    outs = []
+    for one_shot in ("0", "1"):
+        monkeypatch.setenv("DCNV3_DWCONV_ONESHOT", one_shot)
+        y = dlg.DwConvLnGelu.apply(x, w, b, gamma, beta, 1e-6, torch.bfloat16)
+        torch.cuda.synchronize()
+        conv_out = y.grad_fn.saved_tensors[5]
+        outs.append((y.detach().clone(), conv_out.clone()))
+    assert torch.equal(outs[0][0].view(torch.int16), outs[1][0].view(torch.int16))
+    assert torch.equal(outs[0][1].view(torch.int16), outs[1][1].view(torch.int16))
+    assert float(outs[0][0].float().abs().max()) > 0
+
+
 def test_layer_with_fused_producer_trains(monkeypatch):
     """Layer forward + backward with both fused producers on, against the same layer with them off."""
     from yolo_somi_b200.ops_dcnv3.modules import DCNv3

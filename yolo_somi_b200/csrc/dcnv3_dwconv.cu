@@ -16,6 +16,7 @@
 #include "dcnv3_tma.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace dcnv3 {
 namespace dwc {
@@ -140,6 +141,96 @@ dwconv_ln_gelu(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ w
     }
 }
 
+// The same for the compile-time kernel sizes as a PERSISTENT kernel: one wave of CTAs, each walking a strided list of
+// tiles with two window buffers -- the TMA box of the next tile is in flight while this one is computed.  (The one-shot
+// form runs 1600 CTAs of 51 KB at two per SM for cfg2: 5.4 waves, and every CTA starts by waiting for its own box.)
+template <typename T, int K, int CPP>
+__global__ void __launch_bounds__(kThreads)
+dwconv_ln_gelu_persistent(const __grid_constant__ CUtensorMap tmap, const T *__restrict__ wdw, const float *__restrict__ bdw,
+                          const float *__restrict__ gamma, const float *__restrict__ beta, T *__restrict__ out,
+                          T *__restrict__ conv_out, const Params pp) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar[2];
+    const int tid = threadIdx.x;
+    const int win = kTile + 2 * pp.r;
+    constexpr int cpp = CPP;
+    const unsigned win_bytes = (unsigned)(win * win * pp.C * 2);
+    const int per_image = pp.tiles_x * pp.tiles_y, total = per_image * pp.N;
+    int t = blockIdx.x;
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_barrier_init();
+        if (t < total) {
+            const int n = t / per_image, r = t % per_image;
+            mbar_expect_tx(&bar[0], win_bytes);
+            tma_load_4d(smem, &tmap, &bar[0], 0, (r % pp.tiles_x) * kTile - pp.r, (r / pp.tiles_x) * kTile - pp.r, n);
+        }
+    }
+    const int cl = tid % cpp, ch0 = cl * 8;
+    float g8[8], b8[8], cb8[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { g8[e] = gamma[ch0 + e]; b8[e] = beta[ch0 + e]; cb8[e] = bdw[ch0 + e]; }
+    uint4 wr[K * K];
+#pragma unroll
+    for (int i = 0; i < K * K; ++i) wr[i] = __ldg(reinterpret_cast<const uint4 *>(wdw + (size_t)i * pp.C + ch0));
+    const uint32_t pix_b = pp.C * 2, row_b = win * pix_b;
+    __syncthreads();
+    unsigned phases = 0u;                      // bit s: the parity buffer s completes next
+    const int ppw = kThreads / cpp;
+    for (int stage = 0; t < total; t += gridDim.x, stage ^= 1) {
+        const int tn = t + gridDim.x;
+        if (tid == 0 && tn < total) {          // the other buffer was released by the barrier that ended the last pass
+            const int n2 = tn / per_image, r2 = tn % per_image;
+            mbar_expect_tx(&bar[stage ^ 1], win_bytes);
+            tma_load_4d(smem + (size_t)(stage ^ 1) * win_bytes, &tmap, &bar[stage ^ 1], 0, (r2 % pp.tiles_x) * kTile - pp.r,
+                        (r2 / pp.tiles_x) * kTile - pp.r, n2);
+        }
+        mbar_wait(&bar[stage], (phases >> stage) & 1u);
+        phases ^= 1u << stage;
+        const int n = t / per_image, r = t % per_image;
+        const int x0 = (r % pp.tiles_x) * kTile, y0 = (r / pp.tiles_x) * kTile;
+        const uint32_t smem_lane = smem_u32(smem) + stage * win_bytes + ch0 * 2;
+        for (int p = tid / cpp; p < kTile * kTile; p += ppw) {
+            const int px = p % kTile, py = p / kTile;
+            float acc[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = cb8[e];
+            const uint32_t base = smem_lane + py * row_b + px * pix_b;
+#pragma unroll
+            for (int j = 0; j < K; ++j)
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    uint4 v;
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(base + j * row_b + i * pix_b));
+                    fma8<T>(acc, v, wr[j * K + i]);
+                }
+            float s = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s += acc[e];
+#pragma unroll
+            for (int o = cpp >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float mean = s * pp.inv_c;
+            float q = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { const float d = acc[e] - mean; q += d * d; }
+#pragma unroll
+            for (int o = cpp >> 1; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+            const float rstd = rsqrtf(fmaf(q, pp.inv_c, pp.eps));
+            float y[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) y[e] = gelu_erf((acc[e] - mean) * rstd * g8[e] + b8[e]);
+            const int ox = x0 + px, oy = y0 + py;
+            if (ox < pp.W && oy < pp.H) {
+                const size_t at = (((size_t)n * pp.H + oy) * pp.W + ox) * pp.C + ch0;
+                *reinterpret_cast<uint4 *>(out + at) = pack<T>(y);
+                if (conv_out) *reinterpret_cast<uint4 *>(conv_out + at) = pack<T>(acc);
+            }
+        }
+        __syncthreads();                        // everybody is done with this buffer: the next pass may refill it
+    }
+}
+
 template <typename T>
 static int launch(const void *x, const void *wdw_v, const float *bdw, const float *gamma, const float *beta, void *out, void *conv_out,
                   int N, int H, int W, int C, int k, float eps, int dtype, cudaStream_t stream) {
@@ -158,6 +249,28 @@ static int launch(const void *x, const void *wdw_v, const float *bdw, const floa
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kern<<<grid, kThreads, smem, stream>>>(tmap, wdw, bdw, gamma, beta, static_cast<T *>(out), static_cast<T *>(conv_out), pp);
     };
+    // k == 3 and two windows within half an SM's shared memory: the persistent, double-buffered form
+    const char *eo = std::getenv("DCNV3_DWCONV_ONESHOT");      // (read per call: the tests compare the two forms)
+    const bool one_shot = eo && eo[0] == '1';
+    if (k == 3 && 2 * smem <= 100 * 1024 + 8 * 1024 && !one_shot) {
+        static int num_sms = 0;
+        if (num_sms == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        }
+        const long long total = (long long)pp.tiles_x * pp.tiles_y * N;
+        auto gp = [&](auto kern) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * smem));
+            int occ = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, 2 * smem) != cudaSuccess || occ < 1) occ = 1;
+            const int ctas = (int)std::min<long long>(total, (long long)num_sms * occ);
+            kern<<<ctas, kThreads, 2 * smem, stream>>>(tmap, wdw, bdw, gamma, beta, static_cast<T *>(out), static_cast<T *>(conv_out), pp);
+        };
+        if (C == 256) gp(dwconv_ln_gelu_persistent<T, 3, 32>); else if (C == 128) gp(dwconv_ln_gelu_persistent<T, 3, 16>);
+        else gp(dwconv_ln_gelu_persistent<T, 3, 8>);
+        return (int)cudaGetLastError();
+    }
     if (k == 3) {
         if (C == 256) go(dwconv_ln_gelu<T, 3, 32>); else if (C == 128) go(dwconv_ln_gelu<T, 3, 16>); else go(dwconv_ln_gelu<T, 3, 8>);
     } else {
