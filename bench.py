@@ -320,17 +320,6 @@ def layer_row(dev, dtype):
         return e0.elapsed_time(e1) / n
 
     fused_eager_ms = timed()
-    # eager, the ~75 launches of the layer's forward + backward take the host as long to enqueue as the GPU to run
-    # (scripts/layer_row_probe.py: 1.08 - 1.21 ms of enqueue against 1.15 - 1.26 ms): the row is the GPU's time,
-    # measured on the captured form (train_step.graph_block = make_graphed_callables), with the eager time beside it
-    fused_ms, graphed = fused_eager_ms, False
-    try:
-        from yolo_somi_b200.train_step import graph_block
-        gl = graph_block(layer, (xs[0].detach().clone().requires_grad_(True),))
-        fused_ms, graphed = min(fused_eager_ms, timed(fn=gl)), True
-        del gl
-    except Exception:
-        pass
     old = {k: os.environ.get(k) for k in ("DCNV3_FUSED_PROJ", "DCNV3_FUSED_DWCONV")}
     os.environ["DCNV3_FUSED_PROJ"] = "0"; os.environ["DCNV3_FUSED_DWCONV"] = "0"
     try:
@@ -341,6 +330,18 @@ def layer_row(dev, dtype):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+    # eager, the ~75 launches of the layer's forward + backward take the host as long to enqueue as the GPU to run
+    # (scripts/layer_row_probe.py: 1.08 - 1.21 ms of enqueue against 1.15 - 1.26 ms): the row is the GPU's time,
+    # measured on the captured form (train_step.graph_block = make_graphed_callables, which patches the module's
+    # forward in place -- hence last), with the eager time beside it
+    fused_ms, graphed = fused_eager_ms, False
+    try:
+        from yolo_somi_b200.train_step import graph_block
+        gl = graph_block(layer, (xs[0].detach().clone().requires_grad_(True),))
+        fused_ms, graphed = min(fused_eager_ms, timed(fn=gl)), True
+        del gl
+    except Exception:
+        pass
     return {"fwd_bwd_ms_fused_producers": fused_ms, "fwd_bwd_ms_fused_producers_eager": fused_eager_ms,
             "fused_row_from_cuda_graph": graphed, "fwd_bwd_ms_pytorch_producers": unfused_ms,
             "what": "DCNv3 layer forward + backward (input_proj, dwconv+LN+GELU, offset/mask, sampler, "
