@@ -468,21 +468,23 @@ def train_row(args, rank, world, local_rank, dev, amp_dtype=torch.float16, graph
         try:
             import copy
             from yolo_somi_b200.hosting import GraphedInference, fuse_for_inference
-            fm = fuse_for_inference(copy.deepcopy(m))
-            gi = GraphedInference(fm, x, autocast_dtype=amp_dtype)
+            fm = fuse_for_inference(copy.deepcopy(m), half=(amp_dtype == torch.float16))
+            xg = x.half() if amp_dtype == torch.float16 else x
+            gi = GraphedInference(fm, xg, autocast_dtype=None if amp_dtype == torch.float16 else amp_dtype)
             for _ in range(3):
-                gi(x)
+                gi(xg)
             torch.cuda.synchronize()
             a.record()
             for _ in range(10):
-                gi(x)
+                gi(xg)
             b.record(); torch.cuda.synchronize()
             infer["eager"] = {"img_per_s": infer["img_per_s"], "ms_per_batch": infer["ms_per_batch"]}
             g_ips = 32 * 10 / (a.elapsed_time(b) * 1e-3)
             infer["fused_bn_cuda_graph"] = {"img_per_s": g_ips, "ms_per_batch": a.elapsed_time(b) / 10}
             if g_ips > infer["img_per_s"]:
                 infer["img_per_s"], infer["ms_per_batch"] = g_ips, a.elapsed_time(b) / 10
-                infer["mode"] = "BatchNorm folded into conv / output_proj, forward replayed as one CUDA graph"
+                infer["mode"] = ("BatchNorms folded (conv weights / output_proj; the folded bias joins the activation in one pass of "
+                                 "dcnv3_bias_act_sm100), model.half() as the reference's val.py, forward replayed as one CUDA graph")
             del gi, fm
         except Exception as exc:
             infer["fused_bn_cuda_graph"] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}

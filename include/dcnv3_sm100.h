@@ -181,6 +181,13 @@ DCNV3_API int dcnv3_dwconv_ln_gelu_backward_sm100(const void *x, const void *con
 DCNV3_API int dcnv3_mask_softmax_backward_sm100(const void *grad_mask, const void *mask, void *grad_logit,
                         long long rows, int points, int dtype, void *stream /* cudaStream_t */);
 
+/* The elementwise tail of a hosted Conv block in its inference form, act(conv(x) + bias) with the BatchNorm folded
+ * (reference: Conv.forward_fuse, models/common.py:55-66, after models/yolo.py fuse() / utils/torch_utils.py:202-222):
+ *   y[r, c] = act(x[r, c] + bias[c]);  x, y [rows, C] channels-last 16-bit, y may alias x; bias [C] fp32;
+ *   act: 0 = identity, 1 = SiLU; C a multiple of 8; pointers 16-byte aligned. */
+DCNV3_API int dcnv3_bias_act_sm100(const void *x, const float *bias, void *y, long long rows, int C, int act,
+                        int dtype, void *stream /* cudaStream_t */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,8 +87,17 @@ def test_fuse_for_inference_folds_every_batchnorm_and_keeps_the_outputs():
     x = torch.randn(2, 8, 10, 10)
     want = conv.eval()(x)
     fused = hosting.fuse_for_inference(copy.deepcopy(conv))
-    assert isinstance(fused.bn, nn.Identity) and fused.conv.bias is not None
+    # the folded bias joins the activation (BiasAct: one pass on the GPU, the plain expression here)
+    assert isinstance(fused.bn, nn.Identity) and fused.conv.bias is None and isinstance(fused.act, hosting.BiasAct)
+    assert fused.act.kind == "silu" and fused.act.bias.dtype == torch.float32
     assert torch.allclose(fused(x), want, rtol=1e-5, atol=1e-5)
+    # an activation BiasAct does not know keeps the bias inside the convolution
+    other = hosting.Conv(8, 16, 3, 1, act=nn.ReLU())
+    with torch.no_grad():
+        other.bn.running_mean.normal_(); other.bn.running_var.uniform_(0.5, 2.0)
+    want_other = other.eval()(x)
+    fo = hosting.fuse_for_inference(copy.deepcopy(other))
+    assert fo.conv.bias is not None and isinstance(fo.act, nn.ReLU) and torch.allclose(fo(x), want_other, rtol=1e-5, atol=1e-5)
     # the wrapper's BatchNorm goes into output_proj: check the affine map itself (the DCNv3 core needs a GPU)
     blk = hosting.DCNv3_YOLO(16, 16, 3)
     with torch.no_grad():

@@ -283,12 +283,41 @@ def test_fused_graphed_inference_matches_the_eager_model():
     x = torch.rand(2, 3, 256, 256, device="cuda").to(memory_format=torch.channels_last)
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
         want = [t.float() for t in model(x)]
-    gi = GraphedInference(fuse_for_inference(copy.deepcopy(model)), x)
-    x2 = torch.rand_like(x)
-    gi(x2)                                        # another input in between: the replay must take the new one
-    got = [t.float().clone() for t in gi(x)]
-    torch.cuda.synchronize()
-    assert not any(isinstance(m, torch.nn.BatchNorm2d) for m in gi.model.modules())
-    for a, b in zip(got, want):
-        assert a.shape == b.shape
-        assert (a - b).norm() <= 2e-2 * b.norm() + 1e-3, float((a - b).norm() / b.norm())
+    for half in (False, True):                    # autocast over fp32 weights | model.half() as the reference's val.py
+        fm = fuse_for_inference(copy.deepcopy(model), half=half)
+        xin = x.half() if half else x
+        gi = GraphedInference(fm, xin, autocast_dtype=None if half else torch.float16)
+        gi(torch.rand_like(xin))                  # another input in between: the replay must take the new one
+        got = [t.float().clone() for t in gi(xin)]
+        torch.cuda.synchronize()
+        assert not any(isinstance(m, torch.nn.BatchNorm2d) for m in gi.model.modules())
+        assert any(type(m).__name__ == "BiasAct" for m in gi.model.modules())
+        for a, b in zip(got, want):
+            assert a.shape == b.shape
+            assert (a - b).norm() <= 2e-2 * b.norm() + 1e-3, (half, float((a - b).norm() / b.norm()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 64, 7, 9), (1, 1024, 3, 5), (3, 24, 8, 8), (4, 256, 40, 40)])
+def test_bias_act_kernel_matches_the_expression(shape, dt):
+    """dcnv3_bias_act_sm100 (csrc/dcnv3_hosting.cu) through hosting.BiasAct: act(x + bias) on channels-last 16-bit
+    maps, in place, against the fp32 expression rounded once; a map that is not channels-last takes the fallback."""
+    from yolo_somi_b200.hosting import BiasAct
+    g = torch.Generator(device="cpu").manual_seed(sum(shape))
+    x = (3 * torch.randn(*shape, generator=g)).to(dt)
+    bias = torch.randn(shape[1], generator=g)
+    for kind in ("silu", "identity"):
+        mod = BiasAct(bias, kind).cuda()
+        t = x.float() + bias.view(1, -1, 1, 1)
+        want = (torch.nn.functional.silu(t) if kind == "silu" else t).to(dt)
+        xc = x.cuda().to(memory_format=torch.channels_last)
+        with torch.no_grad():
+            got = mod(xc)
+        torch.cuda.synchronize()
+        assert got.data_ptr() == xc.data_ptr()                       # in place
+        ulp = 2.0 ** -7 if dt == torch.bfloat16 else 2.0 ** -10
+        assert float((got.float().cpu() - want.float()).abs().max()) <= ulp * float(want.float().abs().max()) + 1e-6
+        with torch.no_grad():
+            fb = mod(x.cuda().contiguous())                          # NCHW-contiguous: the PyTorch expression
+        assert float((fb.float().cpu() - want.float()).abs().max()) <= 2 * ulp * float(want.float().abs().max()) + 1e-6

@@ -21,7 +21,7 @@ EXPORTS = ("dcnv3_sm100_abi_version", "dcnv3_sm100_strerror", "dcnv3_forward_sm1
            "dcnv3_host_pipeline_create", "dcnv3_host_pipeline_run", "dcnv3_host_pipeline_sync",
            "dcnv3_host_pipeline_destroy", "dcnv3_offset_mask_proj_padded_cols",
            "dcnv3_offset_mask_proj_sm100", "dcnv3_dwconv_ln_gelu_sm100",
-           "dcnv3_dwconv_ln_gelu_backward_sm100", "dcnv3_mask_softmax_backward_sm100")
+           "dcnv3_dwconv_ln_gelu_backward_sm100", "dcnv3_mask_softmax_backward_sm100", "dcnv3_bias_act_sm100")
 
 _lib = None
 
@@ -71,6 +71,8 @@ def load() -> ctypes.CDLL:
     lib.dcnv3_dwconv_ln_gelu_backward_sm100.argtypes = [c_vp] * 9 + [c_int] * 5 + [c_f, c_int, c_vp]
     lib.dcnv3_mask_softmax_backward_sm100.restype = c_int
     lib.dcnv3_mask_softmax_backward_sm100.argtypes = [c_vp] * 3 + [ctypes.c_longlong, c_int, c_int, c_vp]
+    lib.dcnv3_bias_act_sm100.restype = c_int
+    lib.dcnv3_bias_act_sm100.argtypes = [c_vp] * 3 + [ctypes.c_longlong, c_int, c_int, c_int, c_vp]
     got = lib.dcnv3_sm100_abi_version()
     if got != ABI_VERSION:
         raise DCNv3NativeError(f"{LIB_PATH}: ABI version {got}, expected {ABI_VERSION}; rebuild")

@@ -157,11 +157,56 @@ def _bn_scale_shift(bn: nn.BatchNorm2d):
     return scale, beta - bn.running_mean.double() * scale
 
 
+class BiasAct(nn.Module):
+    """``act(x + bias)`` for NCHW feature maps, the tail of a folded Conv block (the reference's Conv.forward_fuse,
+    models/common.py:55-66, with the folded bias taken out of the convolution).  16-bit channels-last CUDA tensors
+    outside autograd go through one in-place pass of ``dcnv3_bias_act_sm100`` (csrc/dcnv3_hosting.cu); everything
+    else through the plain PyTorch expression."""
+
+    KINDS = {"identity": 0, "silu": 1}
+
+    def __init__(self, bias: torch.Tensor, kind: str):
+        super().__init__()
+        if kind not in self.KINDS:
+            raise ValueError("BiasAct: kind must be one of %s" % (tuple(self.KINDS),))
+        self.kind = kind
+        self.register_buffer("bias", bias.detach().clone().float())
+        self._bias32 = None
+
+    def _bias_f32(self):
+        b = self.bias
+        if b.dtype == torch.float32:
+            return b
+        if self._bias32 is None or self._bias32.device != b.device:       # model.half() narrowed the buffer
+            self._bias32 = b.float()
+        return self._bias32
+
+    def forward(self, x):
+        c = x.shape[1]
+        if (x.is_cuda and x.dim() == 4 and x.dtype in (torch.float16, torch.bfloat16) and c % 8 == 0
+                and not (torch.is_grad_enabled() and x.requires_grad) and x.permute(0, 2, 3, 1).is_contiguous()
+                and x.data_ptr() % 16 == 0):
+            from . import _native
+            lib = _native.load()
+            b = self._bias_f32()
+            with torch.cuda.device(x.device):
+                rc = lib.dcnv3_bias_act_sm100(x.data_ptr(), b.data_ptr(), x.data_ptr(), x.numel() // c, c, self.KINDS[self.kind],
+                                              _native.F16 if x.dtype == torch.float16 else _native.BF16,
+                                              torch.cuda.current_stream().cuda_stream)
+            _native.check(rc, "dcnv3_bias_act_sm100")
+            return x
+        y = x + self.bias.to(x.dtype).view(1, -1, 1, 1)
+        return nn.functional.silu(y) if self.kind == "silu" else y
+
+
 @torch.no_grad()
-def fuse_for_inference(model: nn.Module) -> nn.Module:
+def fuse_for_inference(model: nn.Module, half: bool = False) -> nn.Module:
     """Fold eval-mode BatchNorm layers into what feeds them, in place: ``conv`` + ``bn`` pairs of the zoo's Conv blocks
     (weight' = scale x weight, bias' = scale x bias + shift) and the BatchNorm of a ``DCNv3_YOLO`` wrapper into the
-    DCNv3 layer's ``output_proj``.  The folded norms become ``nn.Identity``.  Returns the model (in eval mode)."""
+    DCNv3 layer's ``output_proj``.  The folded norms become ``nn.Identity``.  Where a Conv block's activation is SiLU or
+    the identity, the folded bias leaves the convolution and joins the activation (``BiasAct``: one pass instead of
+    ATen's broadcast add + SiLU).  ``half=True`` also narrows the model to fp16 as the reference's val / detect do
+    (``model.half()``): no per-call weight casts under autocast.  Returns the model (in eval mode)."""
     model.eval()
     for m in model.modules():
         if isinstance(m, DCNv3_YOLO) and isinstance(m.bn, nn.BatchNorm2d):
@@ -179,15 +224,22 @@ def fuse_for_inference(model: nn.Module) -> nn.Module:
             scale, shift = _bn_scale_shift(m.bn)
             conv = m.conv
             w = (conv.weight.double() * scale[:, None, None, None]).to(conv.weight.dtype)
-            b = ((conv.bias.double() if conv.bias is not None else 0.0) * scale + shift).to(conv.weight.dtype)
+            b = ((conv.bias.double() if conv.bias is not None else 0.0) * scale + shift)
             conv.weight.copy_(w)
-            if conv.bias is None:
-                conv.bias = nn.Parameter(b.to(conv.weight.device))
+            act = getattr(m, "act", None)
+            kind = "silu" if isinstance(act, nn.SiLU) else "identity" if isinstance(act, nn.Identity) else None
+            if kind is not None:
+                conv.bias = None
+                m.act = BiasAct(b.to(conv.weight.device), kind)
+            elif conv.bias is None:
+                conv.bias = nn.Parameter(b.to(conv.weight.dtype).to(conv.weight.device))
             else:
-                conv.bias.copy_(b)
-            m.bn = nn.Identity()
+                conv.bias.copy_(b.to(conv.weight.dtype))
+            m.bn = nn.Identity()       # (the zoo's Conv.forward = act(bn(conv(x))) is its forward_fuse now)
     for p in model.parameters():
         p.requires_grad_(False)
+    if half:
+        model.half()
     return model
 
 
