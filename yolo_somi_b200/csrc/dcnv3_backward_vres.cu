@@ -93,6 +93,13 @@ constexpr int kGroups = VRES_GROUPS;               // builder groups (64 kTpp th
 // second word under a divergent branch, the grad_out copy) at 66 % issue utilisation.  The builders are bound by their
 // instruction stream and its latencies, not by shared-memory bandwidth; the K-major tile stays the default.
 constexpr bool kAmn = VRES_AMN;
+// -DVRES_ZOOB=1: the zero refill as ONE tensor-map load of a box that lies wholly outside its tensor (the hardware
+// zero-fills and fetches nothing) instead of a 32 KB bulk copy from an L2-resident page of zeros.  MEASURED, parity-green:
+// backward 349.6 us against 251.3 us -- the tensor path generates out-of-bounds fill far slower than it copies.
+#ifndef VRES_ZOOB
+#define VRES_ZOOB 0
+#endif
+constexpr bool kZOob = VRES_ZOOB;
 // -DVRES_PIPE=1: the builders' read-modify-writes software-pipelined (the loads of point pt + 1 issued before the stores
 // of point pt unless the two share a cell).  MEASURED, parity-green: backward 274.9 us against 250.8 us -- the address
 // comparisons and the extra live registers cost more than the shortened chains save; off by default.
@@ -223,8 +230,8 @@ struct Sched {
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 1)
 bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ CUtensorMap tmap_msk,
-         const __grid_constant__ CUtensorMap tmap_gout, T *__restrict__ grad_value, uint32_t *__restrict__ far_list,
-         unsigned long long *__restrict__ far_count, const Geom q, const RParams pp) {
+         const __grid_constant__ CUtensorMap tmap_gout, const __grid_constant__ CUtensorMap tmap_zero, T *__restrict__ grad_value,
+         uint32_t *__restrict__ far_list, unsigned long long *__restrict__ far_count, const Geom q, const RParams pp) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t a_ready[kSlots], a_full[kSlots], a_done[kSlots], om_full[kOmStages], om_free[kOmStages],
         row_done[kMaxRing], acc_free[kMaxRing];
@@ -552,7 +559,12 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                     if (dbg) g_vres_dbg[p][4] = clock64();
                     uint64_t *bar = &a_ready[slot];
                     mbar_expect_tx(bar, kATileBytes + (kAmn ? 0 : kGoutBytes));
-                    bulk_fill(slot0 + slot * kATileBytes, g_zero_tile, kATileBytes, bar);
+                    if (kZOob) {
+                        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                     ::"r"(slot0 + slot * kATileBytes), "l"(&tmap_zero), "r"(0), "r"(1 << 20), "r"(smem_u32(bar)) : "memory");
+                    } else {
+                        bulk_fill(slot0 + slot * kATileBytes, g_zero_tile, kATileBytes, bar);
+                    }
                     if (!kAmn) {
                         unsigned char *gs = base + kSlots * kATileBytes + slot * kGoutBytes;
                         tma_load_4d(gs, &tmap_gout, bar, row.g * kCh, j * 8, row.i * 8, row.n);
@@ -718,6 +730,17 @@ static bool launch_typed(const void *offset, const void *mask, const void *grad_
     if (!make_run_tensor_map(&to, offset, dtype, q.N, q.Ho, q.Wo, q.G * kP * 2, kOffRow / 2)) return false;
     if (!make_run_tensor_map(&tm, mask, dtype, q.N, q.Ho, q.Wo, q.G * kP, kMskRow / 2)) return false;
     if (!make_run_tensor_map(&tg, grad_out, dtype, q.N, q.Ho, q.Wo, q.G * q.gc, 8)) return false;
+    CUtensorMap tz = tg;
+    if (kZOob) {
+        // [64][256] 16-bit elements = one coefficient tile, box = the whole map; loaded at row 2^20: all zero fill
+        EncodeTiledFn fn = encode_tiled_fn();
+        void *zp = nullptr;
+        if (!fn || cudaGetSymbolAddress(&zp, g_zero_tile) != cudaSuccess) return false;
+        const cuuint64_t dims[2] = {256, 64}, strides[1] = {512};
+        const cuuint32_t box[2] = {256, 64}, estr[2] = {1, 1};
+        if (fn(&tz, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, zp, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+    }
     static int num_sms = 0;
     if (num_sms == 0) {
         int dev = 0;
@@ -742,7 +765,7 @@ static bool launch_typed(const void *offset, const void *mask, const void *grad_
     uint32_t *far = static_cast<uint32_t *>(scratch);
     pp.far_cap = thr;
     *thr_out = thr;
-    *err = pdl_launch(true, bwd_vres<T>, dim3(ctas), dim3(kThreads), kSmemBytes, stream, to, tm, tg,
+    *err = pdl_launch(true, bwd_vres<T>, dim3(ctas), dim3(kThreads), kSmemBytes, stream, to, tm, tg, tz,
                       static_cast<T *>(grad_value), far, counter, q, pp);
     if (*err == cudaSuccess) *err = cudaGetLastError();
     if (*err != cudaSuccess) return true;
