@@ -100,6 +100,12 @@ constexpr bool kAmn = VRES_AMN;
 #define VRES_ZOOB 0
 #endif
 constexpr bool kZOob = VRES_ZOOB;
+// -DVRES_TMADIAG=n (WRONG results, timing only): 1 = the grad_out boxes (128 rows of 16 bytes per patch) are loaded for
+// the first patches only, 2 = the offset / mask boxes (64 rows of 48 / 32 bytes) as well: what the small-row requests cost.
+#ifndef VRES_TMADIAG
+#define VRES_TMADIAG 0
+#endif
+constexpr int kTmaDiag = VRES_TMADIAG;
 // -DVRES_PIPE=1: the builders' read-modify-writes software-pipelined (the loads of point pt + 1 issued before the stores
 // of point pt unless the two share a cell).  MEASURED, parity-green: backward 274.9 us against 250.8 us -- the address
 // comparisons and the extra live registers cost more than the shortened chains save; off by default.
@@ -545,10 +551,13 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                         unsigned char *st = base + kSlots * (kATileBytes + kGoutBytes) + stage * kOmBytes;
                         uint64_t *bar = &om_full[stage];
                         om_seq[stage] = p;
-                        mbar_expect_tx(bar, kOmBytes);
+                        const bool skip_om = kTmaDiag >= 2 && p >= (unsigned)kOmStages;
+                        mbar_expect_tx(bar, skip_om ? 0u : kOmBytes);
                         // a box starts on a 16-byte boundary of the row: the group's run begins 0..3 words / 0..7 elements in
+                        if (!skip_om) {
                         tma_load_4d(st + kStOff, &tmap_off, bar, (row.g * kP * 4 & ~15) >> 1, j * 8, row.i * 8, row.n);
                         tma_load_4d(st + kStMsk, &tmap_msk, bar, (row.g * kP * 2 & ~15) >> 1, j * 8, row.i * 8, row.n);
+                        }
                         if (kAmn) {
                             tma_load_4d(st + kStGout, &tmap_gout, bar, row.g * kCh, j * 8, row.i * 8, row.n);
                             tma_load_4d(st + kStGout + 1024, &tmap_gout, bar, row.g * kCh + 8, j * 8, row.i * 8, row.n);
@@ -558,14 +567,15 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
                     if (p >= (unsigned)kSlots) mbar_wait_sleep(&a_done[slot], (p / kSlots - 1u) & 1u, (pp.diag & 64) ? 0 : 32, 4, p);
                     if (dbg) g_vres_dbg[p][4] = clock64();
                     uint64_t *bar = &a_ready[slot];
-                    mbar_expect_tx(bar, kATileBytes + (kAmn ? 0 : kGoutBytes));
+                    const bool skip_g = kTmaDiag >= 1 && p >= (unsigned)kSlots;
+                    mbar_expect_tx(bar, kATileBytes + ((kAmn || skip_g) ? 0 : kGoutBytes));
                     if (kZOob) {
                         asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                                      ::"r"(slot0 + slot * kATileBytes), "l"(&tmap_zero), "r"(0), "r"(1 << 20), "r"(smem_u32(bar)) : "memory");
                     } else {
                         bulk_fill(slot0 + slot * kATileBytes, g_zero_tile, kATileBytes, bar);
                     }
-                    if (!kAmn) {
+                    if (!kAmn && !skip_g) {
                         unsigned char *gs = base + kSlots * kATileBytes + slot * kGoutBytes;
                         tma_load_4d(gs, &tmap_gout, bar, row.g * kCh, j * 8, row.i * 8, row.n);
                         tma_load_4d(gs + 1024, &tmap_gout, bar, row.g * kCh + 8, j * 8, row.i * 8, row.n);
