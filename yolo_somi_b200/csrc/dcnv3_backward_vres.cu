@@ -100,6 +100,14 @@ constexpr bool kAmn = VRES_AMN;
 #define VRES_ZOOB 0
 #endif
 constexpr bool kZOob = VRES_ZOOB;
+// -DVRES_LOADER2=1: the loader thread keeps TWO cursors over the patch list -- input boxes and zero refills -- and serves
+// whichever is ready (non-blocking polls) instead of both in program order per patch (a refill then does not wait
+// behind an input buffer the builders have not released yet).  MEASURED, parity-green: backward 252.0 us against 251.2 us --
+// as with the two-warp loader before it, issuing the refill earlier does not shorten the step.
+#ifndef VRES_LOADER2
+#define VRES_LOADER2 0
+#endif
+constexpr bool kLoader2 = VRES_LOADER2;
 // -DVRES_TMADIAG=n (WRONG results, timing only): 1 = the grad_out boxes (128 rows of 16 bytes per patch) are loaded for
 // the first patches only, 2 = the offset / mask boxes (64 rows of 48 / 32 bytes) as well: what the small-row requests cost.
 #ifndef VRES_TMADIAG
@@ -537,7 +545,51 @@ bwd_vres(const __grid_constant__ CUtensorMap tmap_off, const __grid_constant__ C
         }
     } else if (warp == kLoadWarp) {
         // ================================================================== refill + inputs of the next patches
-        if (lane == 0) {
+        if (kLoader2 && lane == 0) {
+            auto try_wait = [](uint64_t *bar, unsigned parity) {
+                uint32_t ok;
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+                return ok != 0;
+            };
+            Sched sa(lo, hi, pp.PR, q.N), sb(lo, hi, pp.PR, q.N);
+            Row ra, rb;
+            bool live_a = sa.next(ra), live_b = sb.next(rb);
+            int ja = 0, jb = 0;
+            unsigned pa = 0, pb = 0;
+            while (live_a || live_b) {
+                bool progress = false;
+                if (live_a) {      // offsets / masks of patch pa: the buffer is free once patch pa - kOmStages has been decoded
+                    const unsigned stage = pa % kOmStages;
+                    if (pa < (unsigned)kOmStages || try_wait(&om_free[stage], (pa / kOmStages - 1u) & 1u)) {
+                        unsigned char *st = base + kSlots * (kATileBytes + kGoutBytes) + stage * kOmBytes;
+                        uint64_t *bar = &om_full[stage];
+                        om_seq[stage] = pa;
+                        mbar_expect_tx(bar, kOmBytes);
+                        tma_load_4d(st + kStOff, &tmap_off, bar, (ra.g * kP * 4 & ~15) >> 1, ja * 8, ra.i * 8, ra.n);
+                        tma_load_4d(st + kStMsk, &tmap_msk, bar, (ra.g * kP * 2 & ~15) >> 1, ja * 8, ra.i * 8, ra.n);
+                        ++pa;
+                        if (++ja >= pp.S) { ja = 0; live_a = sa.next(ra); }
+                        progress = true;
+                    }
+                }
+                if (live_b) {      // zeros + grad_out of patch pb: its slot is free once patch pb - kSlots is through its products
+                    const unsigned slot = pb % kSlots;
+                    if (pb < (unsigned)kSlots || try_wait(&a_done[slot], (pb / kSlots - 1u) & 1u)) {
+                        uint64_t *bar = &a_ready[slot];
+                        mbar_expect_tx(bar, kATileBytes + kGoutBytes);
+                        bulk_fill(slot0 + slot * kATileBytes, g_zero_tile, kATileBytes, bar);
+                        unsigned char *gs = base + kSlots * kATileBytes + slot * kGoutBytes;
+                        tma_load_4d(gs, &tmap_gout, bar, rb.g * kCh, jb * 8, rb.i * 8, rb.n);
+                        tma_load_4d(gs + 1024, &tmap_gout, bar, rb.g * kCh + 8, jb * 8, rb.i * 8, rb.n);
+                        ++pb;
+                        if (++jb >= pp.S) { jb = 0; live_b = sb.next(rb); }
+                        progress = true;
+                    }
+                }
+                if (!progress) __nanosleep(32);
+            }
+        } else if (lane == 0) {
             Sched sch(lo, hi, pp.PR, q.N);
             Row row;
             unsigned p = 0;
