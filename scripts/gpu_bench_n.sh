@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# N-rank bench with the graph leg: GPUS=2 bash scripts/gpu_r2d.sh
+# N-rank bench with the graph leg: GPUS=2 bash scripts/gpu_bench_n.sh
 set -u
 mkdir -p gpurun_out
 N=${GPUS:-2}

@@ -321,3 +321,20 @@ def test_bias_act_kernel_matches_the_expression(shape, dt):
         with torch.no_grad():
             fb = mod(x.cuda().contiguous())                          # NCHW-contiguous: the PyTorch expression
         assert float((fb.float().cpu() - want.float()).abs().max()) <= 2 * ulp * float(want.float().abs().max()) + 1e-6
+
+
+def test_train_step_cpu_graph_flag_and_running_mean():
+    """graph=True needs CUDA: on the CPU the step stays eager (and accumulation is allowed); the logged loss is the MEAN
+    of the steps' losses; the same global batch gives the same update at any world size because the loss is a mean
+    (no `loss * WORLD_SIZE`, see TrainStep._work)."""
+    from yolo_somi_b200.train_step import TrainStep, make_optimizer, synthetic_batch
+    torch.manual_seed(0)
+    model = _TinyDet()
+    ts = TrainStep(model, nc=3, optimizer=make_optimizer(model, lr=0.05), autocast_dtype=None, log_every=1, graph=True)
+    assert ts.graph is False
+    imgs, targets = synthetic_batch(4, 32, nc=3, boxes_per_image=2, device="cpu", seed=1)
+    losses = [float(ts.step(imgs, targets)) for _ in range(3)]
+    ts.step(imgs, targets, last_micro=False)            # allowed in eager mode
+    step, mean = ts.loss_for_log()
+    assert step == 3 and abs(mean - sum(losses) / 3) < 1e-5 * max(1.0, abs(mean))
+    assert losses[2] < losses[0]                         # it trains
