@@ -671,6 +671,16 @@ def run_ours(args, rank, world, local_rank):
         }
     proj = proj_row(dev, dtype) if rank == 0 else None
     layer = layer_row(dev, dtype) if rank == 0 else None
+    # ---- the reference's own CUDA kernels recompiled for sm_100a (baseline/_ref/DCNv3_refcuda.so, built by
+    # scripts/build_reference_cuda.py), timed beside this library on this box: fp16 / fp32, it has no bf16 dispatch
+    refcuda = None
+    if rank == 0 and world == 1 and os.environ.get("BENCH_REF_CUDA", "1") != "0":
+        try:
+            sys.path.insert(0, str(ROOT / "scripts"))
+            import bench_reference_cuda
+            refcuda = bench_reference_cuda.run(iters=5, dev=dev)
+        except Exception as exc:
+            refcuda = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
     # ---- BASELINE configs[2] / [3]: the model-level step, every rank takes part (NCCL gradient all-reduce)
     del sets, host_in, host_out
     torch.cuda.empty_cache()
@@ -741,6 +751,8 @@ def run_ours(args, rank, world, local_rank):
             line["next_rows"] = {"offset_mask_proj": proj, "layer": layer}
         if modes is not None:
             line["precision_modes"] = modes
+        if refcuda is not None:
+            line["reference_cuda_kernels"] = refcuda
         if train is not None:
             line["train_step"] = train
             line["img_per_s"] = train["img_per_s"]
