@@ -22,8 +22,9 @@
  *     ((dx,dy) per point, point index p = i_w*kernel_h + j_h), mask [N,Ho,Wo,G*K],
  *     out / grad_out [N,Ho,Wo,G*gc];  Ho = (H + 2*pad_h - (dil_h*(kernel_h-1)+1))/stride_h + 1
  *     (src/cuda/dcnv3_cuda.cu:40-45), K = kernel_h*kernel_w;
- *   - all tensors of one call share one dtype (fp32 / fp16 / bf16; the reference has no bf16 and
- *     also dispatches fp64, which this library rejects);  arithmetic is fp32 for every dtype
+ *   - all tensors of one call share one dtype (fp32 / fp16 / bf16 / fp64; the reference has no
+ *     bf16);  arithmetic is fp32 for the first three and fp64 for fp64 I/O -- a plain correctness
+ *     path, the one the reference's own test script drives first (models/ops_dcnv3/test.py:33-57)
  *     (reference: opmath_t, dcnv3_im2col_cuda.cuh:30);  gradients are produced in the I/O dtype
  *     (reference: fp32 accumulate then cast, dcnv3_cuda.cu:126-133,168-173);
  *   - inputs are borrowed, outputs are caller-allocated and fully overwritten: no pre-zeroing
@@ -52,11 +53,11 @@ extern "C" {
 #define DCNV3_API
 #endif
 
-enum dcnv3_dtype { DCNV3_F32 = 0, DCNV3_F16 = 1, DCNV3_BF16 = 2 };
+enum dcnv3_dtype { DCNV3_F32 = 0, DCNV3_F16 = 1, DCNV3_BF16 = 2, DCNV3_F64 = 3 };
 
 enum dcnv3_error {
     DCNV3_OK = 0,
-    DCNV3_E_DTYPE = -1,     /* dtype tag not one of dcnv3_dtype                            */
+    DCNV3_E_DTYPE = -1,     /* dtype tag not one of dcnv3_dtype (or DETERMINISTIC with fp64) */
     DCNV3_E_SHAPE = -2,     /* non-positive extent / kernel / stride / dilation, or Ho/Wo  */
                             /* inconsistent with the formula above                         */
     DCNV3_E_NULL = -3,      /* a required pointer is NULL                                  */

@@ -321,7 +321,7 @@ def test_error_conditions_match_reference():
         DCNv3.dcnv3_forward(v3, o3, m3, *geom, 2)         # batch 3, step 2
     assert DCNv3.dcnv3_forward(v3, o3, m3, *geom, 3).shape[0] == 3
     with pytest.raises(RuntimeError):
-        DCNv3.dcnv3_forward(v.double(), o.double(), m.double(), *geom, 256)   # documented deviation
+        DCNv3.dcnv3_forward(v.to(torch.int32), o.to(torch.int32), m.to(torch.int32), *geom, 256)
     with pytest.raises(RuntimeError):
         DCNv3.dcnv3_forward(v, o.half(), m, *geom, 256)
     with pytest.raises(RuntimeError, match="contiguous"):

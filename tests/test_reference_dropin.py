@@ -138,3 +138,57 @@ def test_against_the_reference_cuda_extension(dtype, shape):
         assert frac <= frac_ok, (name, frac)
         if name != "grad_offset":     # a location within an ulp of an integer may floor() differently: SURVEY F5
             assert float(d.max()) <= cap * rms, (name, float(d.max()), rms)
+
+
+# ----------------------------------------------------------------------------- fp64 and the reference's own test script
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [cases.REFTEST_FWD] + cases.REFTEST_BWD + cases.SWEEP + [cases.CFG1], ids=lambda c: c.name)
+def test_fp64_against_the_direct_oracle_and_the_reference_fp64_run(case):
+    """fp64 I/O (csrc/dcnv3_f64.cu; the reference dispatches double, dcnv3_cuda.cu:69,147): all arithmetic in double, so
+    the pixel-space oracle in fp64 is reproduced to summation order, and the reference's own fp64 run (whose reference
+    points / grids are fp32, functions/dcnv3_func.py:103-136: SURVEY F5) to that coordinate rounding."""
+    from oracle import dcnv3_oracle as orc
+    from yolo_somi_b200.ops_dcnv3.functions import DCNv3Function
+    arrs = check_inputs_unchanged(case)
+    v, o, m, g = (torch.as_tensor(np.asarray(a, dtype=np.float64)).cuda() for a in arrs)
+    v.requires_grad_(True); o.requires_grad_(True); m.requires_grad_(True)
+    out = DCNv3Function.apply(v, o, m, *case.geom, 256)
+    out.backward(g)
+    torch.cuda.synchronize()
+    got = [t.detach().cpu().numpy() for t in (out, v.grad, o.grad, m.grad)]
+    a64 = [np.asarray(a, dtype=np.float64) for a in arrs]
+    want = (orc.direct_forward(*a64[:3], *case.geom), *orc.direct_backward(*a64, *case.geom))
+    for name, a, w in zip(("out", "gv", "go", "gm"), got, want):
+        assert a.dtype == np.float64 and a.shape == w.shape, name
+        scale = max(1.0, float(np.abs(w).max()))
+        assert max_abs(a, w) <= 1e-11 * scale, (name, max_abs(a, w))
+        kind, ref64, _ = golden(case.name, "f64", name)
+        assert max_abs(view_like_golden(kind, a), ref64) <= 1e-4 * scale, name
+
+
+@pytest.mark.gpu
+def test_fp64_has_no_deterministic_mode_and_says_so(monkeypatch):
+    import DCNv3
+    c = cases.SWEEP[0]
+    v, o, m, g = (torch.as_tensor(np.asarray(a, dtype=np.float64)).cuda() for a in cases.make_inputs(c))
+    monkeypatch.setenv("DCNV3_DETERMINISTIC", "1")
+    with pytest.raises(RuntimeError, match="fp64"):
+        DCNv3.dcnv3_backward(v, o, m, *c.geom, g, 256)
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_reference_test_script_passes_unmodified_over_the_shim():
+    """`python test.py` of the reference (models/ops_dcnv3/test.py, staged verbatim) with `import DCNv3` resolving to
+    this repository: every check it prints -- forward in double and float, the three gradients in double and float
+    for group_channels in {1, 16, 30, 32, 64, 71, 1025} -- must say True, and its timing loop must run."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("run_reference_test_script", ref_loader.ROOT / "scripts" / "run_reference_test_script.py")
+    runner = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(runner)
+    rc, out, err = runner.run("ours")
+    assert rc == 0, err[-3000:]
+    lines = runner.checks(out)
+    assert len(lines) == 2 + 2 * 7 * 3, out
+    assert all(ln.startswith("* True") for ln in lines), "\n".join(ln for ln in lines if not ln.startswith("* True"))
+    assert out.count("foward time cost") == 3, out

@@ -13,7 +13,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("DCNV3_SM100_LIB", _PKG / "libdcnv3_sm100.so"))
 
 ABI_VERSION = 1
-F32, F16, BF16 = 0, 1, 2
+F32, F16, BF16, F64 = 0, 1, 2, 3
 BWD_DETERMINISTIC = 1
 
 EXPORTS = ("dcnv3_sm100_abi_version", "dcnv3_sm100_strerror", "dcnv3_forward_sm100",

@@ -22,7 +22,7 @@ OBJ_DIR = PKG / "csrc" / "_obj"
 
 SOURCES = ["dcnv3_forward.cu", "dcnv3_forward_tile.cu", "dcnv3_forward_gs.cu", "dcnv3_backward.cu", "dcnv3_backward_mma.cu",
            "dcnv3_backward_strip.cu", "dcnv3_backward_dots.cu", "dcnv3_backward_vmma.cu", "dcnv3_backward_vres.cu", "dcnv3_host_pipeline.cu",
-           "dcnv3_proj.cu", "dcnv3_dwconv.cu", "dcnv3_dwconv_bwd.cu", "dcnv3_hosting.cu", "dcnv3_capi.cu"]
+           "dcnv3_f64.cu", "dcnv3_proj.cu", "dcnv3_dwconv.cu", "dcnv3_dwconv_bwd.cu", "dcnv3_hosting.cu", "dcnv3_capi.cu"]
 # measured alternatives that lost to the defaults (profiles/README.md): built only on request
 EXPERIMENTS = ["experiments/dcnv3_forward_mma.cu", "experiments/dcnv3_backward_mma2.cu", "experiments/dcnv3_backward_tile.cu",
                "experiments/dcnv3_backward_vband.cu"]

@@ -11,11 +11,11 @@ int conv_out(int in, int pad, int dil, int k, int stride) {
     return (in + 2 * pad - (dil * (k - 1) + 1)) / stride + 1;  // dcnv3_cuda.cu:40-45
 }
 
-size_t elem_size(int dtype) { return dtype == DCNV3_F32 ? 4 : 2; }
+size_t elem_size(int dtype) { return dtype == DCNV3_F64 ? 8 : dtype == DCNV3_F32 ? 4 : 2; }
 
 int check_geometry(int N, int H, int W, int Ho, int Wo, int G, int gc, int kh, int kw, int sh,
                    int sw, int ph, int pw, int dh, int dw, int dtype, dcnv3::Geom *q) {
-    if (dtype != DCNV3_F32 && dtype != DCNV3_F16 && dtype != DCNV3_BF16) return DCNV3_E_DTYPE;
+    if (dtype != DCNV3_F32 && dtype != DCNV3_F16 && dtype != DCNV3_BF16 && dtype != DCNV3_F64) return DCNV3_E_DTYPE;
     if (N < 0 || H <= 0 || W <= 0 || G <= 0 || gc <= 0 || kh <= 0 || kw <= 0 || sh <= 0 ||
         sw <= 0 || dh <= 0 || dw <= 0 || ph < 0 || pw < 0)
         return DCNV3_E_SHAPE;
@@ -39,7 +39,7 @@ int dcnv3_sm100_abi_version(void) { return DCNV3_SM100_ABI_VERSION; }
 const char *dcnv3_sm100_strerror(int code) {
     switch (code) {
     case DCNV3_OK: return "ok";
-    case DCNV3_E_DTYPE: return "dcnv3: unsupported dtype (fp32, fp16 and bf16 only)";
+    case DCNV3_E_DTYPE: return "dcnv3: unsupported dtype (fp32, fp16, bf16, fp64; no deterministic backward for fp64)";
     case DCNV3_E_SHAPE: return "dcnv3: invalid geometry (extent/kernel/stride/dilation/pad or Ho/Wo mismatch)";
     case DCNV3_E_NULL: return "dcnv3: null pointer";
     case DCNV3_E_WORKSPACE: return "dcnv3: workspace too small";
@@ -61,6 +61,7 @@ int dcnv3_forward_sm100(const void *value, const void *offset, const void *mask,
     if ((long long)N * Ho * Wo == 0) return DCNV3_OK;
     if (!value || !offset || !mask || !out) return DCNV3_E_NULL;
     if ((uintptr_t)offset % (2 * elem_size(dtype))) return DCNV3_E_ALIGN;
+    if (dtype == DCNV3_F64) return (int)dcnv3::launch_forward_f64(value, offset, mask, out, q, (cudaStream_t)stream);
     return (int)dcnv3::launch_forward(value, offset, mask, out, q, dtype, (cudaStream_t)stream);
 }
 
@@ -68,6 +69,7 @@ size_t dcnv3_backward_workspace_bytes(int N, int H, int W, int G, int gc, int dt
     if (N <= 0 || H <= 0 || W <= 0 || G <= 0 || gc <= 0) return 0;
     dcnv3::Geom q{};
     q.N = N; q.H = H; q.W = W; q.G = G; q.gc = gc;
+    if (dtype == DCNV3_F64) return 0;   // fp64 atomics straight into grad_value
     return dcnv3::backward_workspace_bytes(q, dtype, flags);
 }
 
@@ -86,6 +88,12 @@ int dcnv3_backward_sm100(const void *value, const void *offset, const void *mask
     if (!value || !grad_value) return DCNV3_E_NULL;
     if ((long long)Ho * Wo != 0 && (!offset || !mask || !grad_out || !grad_offset || !grad_mask))
         return DCNV3_E_NULL;
+    if (dtype == DCNV3_F64) {
+        if (flags & DCNV3_BWD_DETERMINISTIC) return DCNV3_E_DTYPE;   // its grad_value is a sum of fp64 atomics
+        if (((uintptr_t)offset | (uintptr_t)grad_offset) % 8) return DCNV3_E_ALIGN;
+        return (int)dcnv3::launch_backward_f64(value, offset, mask, grad_out, grad_value, grad_offset, grad_mask, q,
+                                               (cudaStream_t)stream);
+    }
     const size_t need = dcnv3::backward_workspace_bytes(q, dtype, flags);
     if (need) {
         if (!workspace) return DCNV3_E_NULL;

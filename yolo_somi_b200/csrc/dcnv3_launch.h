@@ -120,6 +120,12 @@ inline cudaError_t pdl_launch(bool allow, void (*kernel)(KArgs...), dim3 grid, d
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
+// fp64 I/O, all arithmetic in double (dcnv3_f64.cu): the reference's own test script drives the extension in double
+cudaError_t launch_forward_f64(const void *value, const void *offset, const void *mask, void *out, const Geom &q,
+                               cudaStream_t stream);
+cudaError_t launch_backward_f64(const void *value, const void *offset, const void *mask, const void *grad_out,
+                                void *grad_value, void *grad_offset, void *grad_mask, const Geom &q, cudaStream_t stream);
+
 size_t backward_workspace_bytes(const Geom &q, int dtype, unsigned flags);
 
 cudaError_t launch_backward(const void *value, const void *offset, const void *mask,

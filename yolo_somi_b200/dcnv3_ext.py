@@ -9,7 +9,9 @@ re-exports them so that ``import DCNv3`` resolves here and the reference's Pytho
 unmodified.
 
 Deviations from the reference, all documented in DESIGN.md:
-  * bf16 is supported; fp64 is rejected (the reference dispatches fp64/fp32/fp16, dcnv3_cuda.cu:69);
+  * bf16 is supported beside the reference's fp64/fp32/fp16 (dcnv3_cuda.cu:69); fp64 is a plain all-double
+    correctness path (csrc/dcnv3_f64.cu: the reference's test.py drives the extension in double) without a
+    deterministic mode;
   * a failed kernel launch raises (the reference printf()s, dcnv3_im2col_cuda.cuh:864-867);
   * outputs are allocated with ``torch.empty`` (every element is written by the kernels);
   * half-precision gradients are produced directly (no fp32 round trip of grad_offset/grad_mask);
@@ -25,7 +27,7 @@ import torch
 
 from . import _native
 
-_DTYPES = {torch.float32: _native.F32, torch.float16: _native.F16, torch.bfloat16: _native.BF16}
+_DTYPES = {torch.float32: _native.F32, torch.float16: _native.F16, torch.bfloat16: _native.BF16, torch.float64: _native.F64}
 
 
 def _conv_out(size, pad, dil, k, stride):
@@ -48,7 +50,7 @@ def _validate(tensors, group, group_channels, im2col_step):
         if t.device != inp.device or t.dtype != inp.dtype:
             raise RuntimeError(f"{name}: expected {inp.dtype} on {inp.device}, got {t.dtype} on {t.device}")
     if inp.dtype not in _DTYPES:
-        raise RuntimeError(f"dcnv3: unsupported dtype {inp.dtype} (float32, float16, bfloat16)")
+        raise RuntimeError(f"dcnv3: unsupported dtype {inp.dtype} (float32, float16, bfloat16, float64)")
     if inp.dim() != 4:
         raise RuntimeError("input must be [N, H, W, C]")
     batch, channels = inp.shape[0], inp.shape[3]
