@@ -90,6 +90,12 @@ def test_reference_import_paths_resolve_to_this_library():
         assert mod is ours and hasattr(mod, "DCNv3")
         fn = importlib.import_module("models.ops_dcnv3.functions.dcnv3_func")
         assert hasattr(fn, "DCNv3Function")
+        # every public name of the reference's two packages (functions/__init__.py, modules/__init__.py) resolves,
+        # and the debug layer's class path carries the same state_dict keys as the layer
+        from models.ops_dcnv3.functions import DCNv3Function, dcnv3_core_pytorch  # noqa: F401
+        from models.ops_dcnv3.modules import DCNv3, DCNv3_pytorch
+        a, b = DCNv3(channels=32, group=2), DCNv3_pytorch(channels=32, group=2)
+        assert list(a.state_dict()) == list(b.state_dict()) and isinstance(b, DCNv3)
     finally:
         for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
             del sys.modules[k]

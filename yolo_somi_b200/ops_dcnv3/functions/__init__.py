@@ -1,1 +1,1 @@
-from .dcnv3_func import DCNv3Function, dcnv3_core  # noqa: F401
+from .dcnv3_func import DCNv3Function, dcnv3_core, dcnv3_core_pytorch  # noqa: F401

@@ -64,3 +64,13 @@ def dcnv3_core(input, offset, mask, kernel_h, kernel_w, stride_h, stride_w, pad_
     return DCNv3Function.apply(input, offset, mask, kernel_h, kernel_w, stride_h, stride_w,
                                pad_h, pad_w, dilation_h, dilation_w, group, group_channels,
                                offset_scale, im2col_step)
+
+
+def dcnv3_core_pytorch(input, offset, mask, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
+                       dilation_h, dilation_w, group, group_channels, offset_scale):
+    """The NAME of the reference's debug implementation (functions/dcnv3_func.py:147-188), with its signature, so that
+    ``from models.ops_dcnv3.functions import DCNv3Function, dcnv3_core_pytorch`` keeps importing.  Here it computes the
+    same function on the sm_100a kernels (CUDA tensors only: this library has no PyTorch / CPU path; the grid_sample
+    restatement lives in ``oracle/`` as test infrastructure and is never imported from here)."""
+    return dcnv3_core(input, offset, mask, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
+                      dilation_h, dilation_w, group, group_channels, offset_scale)

@@ -1,1 +1,1 @@
-from .dcnv3 import DCNv3  # noqa: F401
+from .dcnv3 import DCNv3, DCNv3_pytorch  # noqa: F401

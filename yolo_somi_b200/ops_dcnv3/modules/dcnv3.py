@@ -187,3 +187,10 @@ class DCNv3(nn.Module):
             cfs = cfs.repeat_interleave(self.group_channels, dim=-1)  # per group -> per channel
             y = y * (1 - cfs) + x * cfs
         return _linear(y, self.output_proj)
+
+
+class DCNv3_pytorch(DCNv3):
+    """The NAME of the reference's debug layer (modules/dcnv3.py:95-219): same constructor, same parameters, same
+    ``state_dict`` keys as ``DCNv3``, so imports (``from models.ops_dcnv3.modules import DCNv3, DCNv3_pytorch``) and
+    checkpoints that pickled this class path keep loading.  Here it IS the sm_100a layer -- there is no PyTorch / CPU
+    sampler in this library (the reference's pure-PyTorch form is restated in ``oracle/`` as test infrastructure)."""
