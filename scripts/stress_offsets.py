@@ -15,7 +15,10 @@ dists = {"N(0,0.5)": lambda: 0.5 * torch.randn(N, H, W, G * 18, generator=g),
          "N(0,1)": lambda: torch.randn(N, H, W, G * 18, generator=g),
          "N(0,2)": lambda: 2.0 * torch.randn(N, H, W, G * 18, generator=g),
          "U(-4,4)": lambda: 8.0 * torch.rand(N, H, W, G * 18, generator=g) - 4.0}
+only = os.environ.get('STRESS_ONLY')   # e.g. 'N(0,2)': one distribution (for an ncu launch list)
 for name, mk in dists.items():
+    if only and name != only:
+        continue
     o = mk().bfloat16().cuda()
     for _ in range(3):
         DCNv3.dcnv3_forward(v, o, m, *geom, 256); DCNv3.dcnv3_backward(v, o, m, *geom, go, 256)

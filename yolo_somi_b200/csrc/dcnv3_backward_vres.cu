@@ -731,28 +731,71 @@ far_points(const uint32_t *far_list, const unsigned long long *far_count, unsign
         for (size_t i = tid; i < plane_vec; i += (size_t)gridDim.x * 256) plane[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         return;
     }
+    // Two phases per batch of 32 entries.  Phase 1, lane <-> entry: the entry, its offset pair and its mask -- a chain of
+    // dependent loads that mostly miss L2 -- are fetched for 32 points at once.  Phase 2, lane <-> (corner, channel pair):
+    // the points' locations are broadcast by shuffles, four points at a time (their grad_out loads are issued together,
+    // then their reductions).  (One warp per point, its loads one after the other: 125 us for the ~330 k far points of
+    // N(0, 2)-pixel offsets at cfg2; this form ~25 us: backward 491 -> 368 us there, 440 -> 324 us for U(-4, 4).)
     const int lane = threadIdx.x & 31, corner = lane >> 3, cp = lane & 7;
     const int C = q.G * q.gc;
-    for (size_t i = tid >> 5; i < count; i += ((size_t)gridDim.x * 256) >> 5) {
-        uint32_t e;
-        asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(e) : "l"(far_list + i) : "memory");
-        const int pt = (int)(e & 15u);
-        size_t pg = e >> 4;
-        const int g = (int)(pg % q.G); pg /= q.G;        // pg: pixel (n, ho, wo) from here on
-        const int wo = (int)(pg % q.Wo), ho = (int)((pg / q.Wo) % q.Ho), n = (int)(pg / ((size_t)q.Wo * q.Ho));
-        const size_t pix = pg;
-        const T *op = offset + (pix * q.G + g) * (kP * 2) + 2 * pt;
-        const float m = to_f32(mask[(pix * q.G + g) * kP + pt]);
-        const float lw_abs = axis_base(wo, 3, 1, q.pw, 1, q.sigma) + ((float)(pt / 3) + to_f32(op[0])) * q.sigma;
-        const float lh_abs = axis_base(ho, 3, 1, q.ph, 1, q.sigma) + ((float)(pt % 3) + to_f32(op[1])) * q.sigma;
-        if (!(lh_abs > -1.f && lw_abs > -1.f && lh_abs < (float)q.H && lw_abs < (float)q.W)) continue;   // (:262-263)
-        const float fw = floorf(lw_abs), fh = floorf(lh_abs);
-        const float lw = lw_abs - fw, lh = lh_abs - fh;
-        const float cf = ((corner & 2) ? lh : 1.f - lh) * m * ((corner & 1) ? lw : 1.f - lw);
-        const int hh = (int)fh + (corner >> 1), ww = (int)fw + (corner & 1);
-        if ((unsigned)hh < (unsigned)q.H && (unsigned)ww < (unsigned)q.W && cf != 0.f) {
-            const float2 gq = unpack2(*reinterpret_cast<const uint32_t *>(grad_out + pix * C + g * kCh + 2 * cp), T());
-            red_add2(grad_value + (((size_t)n * q.H + hh) * q.W + ww) * C + g * kCh + 2 * cp, pack2(cf * gq.x, cf * gq.y, T()));
+    const size_t n_warps = ((size_t)gridDim.x * 256) >> 5;
+    // entries per warp and batch: as few as spread the list over all warps (a few thousand far points -- the usual case --
+    // are one point per warp, all in flight at once: 6 us; with 32 per warp the same list took 19 us on 110 warps)
+    const unsigned bsz = (unsigned)((count + n_warps - 1) / n_warps < 32 ? (count + n_warps - 1) / n_warps : 32);
+    for (size_t base = (tid >> 5) * bsz; base < count; base += n_warps * bsz) {
+        const size_t i = base + lane;
+        float lw_abs = 0.f, lh_abs = 0.f, m = 0.f;
+        uint32_t pix32 = 0;
+        int g = 0;
+        bool ok = (unsigned)lane < bsz && i < count;
+        if (ok) {
+            uint32_t e;
+            asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(e) : "l"(far_list + i) : "memory");
+            const int pt = (int)(e & 15u);
+            const size_t pg = e >> 4;
+            g = (int)(pg % q.G);
+            const size_t pix = pg / q.G;                   // pixel (n, ho, wo); < 2^28 (plan())
+            pix32 = (uint32_t)pix;
+            const int wo = (int)(pix % q.Wo), ho = (int)((pix / q.Wo) % q.Ho);
+            const float2 d = load_pair(offset + (pix * q.G + g) * (kP * 2) + 2 * pt);
+            m = to_f32(mask[(pix * q.G + g) * kP + pt]);
+            lw_abs = axis_base(wo, 3, 1, q.pw, 1, q.sigma) + ((float)(pt / 3) + d.x) * q.sigma;
+            lh_abs = axis_base(ho, 3, 1, q.ph, 1, q.sigma) + ((float)(pt % 3) + d.y) * q.sigma;
+            ok = lh_abs > -1.f && lw_abs > -1.f && lh_abs < (float)q.H && lw_abs < (float)q.W;   // (:262-263)
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, ok);
+        while (todo) {
+            const T *gsrc[4];
+            T *gdst[4];
+            float cfs[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int src = todo ? __ffs(todo) - 1 : 0;
+                const bool have = todo != 0u;
+                todo &= todo - 1u;
+                const float bw = __shfl_sync(0xffffffffu, lw_abs, src), bh = __shfl_sync(0xffffffffu, lh_abs, src);
+                const float bm = __shfl_sync(0xffffffffu, m, src);
+                const uint32_t bpix = __shfl_sync(0xffffffffu, pix32, src);
+                const int bg = __shfl_sync(0xffffffffu, g, src);
+                const float fw = floorf(bw), fh = floorf(bh);
+                const float lw = bw - fw, lh = bh - fh;
+                const float cf = ((corner & 2) ? lh : 1.f - lh) * bm * ((corner & 1) ? lw : 1.f - lw);
+                const int hh = (int)fh + (corner >> 1), ww = (int)fw + (corner & 1);
+                const size_t n = bpix / ((size_t)q.Wo * q.Ho);
+                const bool use = have && (unsigned)hh < (unsigned)q.H && (unsigned)ww < (unsigned)q.W && cf != 0.f;
+                cfs[u] = use ? cf : 0.f;
+                gsrc[u] = grad_out + (size_t)bpix * C + bg * kCh + 2 * cp;
+                gdst[u] = use ? grad_value + ((n * q.H + hh) * q.W + ww) * C + bg * kCh + 2 * cp : nullptr;
+            }
+            uint32_t gw[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) gw[u] = gdst[u] ? __ldg(reinterpret_cast<const uint32_t *>(gsrc[u])) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (gdst[u]) {
+                    const float2 gq = unpack2(gw[u], T());
+                    red_add2(gdst[u], pack2(cfs[u] * gq.x, cfs[u] * gq.y, T()));
+                }
         }
     }
 }
