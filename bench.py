@@ -350,6 +350,49 @@ def layer_row(dev, dtype):
 
 # ------------------------------------------------------------------------------- our arm
 # ------------------------------------------------------------------------------- BASELINE configs[2] / [3]
+def cfg5_row(dev, iters=10):
+    """BASELINE configs[4]: the high-resolution sweep -- DCNv3 at 192 x 192 (1536 x 1536 input, stride 8), C = 256,
+    group 8 / 16 / 32, bf16, N = 4 images, forward + backward throughput and the HBM-roofline fraction of
+    the algorithmic bytes s (3V + 2O + 9Q).  Two rotating input sets per group count (each > the 126 MB L2)."""
+    import DCNv3
+    n, h, w, c = 4, 192, 192, 256
+    peak, _ = peaks()
+    rows = {}
+    for G in (8, 16, 32):
+        geo = (3, 3, 1, 1, 1, 1, 1, 1, G, c // G, 1.0)
+        sets = []
+        for i in range(2):
+            g = torch.Generator(device="cpu").manual_seed(50 + G + i)
+            value = torch.randn(n, h, w, c, generator=g)
+            offset = torch.randn(n, h, w, G * 18, generator=g)
+            mask = torch.softmax(torch.randn(n, h, w, G, 9, generator=g), -1).reshape(n, h, w, G * 9)
+            grad = torch.randn(n, h, w, c, generator=g)
+            sets.append(tuple(t.to(torch.bfloat16).to(dev) for t in (value, offset, mask, grad)))
+        for v, o, m, go in sets:
+            DCNv3.dcnv3_forward(v, o, m, *geo, 256); DCNv3.dcnv3_backward(v, o, m, *geo, go, 256)
+        a, b_, c_ = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record()
+        for i in range(iters):
+            v, o, m, go = sets[i % 2]
+            DCNv3.dcnv3_forward(v, o, m, *geo, 256)
+        b_.record()
+        for i in range(iters):
+            v, o, m, go = sets[i % 2]
+            DCNv3.dcnv3_backward(v, o, m, *geo, go, 256)
+        c_.record()
+        torch.cuda.synchronize()
+        f, bw = a.elapsed_time(b_) / iters, b_.elapsed_time(c_) / iters
+        pts = n * h * w * G * 9
+        V = n * h * w * c
+        nbytes = 2 * (3 * V + 2 * V + 9 * pts)
+        rows[f"G{G}"] = {"fwd_ms": f, "bwd_ms": bw, "points": pts, "pts_per_s": pts / ((f + bw) * 1e-3),
+                         "algorithmic_bytes": nbytes, "hbm_frac": nbytes / ((f + bw) * 1e-3) / 1e9 / peak}
+        del sets
+        torch.cuda.empty_cache()
+    return {"what": "BASELINE configs[4]: DCNv3 core fwd+bwd at 192x192 (1536x1536 input), C=256, group 8/16/32, bf16, N=4, "
+                    "CUDA events, %d calls per pass over two rotating input sets" % iters, "rows": rows}
+
+
 def _kernel_split(prof):
     """CUDA time of one profiled window by kernel family (torch.profiler / kineto, rank 0)."""
     fam = {"nccl": 0.0, "dcnv3_sm100": 0.0, "conv_gemm": 0.0, "batchnorm_layernorm": 0.0, "elementwise_act_loss": 0.0,
@@ -673,6 +716,12 @@ def run_ours(args, rank, world, local_rank):
     layer = layer_row(dev, dtype) if rank == 0 else None
     # ---- the reference's own CUDA kernels recompiled for sm_100a (baseline/_ref/DCNv3_refcuda.so, built by
     # scripts/build_reference_cuda.py), timed beside this library on this box: fp16 / fp32, it has no bf16 dispatch
+    cfg5 = None
+    if rank == 0:
+        try:
+            cfg5 = cfg5_row(dev)
+        except Exception as exc:
+            cfg5 = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
     refcuda = None
     if rank == 0 and world == 1 and os.environ.get("BENCH_REF_CUDA", "1") != "0":
         try:
@@ -753,6 +802,8 @@ def run_ours(args, rank, world, local_rank):
             line["precision_modes"] = modes
         if refcuda is not None:
             line["reference_cuda_kernels"] = refcuda
+        if cfg5 is not None:
+            line["cfg5_sweep"] = cfg5
         if train is not None:
             line["train_step"] = train
             line["img_per_s"] = train["img_per_s"]
