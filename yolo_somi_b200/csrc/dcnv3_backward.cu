@@ -510,7 +510,7 @@ static cudaError_t backward_typed(const void *value, const void *offset, const v
             const bool split = !(e && e[0]) || (e[0] == 's' && e[1] == 'p');
             const char *ev = std::getenv("DCNV3_VALUE");
             const bool hmma = ev && ev[0] == 'h';
-            // group_channels == 16, maps up to 156 wide: grad_value with the accumulator resident in tensor memory
+            // group_channels == 16, maps up to 240 wide: grad_value with the accumulator resident in tensor memory
             // (dcnv3_backward_vres.cu) -- written once in the I/O dtype: no fp32 plane, nothing to zero or to narrow.
             // DCNV3_VALUE=mma keeps the plane form (dcnv3_backward_vmma.cu).
             if (split && vec_ok && !(ev && ev[0]) && backward_vres_eligible(offset, mask, grad_out, grad_value, q) &&

@@ -814,7 +814,10 @@ static bool plan(const Geom &q, RParams *pp) {
     if (pp->bx_rel > 0 || pp->by_rel > 0 || (pp->S + 1) * 8 + pp->bx_rel < q.W || (pp->PR + 1) * 8 + pp->by_rel < q.H) return false;
     pp->nbxp = (pp->S + 2) & ~1;                        // S + 1 blocks per block row, padded to a whole tile
     pp->ring = std::min(kMaxRing, 64 / pp->nbxp);
-    if (pp->ring < 3) return false;                     // two rows in work + one leaving
+    // (three rows: two in work + one leaving.  With two -- maps 157 .. 240 px wide -- the first product of a patch row waits
+    // until the block row above the previous one has been drained; the builders run ahead into their slots meanwhile)
+    static const int min_ring = [] { const char *e = std::getenv("DCNV3_VRES_MINRING"); return e ? atoi(e) : 2; }();
+    if (pp->ring < min_ring) return false;
     if ((long long)q.N * q.Ho * q.Wo * q.G >= (1LL << 28)) return false;   // a far-list entry = (pixel, group) << 4 | point
     const long long rows = (long long)q.N * q.G * pp->PR;
     if (rows >= (1LL << 30)) return false;
