@@ -26,6 +26,15 @@ SRC = REF / "models" / "ops_dcnv3" / "src"
 OUT = REF / "DCNv3_refcuda.so"
 
 
+def patch_dispatch(text: str) -> str:
+    """The whole patch: `input.type()` -> `input.scalar_type()` as the first argument of the two AT_DISPATCH calls."""
+    patched = text.replace("input.type(), \"ms_deform_attn_forward_cuda\"", "input.scalar_type(), \"ms_deform_attn_forward_cuda\"")
+    patched = patched.replace("input.type(), \"ms_deform_attn_backward_cuda\"", "input.scalar_type(), \"ms_deform_attn_backward_cuda\"")
+    if patched.count("input.scalar_type(), ") != 2:
+        raise RuntimeError("expected exactly two AT_DISPATCH sites to patch in dcnv3_cuda.cu")
+    return patched
+
+
 def build(verbose: bool = False) -> Path:
     if not SRC.is_dir():
         raise FileNotFoundError(f"{SRC}: run scripts/stage_reference.py first")
@@ -38,12 +47,7 @@ def build(verbose: bool = False) -> Path:
         shutil.copytree(SRC, src)
         cu = src / "cuda" / "dcnv3_cuda.cu"
         text = cu.read_text()
-        patched = text.replace("input.type(), \"ms_deform_attn_forward_cuda\"", "input.scalar_type(), \"ms_deform_attn_forward_cuda\"")
-        patched = patched.replace("input.type(), \"ms_deform_attn_backward_cuda\"", "input.scalar_type(), \"ms_deform_attn_backward_cuda\"")
-        if patched == text:      # the dispatch name sits on the line after `input.type(),` in some revisions
-            patched = text.replace("            input.type(), ", "            input.scalar_type(), ")
-        if patched.count("input.scalar_type(), ") != 2:
-            raise RuntimeError("expected exactly two AT_DISPATCH sites to patch in dcnv3_cuda.cu")
+        patched = patch_dispatch(text)
         cu.write_text(patched)
         sources = [str(src / "vision.cpp"), str(src / "cpu" / "dcnv3_cpu.cpp"), str(cu)]
         bdir = work / "build"

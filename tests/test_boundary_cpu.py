@@ -55,6 +55,13 @@ def test_error_codes_without_touching_a_gpu(lib):
     assert ws(2, 8, 8, 2, 4, 0, 1) == 256 + plane * 8
     rc = lib.dcnv3_backward_sm100(16, 16, 16, 16, 16, 16, 16, 16, 8, *geom_ok, 1.0, 2, 0, None)
     assert rc == -4                                                     # DCNV3_E_WORKSPACE
+    # fp64 (DCNV3_F64 = 3, the dtype the reference's own test script starts with): a known dtype, no workspace,
+    # 16-byte (dx, dy) pairs, and no deterministic mode
+    assert _native.F64 == 3 and call((None,) * 4, geom_ok, 3) == -3     # DCNV3_E_NULL, not DCNV3_E_DTYPE
+    assert call((16, 8, 16, 16), geom_ok, 3) == -6                      # offset not aligned to a double pair
+    assert ws(2, 8, 8, 2, 4, 3, 0) == 0
+    rc = lib.dcnv3_backward_sm100(16, 16, 16, 16, 16, 16, 16, None, 0, *geom_ok, 1.0, 3, 1, None)
+    assert rc == -1 and "fp64" in _native.strerror(-1)                  # DETERMINISTIC | fp64
 
 
 def test_shim_rejects_what_the_reference_rejects():

@@ -192,3 +192,21 @@ def test_reference_test_script_passes_unmodified_over_the_shim():
     assert len(lines) == 2 + 2 * 7 * 3, out
     assert all(ln.startswith("* True") for ln in lines), "\n".join(ln for ln in lines if not ln.startswith("* True"))
     assert out.count("foward time cost") == 3, out
+
+
+@needs_ref
+def test_reference_cuda_comparator_patch_is_two_tokens():
+    """scripts/build_reference_cuda.py compiles the reference's extension with exactly two tokens changed: the first
+    argument of its two AT_DISPATCH calls (dcnv3_cuda.cu:70,148).  Checked on the staged source, no compiler needed."""
+    import difflib
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("build_reference_cuda", ref_loader.ROOT / "scripts" / "build_reference_cuda.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    src = (ref_loader.REF / "models" / "ops_dcnv3" / "src" / "cuda" / "dcnv3_cuda.cu").read_text()
+    out = mod.patch_dispatch(src)
+    changed = [ln for ln in difflib.unified_diff(src.splitlines(), out.splitlines(), lineterm="", n=0)
+               if ln[:1] in "+-" and ln[:3] not in ("+++", "---")]
+    assert len(changed) == 4, changed
+    for minus, plus in zip(changed[0::2], changed[1::2]):
+        assert minus[1:].replace("input.type()", "input.scalar_type()") == plus[1:]
