@@ -735,7 +735,8 @@ far_points(const uint32_t *far_list, const unsigned long long *far_count, unsign
     // dependent loads that mostly miss L2 -- are fetched for 32 points at once.  Phase 2, lane <-> (corner, channel pair):
     // the points' locations are broadcast by shuffles, four points at a time (their grad_out loads are issued together,
     // then their reductions).  (One warp per point, its loads one after the other: 125 us for the ~330 k far points of
-    // N(0, 2)-pixel offsets at cfg2; this form ~25 us: backward 491 -> 368 us there, 440 -> 324 us for U(-4, 4).)
+    // N(0, 2)-pixel offsets at cfg2; this form 50 us (ncu): backward 491 -> 366 us there, 440 -> 322 us for U(-4, 4).  Issuing ALL grad_out loads of a batch
+    // before its reductions instead of four at a time: 106 registers, no gain there and +3 us on the usual short list.)
     const int lane = threadIdx.x & 31, corner = lane >> 3, cp = lane & 7;
     const int C = q.G * q.gc;
     const size_t n_warps = ((size_t)gridDim.x * 256) >> 5;
