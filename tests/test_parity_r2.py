@@ -277,3 +277,48 @@ def test_mask_softmax_backward_kernel(dt, rows):
                                                    _native.BF16 if dt == "bf16" else _native.F16,
                                                    torch.cuda.current_stream().cuda_stream)
         assert rc == 0 and torch.equal(out2[:rows].view(torch.int16), out.view(torch.int16))
+
+
+# ----------------------------------------------------------------------------- the far-point list, mid range
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,spread,dt", [((2, 80, 80, 8), 1.8, torch.bfloat16), ((8, 80, 80, 16), 2.0, torch.bfloat16),
+                                              ((4, 64, 96, 8), 2.0, torch.float16)],
+                         ids=["14k-far-bf16", "170k-far-bf16", "50k-far-f16"])
+def test_far_point_list_between_a_few_and_the_fallback_threshold(shape, spread, dt):
+    """Offsets a couple of pixels wide put 1 - 3 % of the points beyond their patch's band: below the 1 / 32 at which the
+    plane form takes over, far above the few thousand of N(0, 1) offsets -- `far_points` then handles several entries per
+    warp and per batch (its lane <-> entry phase), which no other test reaches.  Against the C oracle in fp64 on the
+    rounded inputs, the bars of the other 16-bit tests."""
+    from oracle import dcnv3_oracle as orc
+    from helpers import allclose_frac, max_abs
+    n, h, w, G = shape
+    gen = torch.Generator(device="cpu").manual_seed(31 + n)
+    value = torch.randn(n, h, w, G * 16, generator=gen)
+    offset = spread * torch.randn(n, h, w, G * 18, generator=gen)
+    mask = torch.softmax(torch.randn(n, h, w, G, 9, generator=gen), -1).reshape(n, h, w, G * 9)
+    grad = torch.randn(n, h, w, G * 16, generator=gen)
+    geom = (3, 3, 1, 1, 1, 1, 1, 1, G, 16, 1.0)
+    dev = [t.to(dt).cuda() for t in (value, offset, mask, grad)]
+    arrs = [t.double().cpu().numpy() for t in dev]
+    # the share of points beyond the band (dcnv3_backward_vres.cu: 0 <= px + i + 3 + dx < 15 on both axes) must sit in the
+    # range this test is about
+    o = arrs[1].reshape(n, h, w, G, 9, 2)
+    px = (np.arange(w) % 8)[None, None, :, None, None]
+    py = (np.arange(h) % 8)[None, :, None, None, None]
+    pi = (np.arange(9) // 3)[None, None, None, None, :]
+    pj = (np.arange(9) % 3)[None, None, None, None, :]
+    ub, vb = px + pi + 3 + o[..., 0], py + pj + 3 + o[..., 1]
+    far = 1.0 - np.mean((ub >= 0) & (ub < 15) & (vb >= 0) & (vb < 15))
+    assert 5e-3 < far < 1.0 / 32, far
+    import DCNv3
+    got = list(DCNv3.dcnv3_backward(*dev[:3], *geom, dev[3], 256))
+    torch.cuda.synchronize()
+    want = orc.direct_backward(*arrs, *geom)
+    for name, a, wnt in zip(("gv", "go", "gm"), got, want):
+        a = a.double().cpu().numpy()
+        rms = float(np.sqrt(np.mean(wnt ** 2)))
+        frac = allclose_frac(a, wnt, rtol=1e-2, atol=1e-2 * rms)
+        assert frac <= (5e-4 if name == "go" else 2e-4), (name, frac, max_abs(a, wnt), rms)
+        if name != "go":
+            worst = float(np.max(np.abs(a - wnt) / np.maximum(np.abs(wnt), rms)))
+            assert worst <= (8e-2 if dt == torch.bfloat16 else 2e-2), (name, worst)
