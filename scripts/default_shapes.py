@@ -37,6 +37,9 @@ run("5x5 kernel", 16, 80, 80, 16, 16, k=5)
 run("dilation 2", 16, 80, 80, 16, 16, d=2)
 run("fp32 I/O", 16, 80, 80, 16, 16, dtype=torch.float32)
 run("fp16 I/O", 16, 80, 80, 16, 16, dtype=torch.float16)
+run("fp64 I/O (correctness path)", 4, 80, 80, 16, 16, dtype=torch.float64, iters=5)
+run("map 240 px wide (ring of two)", 2, 64, 240, 16, 16)
+run("map 248 px wide (plane form)", 2, 64, 248, 16, 16)
 run("cfg1 (reference CPU case) fp32", 2, 32, 32, 4, 16, dtype=torch.float32)
 for G in (8, 16, 32):
     run("cfg5 192x192 G=%d" % G, 1, 192, 192, G, 256 // G)

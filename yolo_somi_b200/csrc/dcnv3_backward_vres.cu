@@ -822,6 +822,10 @@ static bool plan(const Geom &q, RParams *pp) {
     if ((long long)q.N * q.Ho * q.Wo * q.G >= (1LL << 28)) return false;   // a far-list entry = (pixel, group) << 4 | point
     const long long rows = (long long)q.N * q.G * pp->PR;
     if (rows >= (1LL << 30)) return false;
+    // With a ring of two the pipeline stalls once per patch row, and a CTA's first row is built twice: worth it only for
+    // runs of several patch rows per CTA (192 x 192, G = 16: N = 4 -> 10.7 rows per CTA, 377 -> 361 us; N = 1 -> 2.7 rows,
+    // 109 -> 122 us, so a single image stays on the plane form)
+    if (pp->ring == 2 && rows < 6 * 148) return false;
     pp->total_rows = (int)rows;
     return true;
 }
