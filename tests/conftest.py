@@ -10,6 +10,12 @@ for p in (ROOT, ROOT / "tests", ROOT / "tests" / "golden"):
         sys.path.insert(0, str(p))
 
 
+# The parity tests keep exercising the resident-accumulator value kernel on their small shapes: in production a size
+# heuristic (csrc/dcnv3_backward_vres.cu: backward_vres_preferred) sends short runs to the plane form, which is faster there.
+# tests/test_parity_r2.py::test_small_shapes_take_the_plane_form_by_default covers the default dispatch.
+os.environ.setdefault("DCNV3_VRES_MIN_ROWS", "0")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
 

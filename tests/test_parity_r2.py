@@ -322,3 +322,33 @@ def test_far_point_list_between_a_few_and_the_fallback_threshold(shape, spread, 
         if name != "go":
             worst = float(np.max(np.abs(a - wnt) / np.maximum(np.abs(wnt), rms)))
             assert worst <= (8e-2 if dt == torch.bfloat16 else 2e-2), (name, worst)
+
+
+@pytest.mark.gpu
+def test_small_shapes_take_the_plane_form_by_default():
+    """The size heuristic of the default dispatch (backward_vres_preferred: >= 8 patch rows per SM, >= 4 patches per row)
+    in a FRESH process without the test suite's DCNV3_VRES_MIN_ROWS=0: a small shape and a large one, both against the
+    C oracle -- whichever form runs, the result is the same function."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent('''
+        import sys, numpy as np, torch
+        sys.path[:0] = [%r, %r]
+        import DCNv3
+        from oracle import dcnv3_oracle as orc
+        for n, h, w, G in ((2, 40, 40, 8), (12, 80, 80, 16)):
+            g = torch.Generator().manual_seed(5)
+            v = torch.randn(n, h, w, G * 16, generator=g); o = torch.randn(n, h, w, G * 18, generator=g)
+            m = torch.softmax(torch.randn(n, h, w, G, 9, generator=g), -1).reshape(n, h, w, -1); go = torch.randn(n, h, w, G * 16, generator=g)
+            dev = [t.bfloat16().cuda() for t in (v, o, m, go)]
+            geom = (3, 3, 1, 1, 1, 1, 1, 1, G, 16, 1.0)
+            got = DCNv3.dcnv3_backward(*dev[:3], *geom, dev[3], 256)
+            arrs = [t.double().cpu().numpy() for t in dev]
+            want = orc.direct_backward(*arrs, *geom)
+            for a, wnt in zip(got, want):
+                a = a.double().cpu().numpy(); rms = float(np.sqrt(np.mean(wnt ** 2)))
+                assert np.mean(np.abs(a - wnt) > 1e-2 * np.abs(wnt) + 1e-2 * rms) <= 5e-4
+        print("ok")
+    ''') % (str(cases.__file__).rsplit("/tests/", 1)[0], str(cases.__file__).rsplit("/golden/", 1)[0])
+    env = {k: v for k, v in __import__("os").environ.items() if k != "DCNV3_VRES_MIN_ROWS"}
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]

@@ -513,7 +513,7 @@ static cudaError_t backward_typed(const void *value, const void *offset, const v
             // group_channels == 16, maps up to 240 wide: grad_value with the accumulator resident in tensor memory
             // (dcnv3_backward_vres.cu) -- written once in the I/O dtype: no fp32 plane, nothing to zero or to narrow.
             // DCNV3_VALUE=mma keeps the plane form (dcnv3_backward_vmma.cu).
-            if (split && vec_ok && !(ev && ev[0]) && backward_vres_eligible(offset, mask, grad_out, grad_value, q) &&
+            if (split && vec_ok && !(ev && ev[0]) && backward_vres_preferred(q) && backward_vres_eligible(offset, mask, grad_out, grad_value, q) &&
                 backward_vmma_eligible(offset, mask, grad_out, acc, q)) {
                 cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
                 // (the channel-sum kernel zeroes the scratch header: the far-point counter lives there)

@@ -822,10 +822,7 @@ static bool plan(const Geom &q, RParams *pp) {
     if ((long long)q.N * q.Ho * q.Wo * q.G >= (1LL << 28)) return false;   // a far-list entry = (pixel, group) << 4 | point
     const long long rows = (long long)q.N * q.G * pp->PR;
     if (rows >= (1LL << 30)) return false;
-    // With a ring of two the pipeline stalls once per patch row, and a CTA's first row is built twice: worth it only for
-    // runs of several patch rows per CTA (192 x 192, G = 16: N = 4 -> 10.7 rows per CTA, 377 -> 361 us; N = 1 -> 2.7 rows,
-    // 109 -> 122 us, so a single image stays on the plane form)
-    if (pp->ring == 2 && rows < 6 * 148) return false;
+
     pp->total_rows = (int)rows;
     return true;
 }
@@ -896,6 +893,24 @@ bool backward_vres_eligible(const void *offset, const void *mask, const void *gr
     vres::RParams pp;
     if (((uintptr_t)grad_out | (uintptr_t)grad_value | (uintptr_t)offset | (uintptr_t)mask) % 16) return false;
     return vres::plan(q, &pp);
+}
+
+// Is the resident-accumulator kernel the FASTER choice for this shape?  (plan() says whether it is possible.)  A CTA builds
+// the patch row above its run a second time and every patch row ends with a drain, so short runs and short rows lose to
+// the plane form (scripts/vres_vs_plane.py, backward in us, this kernel / plane form): 80 x 80, G = 16: N = 1 51 / 44, N = 4
+// 86 / 79, N = 6 112 / 110, N = 8 138 / 141, N = 16 249 / 264; 40 x 40: N = 16 78 / 78, N = 64 246 / 261; 20 x 20, G = 32 (three
+// patches per row): N = 16 60 / 52, N = 128 356 / 322; 192 x 192 (ring of two): N = 1 122 / 109, N = 4 361 / 377.
+// Hence: at least four patches per row and at least `min_rows_per_sm` (8; DCNV3_VRES_MIN_ROWS, 0 = always) patch rows per SM.
+bool backward_vres_preferred(const Geom &q) {
+    static const int min_rows_per_sm = [] { const char *e = std::getenv("DCNV3_VRES_MIN_ROWS"); return e ? atoi(e) : 8; }();
+    if (min_rows_per_sm <= 0) return true;
+    static const int num_sms = [] {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        return n;
+    }();
+    const long long rows = (long long)q.N * q.G * ((q.Ho + 7) / 8);
+    return (q.Wo + 7) / 8 >= 4 && rows >= (long long)min_rows_per_sm * num_sms;
 }
 
 size_t backward_vres_scratch_bytes(const Geom &q) {

@@ -74,6 +74,8 @@ bool try_launch_backward_vmma(const void *offset, const void *mask, const void *
 // `scratch`: backward_vres_scratch_bytes(q) bytes (one 16-bit far-point mask per pixel and group)
 bool backward_vres_eligible(const void *offset, const void *mask, const void *grad_out, const void *grad_value, const Geom &q);
 size_t backward_vres_scratch_bytes(const Geom &q);
+// the size heuristic: is it also the faster form for this shape (enough patch rows per SM, rows of at least four patches)
+bool backward_vres_preferred(const Geom &q);
 // `counter`: 64-bit far-point count, zeroed by the caller's previous kernel; `*thr`: the count above which the result is
 // NOT final (too many far points for the 16-bit atomics: the caller then runs the plane form, conditionally, on top)
 bool try_launch_backward_vres(const void *offset, const void *mask, const void *grad_out, void *grad_value, void *scratch,
